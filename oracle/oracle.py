@@ -1,0 +1,368 @@
+"""CPU oracle for the D-LKA hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product package
+(``deformablelka_b200``) never does.
+
+The oracle restates, on CPU, what the reference computes on the hot path:
+
+* stock layers (``nn.Conv2d/Conv3d``, ``nn.GELU``) are the very PyTorch CPU ops the
+  reference calls (2D/deformable_LKA/deformable_LKA.py:10-16,95,128-131;
+  3D/d_lka_former/network_architecture/synapse/transformerblock.py:637-641,659-662);
+* the 3D deformable convolution (CUDA-only in the reference: 3D/dcn/src/deform_conv.h:46)
+  is restated in C (``dlka_oracle.c``: im2col per deform_im2col_cuda.cuh:192-265,
+  sampler per :26-72) followed by ``torch.addmm`` exactly as deform_conv_cuda.cu:113-123;
+* the 2D deformable convolution is ``torchvision.ops.deform_conv2d`` on CPU (the
+  reference's own third-party dependency, 2D/deformable_LKA/deformable_LKA.py:18-25)
+  with a C restatement beside it that the tests pin against torchvision.
+
+Module classes below keep the reference's attribute names so state_dicts are
+interchangeable with the reference modules and with ``deformablelka_b200``.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libdlka_oracle.so")
+_SRC = os.path.join(_HERE, "dlka_oracle.c")
+
+
+def build(force: bool = False) -> str:
+    """Compile dlka_oracle.c with gcc (OpenMP) into oracle/libdlka_oracle.so."""
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        cmd = ["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-shared", "-fPIC", "-o", _SO, _SRC, "-lm"]
+        subprocess.check_call(cmd)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = ctypes.CDLL(_SO)
+    return _lib
+
+
+def _fp(t: Optional[torch.Tensor]):
+    if t is None:
+        return ctypes.c_void_p(0)
+    assert t.dtype == torch.float32 and t.is_contiguous() and t.device.type == "cpu"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _ip(t: torch.Tensor):
+    assert t.dtype == torch.int32 and t.is_contiguous()
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _triple(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v, v)
+
+
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+def out_extent(n, pad, dil, k, stride):
+    return (n + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+
+
+# --------------------------------------------------------------------------------------
+# 3D deformable convolution (D3D.deform_conv_forward restated)
+# --------------------------------------------------------------------------------------
+def deform_conv3d(input: torch.Tensor, offset: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
+                  stride=1, padding=0, dilation=1, groups: int = 1, deformable_groups: int = 1,
+                  im2col_step: int = 64, chunk: int = 32768) -> torch.Tensor:
+    """Follows deform_conv_cuda_forward (3D/dcn/src/cuda/deform_conv_cuda.cu:18-126).
+
+    ``im2col_step`` only changes how the reference batches its im2col buffer; the result does
+    not depend on it, but the reference's divisibility assert (cu:61-63) is kept.
+    """
+    input = input.contiguous().float()
+    offset = offset.contiguous().float()
+    weight = weight.contiguous().float()
+    B, C, D, H, W = input.shape
+    Co, Cg, kd, kh, kw = weight.shape
+    sd, sh, sw = _triple(stride)
+    pd, ph, pw = _triple(padding)
+    dd, dh, dw = _triple(dilation)
+    if C != Cg * groups:
+        raise RuntimeError(f"Input shape and kernel channels wont match: ({C} vs {Cg * groups}).")
+    if C % groups or Co % groups:
+        raise RuntimeError("channels and channels_out must divide group")
+    step = min(B, im2col_step)
+    if B % step:
+        raise RuntimeError(f"batch({B}) must divide im2col_step({step})")
+    K = kd * kh * kw
+    Do, Ho, Wo = out_extent(D, pd, dd, kd, sd), out_extent(H, ph, dh, kh, sh), out_extent(W, pw, dw, kw, sw)
+    if tuple(offset.shape) != (B, deformable_groups * 3 * K, Do, Ho, Wo):
+        raise RuntimeError(f"offset shape {tuple(offset.shape)} != {(B, deformable_groups * 3 * K, Do, Ho, Wo)}")
+    Vo = Do * Ho * Wo
+    out = torch.empty(B, Co, Vo, dtype=torch.float32)
+    w_g = weight.view(groups, Co // groups, Cg * K)
+    b_g = bias.float().view(groups, Co // groups)
+    L = lib()
+    for b in range(B):
+        for v0 in range(0, Vo, chunk):
+            v1 = min(Vo, v0 + chunk)
+            cols = torch.empty(C * K, v1 - v0, dtype=torch.float32)
+            L.oracle_deform_im2col3d(_fp(input), _fp(offset), _fp(cols), B, C, D, H, W, kd, kh, kw,
+                                     sd, sh, sw, pd, ph, pw, dd, dh, dw, deformable_groups, b,
+                                     ctypes.c_int64(v0), ctypes.c_int64(v1))
+            cols_g = cols.view(groups, Cg * K, v1 - v0)
+            for g in range(groups):
+                # at::addmm(bias_g, columns_g^T, weight_g^T)   (cu:113-119)
+                o = torch.addmm(b_g[g], cols_g[g].t(), w_g[g].t())  # [n, Co/g]
+                out[b, g * (Co // groups):(g + 1) * (Co // groups), v0:v1] = o.t()
+    return out.view(B, Co, Do, Ho, Wo)
+
+
+def deform_conv3d_c(input, offset, weight, bias, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1):
+    """All-C variant (naive GEMM) -- small shapes only; cross-checks the addmm variant."""
+    input = input.contiguous().float(); offset = offset.contiguous().float(); weight = weight.contiguous().float()
+    B, C, D, H, W = input.shape
+    Co, Cg, kd, kh, kw = weight.shape
+    sd, sh, sw = _triple(stride); pd, ph, pw = _triple(padding); dd, dh, dw = _triple(dilation)
+    Do, Ho, Wo = out_extent(D, pd, dd, kd, sd), out_extent(H, ph, dh, kh, sh), out_extent(W, pw, dw, kw, sw)
+    out = torch.empty(B, Co, Do, Ho, Wo, dtype=torch.float32)
+    lib().oracle_deform_conv3d_forward(_fp(input), _fp(offset), _fp(weight), _fp(bias.contiguous().float()), _fp(out),
+                                       B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw, dd, dh, dw,
+                                       groups, deformable_groups)
+    return out
+
+
+def sample_indices3d(offset, in_size, kernel_size, stride=1, padding=0, dilation=1, deformable_groups=1):
+    """Integer planes of the sampler (floor per axis + validity / corner mask), for bit-exact parity."""
+    offset = offset.contiguous().float()
+    D, H, W = in_size
+    kd, kh, kw = _triple(kernel_size)
+    sd, sh, sw = _triple(stride); pd, ph, pw = _triple(padding); dd, dh, dw = _triple(dilation)
+    B = offset.shape[0]
+    K = kd * kh * kw
+    Vo = offset.shape[2] * offset.shape[3] * offset.shape[4]
+    low = torch.empty(B * deformable_groups, Vo, K, 3, dtype=torch.int32)
+    mask = torch.empty(B * deformable_groups, Vo, K, dtype=torch.int32)
+    lib().oracle_sample_indices3d(_fp(offset), _ip(low), _ip(mask), B, D, H, W, kd, kh, kw, sd, sh, sw,
+                                  pd, ph, pw, dd, dh, dw, deformable_groups)
+    return low, mask
+
+
+# --------------------------------------------------------------------------------------
+# 2D deformable convolution
+# --------------------------------------------------------------------------------------
+def deform_conv2d_c(input, offset, weight, bias=None, stride=1, padding=0, dilation=1, mask=None):
+    """C restatement of torchvision.ops.deform_conv2d (same argument meaning)."""
+    input = input.contiguous().float(); offset = offset.contiguous().float(); weight = weight.contiguous().float()
+    B, C, H, W = input.shape
+    Co, Cg, kh, kw = weight.shape
+    sh, sw = _pair(stride); ph, pw = _pair(padding); dh, dw = _pair(dilation)
+    n_off = offset.shape[1] // (2 * kh * kw)
+    n_wg = C // Cg
+    Ho, Wo = out_extent(H, ph, dh, kh, sh), out_extent(W, pw, dw, kw, sw)
+    out = torch.empty(B, Co, Ho, Wo, dtype=torch.float32)
+    lib().oracle_deform_conv2d_forward(_fp(input), _fp(offset), _fp(None if mask is None else mask.contiguous().float()),
+                                       _fp(weight), _fp(None if bias is None else bias.contiguous().float()), _fp(out),
+                                       B, C, H, W, Co, kh, kw, sh, sw, ph, pw, dh, dw, n_wg, n_off)
+    return out
+
+
+def deform_conv2d(input, offset, weight, bias=None, stride=1, padding=0, dilation=1, mask=None):
+    """The reference's own dependency on CPU: torchvision.ops.deform_conv2d."""
+    import torchvision
+    return torchvision.ops.deform_conv2d(input, offset, weight, bias, _pair(stride), _pair(padding), _pair(dilation), mask)
+
+
+def sample_indices2d(offset, in_size, kernel_size, stride=1, padding=0, dilation=1, n_offset_grps=1):
+    offset = offset.contiguous().float()
+    H, W = in_size
+    kh, kw = _pair(kernel_size)
+    sh, sw = _pair(stride); ph, pw = _pair(padding); dh, dw = _pair(dilation)
+    B = offset.shape[0]
+    K = kh * kw
+    P = offset.shape[2] * offset.shape[3]
+    low = torch.empty(B * n_offset_grps, P, K, 2, dtype=torch.int32)
+    mask = torch.empty(B * n_offset_grps, P, K, dtype=torch.int32)
+    lib().oracle_sample_indices2d(_fp(offset), _ip(low), _ip(mask), B, H, W, kh, kw, sh, sw, ph, pw, dh, dw, n_offset_grps)
+    return low, mask
+
+
+# --------------------------------------------------------------------------------------
+# Module restatements (same attribute names / state_dict keys as the reference)
+# --------------------------------------------------------------------------------------
+class _DeformConv2dParams(nn.Module):
+    """Holds ``weight`` like torchvision.ops.DeformConv2d(bias=False) (deformable_LKA.py:18-25)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, padding, groups, stride, dilation):
+        super().__init__()
+        self.kernel_size = _pair(kernel_size); self.padding = _pair(padding)
+        self.stride = _pair(stride); self.dilation = _pair(dilation); self.groups = groups
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, *self.kernel_size))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        self.register_parameter("bias", None)
+
+
+class DeformConv2D(nn.Module):
+    """Restates ``DeformConv`` (2D/deformable_LKA/deformable_LKA.py:5-30)."""
+
+    def __init__(self, in_channels, groups, kernel_size=(3, 3), padding=1, stride=1, dilation=1, bias=True, impl="torchvision"):
+        super().__init__()
+        self.offset_net = nn.Conv2d(in_channels, 2 * kernel_size[0] * kernel_size[1], kernel_size=kernel_size,
+                                    padding=padding, stride=stride, dilation=dilation, bias=True)
+        self.deform_conv = _DeformConv2dParams(in_channels, in_channels, kernel_size, padding, groups, stride, dilation)
+        self.impl = impl
+
+    def forward(self, x):
+        offsets = self.offset_net(x)
+        dc = self.deform_conv
+        fn = deform_conv2d if self.impl == "torchvision" else deform_conv2d_c
+        return fn(x, offsets, dc.weight, None, dc.stride, dc.padding, dc.dilation, None)
+
+
+class deformable_LKA(nn.Module):
+    """Restates deformable_LKA (2D/deformable_LKA/deformable_LKA.py:90-104)."""
+
+    def __init__(self, dim, impl="torchvision"):
+        super().__init__()
+        self.conv0 = DeformConv2D(dim, kernel_size=(5, 5), padding=2, groups=dim, impl=impl)
+        self.conv_spatial = DeformConv2D(dim, kernel_size=(7, 7), stride=1, padding=9, groups=dim, dilation=3, impl=impl)
+        self.conv1 = nn.Conv2d(dim, dim, 1)
+
+    def forward(self, x):
+        u = x.clone()
+        attn = self.conv0(x)
+        attn = self.conv_spatial(attn)
+        attn = self.conv1(attn)
+        return u * attn
+
+
+class deformable_LKA_Attention(nn.Module):
+    """Restates deformable_LKA_Attention (2D/deformable_LKA/deformable_LKA.py:124-140)."""
+
+    def __init__(self, d_model, impl="torchvision"):
+        super().__init__()
+        self.proj_1 = nn.Conv2d(d_model, d_model, 1)
+        self.activation = nn.GELU()
+        self.spatial_gating_unit = deformable_LKA(d_model, impl=impl)
+        self.proj_2 = nn.Conv2d(d_model, d_model, 1)
+
+    def forward(self, x):
+        shortcut = x.clone()
+        x = self.proj_1(x)
+        x = self.activation(x)
+        x = self.spatial_gating_unit(x)
+        x = self.proj_2(x)
+        return x + shortcut
+
+
+class DeformConv3D(nn.Module):
+    """Restates DeformConv (3D/dcn/modules/deform_conv.py:15-63)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation=1, groups=1,
+                 deformable_groups=1, im2col_step=64, bias=True):
+        super().__init__()
+        if in_channels % groups != 0:
+            raise ValueError('in_channels {} must be divisible by groups {}'.format(in_channels, groups))
+        if out_channels % groups != 0:
+            raise ValueError('out_channels {} must be divisible by groups {}'.format(out_channels, groups))
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride = _triple(kernel_size), _triple(stride)
+        self.padding, self.dilation = _triple(padding), _triple(dilation)
+        self.groups, self.deformable_groups, self.im2col_step = groups, deformable_groups, im2col_step
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, *self.kernel_size))
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        fan_in, _ = nn.init._calculate_fan_in_and_fan_out(self.weight)
+        bound = 1 / math.sqrt(fan_in)
+        nn.init.uniform_(self.bias, -bound, bound)
+        if not bias:
+            self.bias.requires_grad = False
+
+    def forward(self, input, offset):
+        K = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+        assert 3 * self.deformable_groups * K == offset.shape[1]
+        return deform_conv3d(input, offset, self.weight, self.bias, self.stride, self.padding, self.dilation,
+                             self.groups, self.deformable_groups, self.im2col_step)
+
+
+class DeformConvPack3D(DeformConv3D):
+    """Restates DeformConvPack (synapse/deform_conv.py:67-105): conv_offset ignores dilation, zero-init."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation=1, groups=1,
+                 deformable_groups=1, im2col_step=64, bias=True, lr_mult=0.1):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups,
+                         deformable_groups, im2col_step, bias)
+        oc = self.deformable_groups * 3 * self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+        self.conv_offset = nn.Conv3d(self.in_channels, oc, kernel_size=self.kernel_size, stride=self.stride,
+                                     padding=self.padding, bias=True)
+        self.conv_offset.weight.data.zero_()
+        self.conv_offset.bias.data.zero_()
+
+    def forward(self, input):
+        offset = self.conv_offset(input)
+        return deform_conv3d(input, offset, self.weight, self.bias, self.stride, self.padding, self.dilation,
+                             self.groups, self.deformable_groups, self.im2col_step)
+
+
+class LKA3d_deform(nn.Module):
+    """Restates LKA3d_deform (synapse/transformerblock.py:634-652)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.conv0 = nn.Conv3d(dim, dim, 5, padding=2, groups=dim)
+        self.conv_spatial = nn.Conv3d(dim, dim, 7, stride=1, padding=9, groups=dim, dilation=3)
+        self.deform_conv = DeformConvPack3D(in_channels=dim, out_channels=dim, kernel_size=(3, 3, 3), stride=1, padding=1)
+        self.conv1 = nn.Conv3d(dim, dim, 1)
+
+    def forward(self, x):
+        u = x.clone()
+        attn = self.conv0(x)
+        attn = self.conv_spatial(attn)
+        attn = attn.contiguous()
+        attn = self.deform_conv(attn)
+        attn = self.conv1(attn)
+        return u * attn
+
+
+class LKA_Attention3d_deform(nn.Module):
+    """Restates LKA_Attention3d_deform (synapse/transformerblock.py:655-673)."""
+
+    def __init__(self, d_model):
+        super().__init__()
+        self.proj_1 = nn.Conv3d(d_model, d_model, 1)
+        self.activation = nn.GELU()
+        self.spatial_gating_unit = LKA3d_deform(d_model)
+        self.proj_2 = nn.Conv3d(d_model, d_model, 1)
+
+    def forward(self, x, B, C, H, W, D):
+        x = x.permute(0, 2, 1).reshape(B, C, H, W, D)
+        shortcut = x.clone()
+        x = self.proj_1(x)
+        x = self.activation(x)
+        x = self.spatial_gating_unit(x)
+        x = self.proj_2(x)
+        x = x + shortcut
+        return x.reshape(B, C, H * W * D).permute(0, 2, 1)
+
+
+def randomize_offsets_(module: nn.Module, std: float = 0.05, bias_range: float = 1.0, seed: int = 0) -> None:
+    """re-initialise the zero-initialised 3D ``conv_offset`` so offsets are non-trivial."""
+    g = torch.Generator().manual_seed(seed)
+    for m in module.modules():
+        if hasattr(m, "conv_offset"):
+            with torch.no_grad():
+                m.conv_offset.weight.copy_(torch.randn(m.conv_offset.weight.shape, generator=g) * std)
+                m.conv_offset.bias.copy_((torch.rand(m.conv_offset.bias.shape, generator=g) * 2 - 1) * bias_range)
