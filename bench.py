@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: 3D D-LKA block forward at (B,C,D,H,W) = (2,96,64,128,128).
+
+    python bench.py --gpus N --steps K --warmup W            (ours; under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (reference arm: CPU oracle)
+
+A "step" is one forward of ``LKA_Attention3d_deform`` (proj_1 -> GELU -> dw5^3 -> dw7^3 dil3 ->
+conv_offset -> deformable 3^3 conv -> conv1 -> gate -> proj_2 -> +shortcut) over one batch of synthetic
+tokens [2, 64*128*128, 96].  Metric: GVoxel/s with voxels = B*D*H*W per step.
+Multi-GPU: every rank runs the same per-rank batch (weak scaling, no data-path collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "3D D-LKA block fwd GVoxel/s @ (2,96,64,128,128)"
+SHAPE = dict(B=2, C=96, D1=64, D2=128, D3=128)
+# algorithmic work per voxel at C=96 (SURVEY.md 8d / DESIGN.md): compulsory HBM bytes and tensor-pipe FLOPs
+HBM_BYTES_PER_VOXEL = 2 * 96 * 4
+CONTRACTION_FLOP_PER_VOXEL = 2 * 27 * 96 * 81 + 2 * 27 * 96 * 96 + 3 * 2 * 96 * 96
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median over the upper half of the samples = under load
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_block(C, device, seed=1234):
+    """Parameters: PyTorch default init under seed 1234; the zero-initialised conv_offset is re-initialised
+    N(0, 0.05^2) / U(-1, 1) so offsets are non-trivial."""
+    import deformablelka_b200 as dl
+    torch.manual_seed(seed)
+    m = dl.LKA_Attention3d_deform(C)
+    g = torch.Generator().manual_seed(seed)
+    co = m.spatial_gating_unit.deform_conv.conv_offset
+    with torch.no_grad():
+        co.weight.copy_(torch.randn(co.weight.shape, generator=g) * 0.05)
+        co.bias.copy_(torch.rand(co.bias.shape, generator=g) * 2 - 1)
+    return m.to(device).eval()
+
+
+def cpu_reference_sample(C, threads, sample_dims=(16, 64, 64), iters=1):
+    """The reference's CPU implementation of the path = the oracle (stock nn.Conv3d/GELU + restated D3D) on a
+    bounded sample of the workload: one sub-volume [1, C, 16, 64, 64] (1/32 of the step's voxels)."""
+    from oracle import oracle
+    torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    m = oracle.LKA_Attention3d_deform(C).eval()
+    oracle.randomize_offsets_(m, std=0.05, bias_range=1.0, seed=1234)
+    d1, d2, d3 = sample_dims
+    x = torch.randn(1, d1 * d2 * d3, C)
+    times = []
+    with torch.no_grad():
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            m(x, 1, C, d1, d2, d3)
+            times.append(time.perf_counter() - t0)
+    vox = d1 * d2 * d3
+    t = sum(times) / len(times)
+    return vox / t / 1e9, t, f"1x{C}x{d1}x{d2}x{d3} sub-volume of the step ({vox} of {2 * 64 * 128 * 128} voxels), {iters} iteration(s)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, t, sample = cpu_reference_sample(SHAPE["C"], threads)
+        if i >= args.warmup:
+            vals.append((v, t))
+    v = sum(x[0] for x in vals) / len(vals)
+    t = sum(x[1] for x in vals) / len(vals)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "GVoxel/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LKA_Attention3d_deform fwd, tokens [2, 64*128*128, 96] (3D D-LKA block)", "reference_arm":
+                   "oracle port of the reference CPU path (D3D is CUDA-only, 3D/dcn/src/deform_conv.h:46); each step = one bounded sample"},
+        "cpu_baseline": {"value": v, "unit": "GVoxel/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "GVoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--math", default=os.environ.get("DLKA_MATH", "bf16x3"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (ours) needs a CUDA device: there is no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ["DLKA_MATH"] = args.math
+    import deformablelka_b200 as dl
+
+    B, C, D1, D2, D3 = (SHAPE[k] for k in ("B", "C", "D1", "D2", "D3"))
+    N = D1 * D2 * D3
+    vox = B * N
+    m = make_block(C, dev)
+    torch.manual_seed(1234 + rank)
+    x = torch.randn(B, N, C, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        return m(x, B, C, D1, D2, D3)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            y = step()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        n0 = dl.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            y = step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = dl.launch_count() - n0
+        clocks = sampler.stop() if rank == 0 else None
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = t.item()
+
+        # per-kernel durations over the same K steps (CUDA events on the launch stream, inside the library)
+        dl._lib.profile_enable(True)
+        for _ in range(args.steps):
+            y = step()
+        torch.cuda.synchronize()
+        prof = dl._lib.profile_summary()
+        dl._lib.profile_enable(False)
+
+        # end-to-end through the module API with host buffers: pinned H2D of the step input, D2H of the result
+        e2e = None
+        if not args.no_e2e:
+            xh = torch.randn(B, N, C).pin_memory()
+            yh = torch.empty(B, N, C).pin_memory()
+            ksteps = max(2, min(args.steps, 5))
+            for _ in range(2):
+                yh.copy_(m(xh.to(dev, non_blocking=True), B, C, D1, D2, D3), non_blocking=True)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(ksteps):
+                yh.copy_(m(xh.to(dev, non_blocking=True), B, C, D1, D2, D3), non_blocking=True)
+            f1.record()
+            barrier()
+            t2 = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            e2e = {"value": world * vox * ksteps / (t2.item() * 1e-3) / 1e9, "unit": "GVoxel/s",
+                   "h2d_bytes_per_step": xh.numel() * 4, "d2h_bytes_per_step": yh.numel() * 4, "steps": ksteps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    ms_step = ms_total / args.steps
+    value = world * vox / (ms_step * 1e-3) / 1e9
+    # dominant kernel by device time
+    dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (1, float("nan")))
+    dom_name, (dom_n, dom_ms) = dom
+    dom_avg_ms = dom_ms / max(dom_n, 1)
+    launches_per_step = {k: v[0] / args.steps for k, v in prof.items()}
+    total_prof_ms = sum(v[1] for v in prof.values())
+    # tensor-bound roofline on the dominant kernel when it is a contraction kernel, else HBM-bound
+    per_launch_flop = {
+        "igemm_simt_deform": 2 * 27 * C * C * vox, "igemm_simt_conv": 2 * 27 * C * 81 * vox,
+        "tc_deform": 2 * 27 * C * C * vox, "tc_conv_offset": 2 * 27 * C * 81 * vox,
+        "tc_deform_fused": (2 * 27 * C * C + 2 * 2 * C * C) * vox,
+    }
+    if dom_name in per_launch_flop:
+        ach = per_launch_flop[dom_name] / (dom_avg_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom_name, "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " bf16 burst",
+                "avg_launch_ms": dom_avg_ms, "share_of_step": dom_ms / total_prof_ms if total_prof_ms else None}
+    else:
+        ach = HBM_BYTES_PER_VOXEL * vox / (dom_avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "avg_launch_ms": dom_avg_ms, "share_of_step": dom_ms / total_prof_ms if total_prof_ms else None}
+    out = {
+        "metric": METRIC, "value": value, "unit": "GVoxel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "LKA_Attention3d_deform fwd, tokens [2, 64*128*128, 96] per GPU (3D D-LKA block at (2,96,64,128,128))",
+                   "math": args.math, "parallelism": f"dp{world} (batch-sharded replicas, no collective in the timed region)",
+                   "l2": "inputs 805 MB per tensor > 126 MB L2 (no flush needed)",
+                   "params": "default init seed 1234; conv_offset ~ N(0,0.05^2), bias U(-1,1)"},
+        "block_hbm_frac": HBM_BYTES_PER_VOXEL * vox / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+        "block_contraction_tflops": CONTRACTION_FLOP_PER_VOXEL * vox / (ms_step * 1e-3) / 1e12,
+        "roofline": roof,
+        "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if e2e is not None:
+        out["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, t, sample = cpu_reference_sample(C, threads)
+        out["cpu_baseline"] = {"value": v, "unit": "GVoxel/s", "cores": threads, "kind": "port", "sample": sample,
+                               "seconds": t}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

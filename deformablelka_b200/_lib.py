@@ -1,0 +1,168 @@
+"""ctypes binding of libdlka_b200.so (the C ABI declared in include/dlka.h).
+
+There is no CPU path and no fallback: if the shared library is missing this module raises at
+import, and every compute call on a CPU tensor raises RuntimeError (the reference's 3D op does
+the same: "Not implemented on the CPU", 3D/dcn/src/deform_conv.h:46).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_int, c_int32, c_size_t, c_uint64, c_void_p
+from typing import Optional
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdlka_b200.so")
+
+MATH_FP32_SIMT = 0
+MATH_BF16X3 = 1
+_MATH_NAMES = {"fp32": MATH_FP32_SIMT, "fp32_simt": MATH_FP32_SIMT, "bf16x3": MATH_BF16X3}
+
+
+class Block3dParams(Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "proj_1_weight", "proj_1_bias", "conv0_weight", "conv0_bias", "conv_spatial_weight", "conv_spatial_bias",
+        "conv_offset_weight", "conv_offset_bias", "deform_weight", "deform_bias", "conv1_weight", "conv1_bias",
+        "proj_2_weight", "proj_2_bias")]
+
+
+class Block2dParams(Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "proj_1_weight", "proj_1_bias", "conv0_offset_weight", "conv0_offset_bias", "conv0_deform_weight",
+        "conv_spatial_offset_weight", "conv_spatial_offset_bias", "conv_spatial_deform_weight",
+        "conv1_weight", "conv1_bias", "proj_2_weight", "proj_2_bias")]
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python deformablelka_b200/build.py` "
+            "(deformablelka_b200 has no CPU / PyTorch fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    I = c_int
+    V = c_void_p
+    lib.dlka_version.restype = c_int
+    lib.dlka_status_string.restype = c_char_p
+    lib.dlka_status_string.argtypes = [c_int]
+    lib.dlka_last_cuda_error.restype = c_char_p
+    lib.dlka_launch_count.restype = c_uint64
+    lib.dlka_profile_enable.restype = c_int
+    lib.dlka_profile_enable.argtypes = [c_int]
+    lib.dlka_profile_summary.restype = c_int
+    lib.dlka_profile_summary.argtypes = [c_char_p, c_size_t]
+    lib.dlka_deform_conv3d_workspace_bytes.restype = c_size_t
+    lib.dlka_deform_conv3d_workspace_bytes.argtypes = [I] * 20
+    lib.dlka_deform_conv3d_forward.restype = c_int
+    lib.dlka_deform_conv3d_forward.argtypes = [V] * 5 + [I] * 22 + [V, c_size_t, V]
+    lib.dlka_deform_conv3d_sample_indices.restype = c_int
+    lib.dlka_deform_conv3d_sample_indices.argtypes = [V] * 3 + [I] * 17 + [V]
+    lib.dlka_deform_conv2d_workspace_bytes.restype = c_size_t
+    lib.dlka_deform_conv2d_workspace_bytes.argtypes = [I] * 15
+    lib.dlka_deform_conv2d_forward.restype = c_int
+    lib.dlka_deform_conv2d_forward.argtypes = [V] * 6 + [I] * 16 + [V, c_size_t, V]
+    lib.dlka_deform_conv2d_sample_indices.restype = c_int
+    lib.dlka_deform_conv2d_sample_indices.argtypes = [V] * 3 + [I] * 12 + [V]
+    lib.dlka_deform_conv_pack3d_workspace_bytes.restype = c_size_t
+    lib.dlka_deform_conv_pack3d_workspace_bytes.argtypes = [I] * 20
+    lib.dlka_deform_conv_pack3d_forward.restype = c_int
+    lib.dlka_deform_conv_pack3d_forward.argtypes = [V] * 6 + [I] * 22 + [V, c_size_t, V]
+    lib.dlka_deform_conv_pack2d_workspace_bytes.restype = c_size_t
+    lib.dlka_deform_conv_pack2d_workspace_bytes.argtypes = [I] * 14
+    lib.dlka_deform_conv_pack2d_forward.restype = c_int
+    lib.dlka_deform_conv_pack2d_forward.argtypes = [V] * 6 + [I] * 15 + [V, c_size_t, V]
+    for name in ("dlka_lka3d_deform", "dlka_lka_attention3d_deform"):
+        getattr(lib, name + "_workspace_bytes").restype = c_size_t
+        getattr(lib, name + "_workspace_bytes").argtypes = [I] * 5
+        getattr(lib, name + "_forward").restype = c_int
+        getattr(lib, name + "_forward").argtypes = [POINTER(Block3dParams), V, V] + [I] * 6 + [V, c_size_t, V]
+    lib.dlka_lka_attention3d_deform_forward_host.restype = c_int
+    lib.dlka_lka_attention3d_deform_forward_host.argtypes = (
+        [POINTER(Block3dParams), V, V] + [I] * 6 + [V, c_size_t, V, c_size_t, V])
+    for name in ("dlka_deformable_lka2d", "dlka_deformable_lka_attention2d"):
+        getattr(lib, name + "_workspace_bytes").restype = c_size_t
+        getattr(lib, name + "_workspace_bytes").argtypes = [I] * 4
+        getattr(lib, name + "_forward").restype = c_int
+        getattr(lib, name + "_forward").argtypes = [POINTER(Block2dParams), V, V] + [I] * 5 + [V, c_size_t, V]
+    return lib
+
+
+lib = _load()
+
+
+def math_mode(name_or_int) -> int:
+    if isinstance(name_or_int, int):
+        return name_or_int
+    try:
+        return _MATH_NAMES[str(name_or_int).lower()]
+    except KeyError:
+        raise ValueError(f"unknown math mode {name_or_int!r}; expected one of {sorted(_MATH_NAMES)}")
+
+
+def default_math() -> int:
+    return math_mode(os.environ.get("DLKA_MATH", "fp32"))
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib.dlka_status_string(status).decode()
+        cuda = lib.dlka_last_cuda_error().decode()
+        raise RuntimeError(f"{what}: {msg}" + (f" [{cuda}]" if cuda and status in (-4, -5) else ""))
+
+
+def dptr(t: Optional[torch.Tensor], what: str = "tensor") -> Optional[int]:
+    """Device pointer of a contiguous fp32 CUDA tensor (None passes through as NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: Not implemented on the CPU (deformablelka_b200 is CUDA-only)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{what}: expected float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{what} tensor has to be contiguous")
+    return t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Workspace:
+    """Per-device grow-only scratch buffer handed to the library (it never allocates itself)."""
+
+    _bufs = {}
+
+    @classmethod
+    def get(cls, device: torch.device, nbytes: int) -> torch.Tensor:
+        key = (device.index if device.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream(device).cuda_stream)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            cls._bufs[key] = None
+            buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf
+
+    @classmethod
+    def clear(cls) -> None:
+        cls._bufs.clear()
+
+
+def launch_count() -> int:
+    return int(lib.dlka_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    lib.dlka_profile_enable(1 if on else 0)
+
+
+def profile_summary() -> dict:
+    """{kernel name: (launches, total_ms)} since the last call; synchronises the recorded events."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib.dlka_profile_summary(buf, len(buf)), "dlka_profile_summary")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split()
+        out[name] = (int(n), float(ms))
+    return out

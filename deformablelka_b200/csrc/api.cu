@@ -1,0 +1,651 @@
+// api.cu -- the C ABI of libdlka_b200.so (see include/dlka.h for the contract and the reference
+// interfaces each entry point replaces).
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <string.h>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace dlka {
+
+thread_local char g_last_cuda_error[256] = {0};
+static std::atomic<uint64_t> g_launches{0};
+
+void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---- optional per-kernel event timing ---------------------------------------------------
+struct ProfRec {
+    const char *name;
+    cudaEvent_t a, b;
+};
+static std::atomic<int> g_profiling{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+
+KernelScope::KernelScope(const char *n, cudaStream_t s) : name(n), st(s), a(nullptr), b(nullptr), active(false)
+{
+    if (!g_profiling.load(std::memory_order_relaxed)) return;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    active = cudaEventRecord(a, st) == cudaSuccess;
+}
+
+KernelScope::~KernelScope()
+{
+    if (!active) return;
+    cudaEventRecord(b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back({name, a, b});
+}
+
+int record_cuda_error(cudaError_t e, const char *what)
+{
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? DLKA_ERR_NO_DEVICE : DLKA_ERR_CUDA;
+}
+
+namespace {
+
+int check_device()
+{
+    static thread_local int cached = 1;  // 1 = unknown
+    if (cached != 1) return cached;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cached = record_cuda_error(e, "cudaGetDevice");
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return cached = record_cuda_error(e, "cudaDeviceGetAttribute");
+    if (major != 10) {
+        snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "device compute capability %d.x is not sm_100", major);
+        return cached = DLKA_ERR_NO_DEVICE;
+    }
+    return cached = DLKA_OK;
+}
+
+IgemmArgs dense_args(const float *X, int ldX, i64 M, int Ci, int Co, const float *Wp, int Npad, const float *bias, int epi,
+                     const float *E, int ldE, float *Y, int ldY)
+{
+    IgemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = IGEMM_DENSE; a.epi = epi;
+    a.geo = make_geo(1, Ci, 1, 1, 1, Co, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 1, 3);
+    a.M = M; a.Ktot = Ci; a.Npad = Npad; a.X = X; a.ldX = ldX; a.Wp = Wp; a.bias = bias; a.E = E; a.ldE = ldE;
+    a.Y = Y; a.ldY = ldY;
+    return a;
+}
+
+IgemmArgs conv_args(int mode, const ConvGeo &g, const float *X, const float *Off, const float *Mask, const float *Wp, int Npad,
+                    const float *bias, int epi, const float *E, int ldE, float *Y, int ldY)
+{
+    IgemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = mode; a.epi = epi; a.geo = g;
+    a.M = (i64)g.B * g.Do * g.Ho * g.Wo; a.Ktot = g.K * (g.C / g.groups); a.Npad = Npad;
+    a.X = X; a.ldX = g.C; a.Off = Off; a.Mask = Mask; a.Wp = Wp; a.bias = bias; a.E = E; a.ldE = ldE; a.Y = Y; a.ldY = ldY;
+    return a;
+}
+
+bool bad_geo(const ConvGeo &g)
+{
+    return g.B <= 0 || g.C <= 0 || g.Co <= 0 || g.D <= 0 || g.H <= 0 || g.W <= 0 || g.kd <= 0 || g.kh <= 0 || g.kw <= 0 ||
+           g.sd <= 0 || g.sh <= 0 || g.sw <= 0 || g.pd < 0 || g.ph < 0 || g.pw < 0 || g.dd <= 0 || g.dh <= 0 || g.dw <= 0 ||
+           g.groups <= 0 || g.dg <= 0 || g.C % g.groups || g.Co % g.groups || g.C % g.dg || g.Do <= 0 || g.Ho <= 0 || g.Wo <= 0;
+}
+
+bool is_depthwise(const ConvGeo &g) { return g.groups == g.C && g.Co == g.C && g.C > 1; }
+
+// ---- workspace plans -------------------------------------------------------------------
+struct DeformOpPlan {
+    float *x_cl, *off_cl, *mask_cl, *y_cl, *wp;
+    int Npad;
+};
+
+bool plan_deform_op(Arena &ar, const ConvGeo &g, bool has_mask, DeformOpPlan &p)
+{
+    const i64 Vi = (i64)g.D * g.H * g.W, M = (i64)g.B * g.Do * g.Ho * g.Wo;
+    p.x_cl = ar.take<float>((size_t)g.B * Vi * g.C);
+    p.off_cl = ar.take<float>((size_t)M * g.dg * g.ndim * g.K);
+    p.mask_cl = has_mask ? ar.take<float>((size_t)M * g.dg * g.K) : nullptr;
+    p.y_cl = ar.take<float>((size_t)M * g.Co);
+    if (is_depthwise(g)) {
+        p.Npad = 0;
+        p.wp = ar.take<float>((size_t)g.K * g.C);
+    } else {
+        p.Npad = igemm_simt_npad(g.Co / g.groups);
+        p.wp = ar.take<float>((size_t)g.groups * g.K * (g.C / g.groups) * p.Npad);
+    }
+    return ar.ok();
+}
+
+int run_deform_op(const ConvGeo &g, const float *input, const float *weight, const float *bias, const float *offset,
+                  const float *mask, float *output, int math, void *workspace, size_t workspace_bytes, cudaStream_t st)
+{
+    (void)math;  // the operator-level entry currently always runs the exact fp32 path
+    Arena ar(workspace, workspace_bytes);
+    DeformOpPlan p;
+    if (!plan_deform_op(ar, g, mask != nullptr, p)) return DLKA_ERR_WORKSPACE;
+    const i64 Vi = (i64)g.D * g.H * g.W, Vo = (i64)g.Do * g.Ho * g.Wo;
+    DLKA_TRY(transpose_cs_to_sc(input, p.x_cl, g.B, g.C, Vi, st));
+    DLKA_TRY(transpose_cs_to_sc(offset, p.off_cl, g.B, g.dg * g.ndim * g.K, Vo, st));
+    if (mask) DLKA_TRY(transpose_cs_to_sc(mask, p.mask_cl, g.B, g.dg * g.K, Vo, st));
+    if (is_depthwise(g)) {
+        DLKA_TRY(deform_dwconv_cl(p.x_cl, p.off_cl, p.mask_cl, weight, bias, p.y_cl, g, p.wp, st));
+    } else {
+        if ((g.C / g.groups) % 4 != 0 || (g.C / g.dg) % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+        DLKA_TRY(pack_weight(weight, p.wp, g.Co, g.C / g.groups, g.K, g.groups, p.Npad, st));
+        IgemmArgs a = conv_args(IGEMM_DEFORM, g, p.x_cl, p.off_cl, p.mask_cl, p.wp, p.Npad, bias, EPI_NONE, nullptr, 0, p.y_cl, g.Co);
+        DLKA_TRY(igemm_simt(a, st));
+    }
+    DLKA_TRY(transpose_sc_to_cs(p.y_cl, output, g.B, g.Co, Vo, st));
+    return DLKA_OK;
+}
+
+// ---- 3D block ---------------------------------------------------------------------------
+struct Block3dPlan {
+    float *t1, *t2, *t3, *off;
+    float *wp_proj1, *wp_off, *wp_dcn, *wp_conv1, *wp_proj2, *wp_dw5, *wp_dw7;
+    int np_c, np_off;
+};
+
+bool plan_block3d(Arena &ar, int B, int C, int D1, int D2, int D3, Block3dPlan &p)
+{
+    const size_t M = (size_t)B * D1 * D2 * D3;
+    p.np_c = igemm_simt_npad(C);
+    p.np_off = igemm_simt_npad(81);
+    p.t1 = ar.take<float>(M * C);
+    p.t2 = ar.take<float>(M * C);
+    p.t3 = ar.take<float>(M * C);
+    p.off = ar.take<float>(M * 81);
+    p.wp_proj1 = ar.take<float>((size_t)C * p.np_c);
+    p.wp_conv1 = ar.take<float>((size_t)C * p.np_c);
+    p.wp_proj2 = ar.take<float>((size_t)C * p.np_c);
+    p.wp_off = ar.take<float>((size_t)27 * C * p.np_off);
+    p.wp_dcn = ar.take<float>((size_t)27 * C * p.np_c);
+    p.wp_dw5 = ar.take<float>((size_t)125 * C);
+    p.wp_dw7 = ar.take<float>((size_t)343 * C);
+    return ar.ok();
+}
+
+// u (channels-last, = GELU(proj_1 x) or x itself) -> gate = u * conv1(deform(dw7(dw5(u)))) into p.t3
+int run_lka3d_core(const dlkaBlock3dParams &P, const float *u, Block3dPlan &p, int B, int C, int D1, int D2, int D3,
+                   cudaStream_t st)
+{
+    const i64 M = (i64)B * D1 * D2 * D3;
+    DLKA_TRY(dwconv_cl(u, P.conv0_weight, P.conv0_bias, p.t2, B, C, D1, D2, D3, 5, 5, 5, 1, p.wp_dw5, st));
+    DLKA_TRY(dwconv_cl(p.t2, P.conv_spatial_weight, P.conv_spatial_bias, p.t3, B, C, D1, D2, D3, 7, 7, 7, 3, p.wp_dw7, st));
+    // conv_offset: Conv3d(C -> 81, k3, stride 1, pad 1)  (synapse/deform_conv.py:80-85)
+    const ConvGeo go = make_geo(B, C, D1, D2, D3, 81, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3);
+    DLKA_TRY(pack_weight(P.conv_offset_weight, p.wp_off, 81, C, 27, 1, p.np_off, st));
+    IgemmArgs ao = conv_args(IGEMM_CONV, go, p.t3, nullptr, nullptr, p.wp_off, p.np_off, P.conv_offset_bias, EPI_NONE, nullptr, 0,
+                             p.off, 81);
+    DLKA_TRY(igemm_simt(ao, st));
+    // deformable 3x3x3 conv C -> C, groups 1, dg 1 (transformerblock.py:639)
+    const ConvGeo gd = make_geo(B, C, D1, D2, D3, C, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3);
+    DLKA_TRY(pack_weight(P.deform_weight, p.wp_dcn, C, C, 27, 1, p.np_c, st));
+    IgemmArgs ad = conv_args(IGEMM_DEFORM, gd, p.t3, p.off, nullptr, p.wp_dcn, p.np_c, P.deform_bias, EPI_NONE, nullptr, 0, p.t2, C);
+    DLKA_TRY(igemm_simt(ad, st));
+    // conv1 (1x1x1) then gate with u
+    DLKA_TRY(pack_weight(P.conv1_weight, p.wp_conv1, C, C, 1, 1, p.np_c, st));
+    IgemmArgs a1 = dense_args(p.t2, C, M, C, C, p.wp_conv1, p.np_c, P.conv1_bias, EPI_MUL, u, C, p.t3, C);
+    DLKA_TRY(igemm_simt(a1, st));
+    return DLKA_OK;
+}
+
+bool null_params3d(const dlkaBlock3dParams *P, bool attention)
+{
+    if (!P) return true;
+    if (!P->conv0_weight || !P->conv0_bias || !P->conv_spatial_weight || !P->conv_spatial_bias || !P->conv_offset_weight ||
+        !P->conv_offset_bias || !P->deform_weight || !P->deform_bias || !P->conv1_weight || !P->conv1_bias)
+        return true;
+    if (attention && (!P->proj_1_weight || !P->proj_1_bias || !P->proj_2_weight || !P->proj_2_bias)) return true;
+    return false;
+}
+
+// ---- 2D block ---------------------------------------------------------------------------
+struct Block2dPlan {
+    float *x_cl, *t1, *t2, *t3, *off;
+    float *wp_proj1, *wp_off0, *wp_off1, *wp_conv1, *wp_proj2, *wp_dw0, *wp_dw1;
+    int np_c, np_off0, np_off1;
+};
+
+bool plan_block2d(Arena &ar, int B, int C, int H, int W, Block2dPlan &p)
+{
+    const size_t M = (size_t)B * H * W;
+    p.np_c = igemm_simt_npad(C);
+    p.np_off0 = igemm_simt_npad(50);
+    p.np_off1 = igemm_simt_npad(98);
+    p.x_cl = ar.take<float>(M * C);
+    p.t1 = ar.take<float>(M * C);
+    p.t2 = ar.take<float>(M * C);
+    p.t3 = ar.take<float>(M * C);
+    p.off = ar.take<float>(M * 98);
+    p.wp_proj1 = ar.take<float>((size_t)C * p.np_c);
+    p.wp_conv1 = ar.take<float>((size_t)C * p.np_c);
+    p.wp_proj2 = ar.take<float>((size_t)C * p.np_c);
+    p.wp_off0 = ar.take<float>((size_t)25 * C * p.np_off0);
+    p.wp_off1 = ar.take<float>((size_t)49 * C * p.np_off1);
+    p.wp_dw0 = ar.take<float>((size_t)25 * C);
+    p.wp_dw1 = ar.take<float>((size_t)49 * C);
+    return ar.ok();
+}
+
+// u channels-last -> u * conv1(conv_spatial(conv0(u))) into p.t2
+int run_lka2d_core(const dlkaBlock2dParams &P, const float *u, Block2dPlan &p, int B, int C, int H, int W, cudaStream_t st)
+{
+    const i64 M = (i64)B * H * W;
+    // conv0: offset_net Conv2d(C->50, k5, pad 2) + depthwise deformable k5 (deformable_LKA.py:93)
+    ConvGeo g0 = make_geo(B, C, 1, H, W, 50, 1, 5, 5, 1, 1, 1, 0, 2, 2, 1, 1, 1, 1, 1, 2);
+    DLKA_TRY(pack_weight(P.conv0_offset_weight, p.wp_off0, 50, C, 25, 1, p.np_off0, st));
+    IgemmArgs a0 = conv_args(IGEMM_CONV, g0, u, nullptr, nullptr, p.wp_off0, p.np_off0, P.conv0_offset_bias, EPI_NONE, nullptr, 0,
+                             p.off, 50);
+    DLKA_TRY(igemm_simt(a0, st));
+    ConvGeo d0 = make_geo(B, C, 1, H, W, C, 1, 5, 5, 1, 1, 1, 0, 2, 2, 1, 1, 1, C, 1, 2);
+    DLKA_TRY(deform_dwconv_cl(u, p.off, nullptr, P.conv0_deform_weight, nullptr, p.t2, d0, p.wp_dw0, st));
+    // conv_spatial: offset_net Conv2d(C->98, k7, dil 3, pad 9) + depthwise deformable k7 dil 3 (:94)
+    ConvGeo g1 = make_geo(B, C, 1, H, W, 98, 1, 7, 7, 1, 1, 1, 0, 9, 9, 1, 3, 3, 1, 1, 2);
+    DLKA_TRY(pack_weight(P.conv_spatial_offset_weight, p.wp_off1, 98, C, 49, 1, p.np_off1, st));
+    IgemmArgs a1 = conv_args(IGEMM_CONV, g1, p.t2, nullptr, nullptr, p.wp_off1, p.np_off1, P.conv_spatial_offset_bias, EPI_NONE,
+                             nullptr, 0, p.off, 98);
+    DLKA_TRY(igemm_simt(a1, st));
+    ConvGeo d1 = make_geo(B, C, 1, H, W, C, 1, 7, 7, 1, 1, 1, 0, 9, 9, 1, 3, 3, C, 1, 2);
+    DLKA_TRY(deform_dwconv_cl(p.t2, p.off, nullptr, P.conv_spatial_deform_weight, nullptr, p.t3, d1, p.wp_dw1, st));
+    // conv1 1x1 and the gate
+    DLKA_TRY(pack_weight(P.conv1_weight, p.wp_conv1, C, C, 1, 1, p.np_c, st));
+    IgemmArgs ac = dense_args(p.t3, C, M, C, C, p.wp_conv1, p.np_c, P.conv1_bias, EPI_MUL, u, C, p.t2, C);
+    DLKA_TRY(igemm_simt(ac, st));
+    return DLKA_OK;
+}
+
+bool null_params2d(const dlkaBlock2dParams *P, bool attention)
+{
+    if (!P) return true;
+    if (!P->conv0_offset_weight || !P->conv0_offset_bias || !P->conv0_deform_weight || !P->conv_spatial_offset_weight ||
+        !P->conv_spatial_offset_bias || !P->conv_spatial_deform_weight || !P->conv1_weight || !P->conv1_bias)
+        return true;
+    if (attention && (!P->proj_1_weight || !P->proj_1_bias || !P->proj_2_weight || !P->proj_2_bias)) return true;
+    return false;
+}
+
+}  // namespace
+}  // namespace dlka
+
+using namespace dlka;
+
+extern "C" {
+
+int dlka_version(void) { return DLKA_VERSION; }
+
+const char *dlka_status_string(int status)
+{
+    switch (status) {
+    case DLKA_OK: return "ok";
+    case DLKA_ERR_INVALID_ARGUMENT: return "invalid argument (shape / pointer / size mismatch)";
+    case DLKA_ERR_UNSUPPORTED: return "configuration not supported by libdlka_b200";
+    case DLKA_ERR_WORKSPACE: return "workspace missing or too small";
+    case DLKA_ERR_NO_DEVICE: return "no sm_100 CUDA device (libdlka_b200 has no CPU path)";
+    case DLKA_ERR_CUDA: return "CUDA error";
+    default: return "unknown status";
+    }
+}
+
+const char *dlka_last_cuda_error(void) { return g_last_cuda_error; }
+uint64_t dlka_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int dlka_profile_enable(int on)
+{
+    g_profiling.store(on ? 1 : 0);
+    return DLKA_OK;
+}
+
+int dlka_profile_summary(char *buf, size_t buf_bytes)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<int, double>> agg;
+    for (auto &r : g_prof_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            auto &e = agg[r.name];
+            e.first += 1;
+            e.second += ms;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof_recs.clear();
+    std::string out;
+    char line[160];
+    for (auto &kv : agg) {
+        snprintf(line, sizeof(line), "%s %d %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (!buf || buf_bytes == 0) return DLKA_ERR_INVALID_ARGUMENT;
+    snprintf(buf, buf_bytes, "%s", out.c_str());
+    return DLKA_OK;
+}
+
+// ---------------------------------------------------------------------------- 3D operator
+size_t dlka_deform_conv3d_workspace_bytes(int B, int C, int D, int H, int W, int Co, int kd, int kh, int kw, int sd, int sh,
+                                          int sw, int pd, int ph, int pw, int dild, int dilh, int dilw, int group,
+                                          int deformable_group)
+{
+    ConvGeo g = make_geo(B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw, dild, dilh, dilw, group, deformable_group, 3);
+    if (bad_geo(g)) return 0;
+    Arena ar(nullptr, 0);
+    DeformOpPlan p;
+    plan_deform_op(ar, g, false, p);
+    return ar.off + 256;
+}
+
+int dlka_deform_conv3d_forward(const float *input, const float *weight, const float *bias, const float *offset, float *output,
+                               int B, int C, int D, int H, int W, int Co, int kd, int kh, int kw, int sd, int sh, int sw, int pd,
+                               int ph, int pw, int dild, int dilh, int dilw, int group, int deformable_group, int im2col_step,
+                               int math, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!input || !weight || !bias || !offset || !output) return DLKA_ERR_INVALID_ARGUMENT;
+    if (group <= 0 || deformable_group <= 0 || im2col_step <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    ConvGeo g = make_geo(B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw, dild, dilh, dilw, group, deformable_group, 3);
+    if (bad_geo(g)) return DLKA_ERR_INVALID_ARGUMENT;
+    const int step = B < im2col_step ? B : im2col_step;  // deform_conv_cuda.cu:61-63
+    if (B % step != 0) return DLKA_ERR_INVALID_ARGUMENT;
+    DLKA_TRY(check_device());
+    return run_deform_op(g, input, weight, bias, offset, nullptr, output, math, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dlka_deform_conv3d_sample_indices(const float *offset, int32_t *low, int32_t *mask, int B, int D, int H, int W, int kd, int kh,
+                                      int kw, int sd, int sh, int sw, int pd, int ph, int pw, int dild, int dilh, int dilw,
+                                      int deformable_group, void *stream)
+{
+    if (!offset || !low || !mask) return DLKA_ERR_INVALID_ARGUMENT;
+    ConvGeo g = make_geo(B, deformable_group, D, H, W, deformable_group, kd, kh, kw, sd, sh, sw, pd, ph, pw, dild, dilh, dilw, 1,
+                         deformable_group, 3);
+    if (bad_geo(g)) return DLKA_ERR_INVALID_ARGUMENT;
+    DLKA_TRY(check_device());
+    return sample_indices(offset, low, mask, g, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------- 2D operator
+size_t dlka_deform_conv2d_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int sh, int sw, int ph, int pw,
+                                          int dilh, int dilw, int n_weight_grps, int n_offset_grps)
+{
+    ConvGeo g = make_geo(B, C, 1, H, W, Co, 1, kh, kw, 1, sh, sw, 0, ph, pw, 1, dilh, dilw, n_weight_grps, n_offset_grps, 2);
+    if (bad_geo(g)) return 0;
+    Arena ar(nullptr, 0);
+    DeformOpPlan p;
+    plan_deform_op(ar, g, true, p);
+    return ar.off + 256;
+}
+
+int dlka_deform_conv2d_forward(const float *input, const float *weight, const float *offset, const float *mask, const float *bias,
+                               float *output, int B, int C, int H, int W, int Co, int kh, int kw, int sh, int sw, int ph, int pw,
+                               int dilh, int dilw, int n_weight_grps, int n_offset_grps, int math, void *workspace,
+                               size_t workspace_bytes, void *stream)
+{
+    if (!input || !weight || !offset || !output) return DLKA_ERR_INVALID_ARGUMENT;
+    if (n_weight_grps <= 0 || n_offset_grps <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    ConvGeo g = make_geo(B, C, 1, H, W, Co, 1, kh, kw, 1, sh, sw, 0, ph, pw, 1, dilh, dilw, n_weight_grps, n_offset_grps, 2);
+    if (bad_geo(g)) return DLKA_ERR_INVALID_ARGUMENT;
+    DLKA_TRY(check_device());
+    return run_deform_op(g, input, weight, bias, offset, mask, output, math, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dlka_deform_conv2d_sample_indices(const float *offset, int32_t *low, int32_t *mask, int B, int H, int W, int kh, int kw, int sh,
+                                      int sw, int ph, int pw, int dilh, int dilw, int n_offset_grps, void *stream)
+{
+    if (!offset || !low || !mask) return DLKA_ERR_INVALID_ARGUMENT;
+    ConvGeo g = make_geo(B, n_offset_grps, 1, H, W, n_offset_grps, 1, kh, kw, 1, sh, sw, 0, ph, pw, 1, dilh, dilw, 1, n_offset_grps, 2);
+    if (bad_geo(g)) return DLKA_ERR_INVALID_ARGUMENT;
+    DLKA_TRY(check_device());
+    return sample_indices(offset, low, mask, g, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------- pack operators
+namespace {
+struct PackPlan {
+    float *x_cl, *off_cl, *y_cl, *wp_off, *wp;
+    int np_off, np;
+};
+
+bool plan_pack(Arena &ar, const ConvGeo &g, PackPlan &p)
+{
+    const i64 Vi = (i64)g.D * g.H * g.W, M = (i64)g.B * g.Do * g.Ho * g.Wo;
+    const int noff = g.dg * g.ndim * g.K;
+    p.x_cl = ar.take<float>((size_t)g.B * Vi * g.C);
+    p.off_cl = ar.take<float>((size_t)M * noff);
+    p.y_cl = ar.take<float>((size_t)M * g.Co);
+    p.np_off = igemm_simt_npad(noff);
+    p.wp_off = ar.take<float>((size_t)g.K * g.C * p.np_off);
+    if (is_depthwise(g)) {
+        p.np = 0;
+        p.wp = ar.take<float>((size_t)g.K * g.C);
+    } else {
+        p.np = igemm_simt_npad(g.Co / g.groups);
+        p.wp = ar.take<float>((size_t)g.groups * g.K * (g.C / g.groups) * p.np);
+    }
+    return ar.ok();
+}
+
+// g: geometry of the deformable conv; go: geometry of the offset conv (same taps, its own dilation)
+int run_pack(const ConvGeo &g, const ConvGeo &go, const float *input, const float *offset_weight, const float *offset_bias,
+             const float *weight, const float *bias, float *output, void *workspace, size_t workspace_bytes, cudaStream_t st)
+{
+    if (go.Do != g.Do || go.Ho != g.Ho || go.Wo != g.Wo) return DLKA_ERR_INVALID_ARGUMENT;
+    if (g.C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    Arena ar(workspace, workspace_bytes);
+    PackPlan p;
+    if (!plan_pack(ar, g, p)) return DLKA_ERR_WORKSPACE;
+    const i64 Vi = (i64)g.D * g.H * g.W, Vo = (i64)g.Do * g.Ho * g.Wo;
+    const int noff = g.dg * g.ndim * g.K;
+    DLKA_TRY(transpose_cs_to_sc(input, p.x_cl, g.B, g.C, Vi, st));
+    DLKA_TRY(pack_weight(offset_weight, p.wp_off, noff, g.C, g.K, 1, p.np_off, st));
+    IgemmArgs ao = conv_args(IGEMM_CONV, go, p.x_cl, nullptr, nullptr, p.wp_off, p.np_off, offset_bias, EPI_NONE, nullptr, 0,
+                             p.off_cl, noff);
+    DLKA_TRY(igemm_simt(ao, st));
+    if (is_depthwise(g)) {
+        DLKA_TRY(deform_dwconv_cl(p.x_cl, p.off_cl, nullptr, weight, bias, p.y_cl, g, p.wp, st));
+    } else {
+        if ((g.C / g.groups) % 4 != 0 || (g.C / g.dg) % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+        DLKA_TRY(pack_weight(weight, p.wp, g.Co, g.C / g.groups, g.K, g.groups, p.np, st));
+        IgemmArgs a = conv_args(IGEMM_DEFORM, g, p.x_cl, p.off_cl, nullptr, p.wp, p.np, bias, EPI_NONE, nullptr, 0, p.y_cl, g.Co);
+        DLKA_TRY(igemm_simt(a, st));
+    }
+    DLKA_TRY(transpose_sc_to_cs(p.y_cl, output, g.B, g.Co, Vo, st));
+    return DLKA_OK;
+}
+}  // namespace
+
+size_t dlka_deform_conv_pack3d_workspace_bytes(int B, int C, int D, int H, int W, int Co, int kd, int kh, int kw, int sd, int sh,
+                                               int sw, int pd, int ph, int pw, int dild, int dilh, int dilw, int group,
+                                               int deformable_group)
+{
+    ConvGeo g = make_geo(B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw, dild, dilh, dilw, group, deformable_group, 3);
+    if (bad_geo(g)) return 0;
+    Arena ar(nullptr, 0);
+    PackPlan p;
+    plan_pack(ar, g, p);
+    return ar.off + 256;
+}
+
+int dlka_deform_conv_pack3d_forward(const float *input, const float *offset_weight, const float *offset_bias, const float *weight,
+                                    const float *bias, float *output, int B, int C, int D, int H, int W, int Co, int kd, int kh,
+                                    int kw, int sd, int sh, int sw, int pd, int ph, int pw, int dild, int dilh, int dilw, int group,
+                                    int deformable_group, int im2col_step, int math, void *workspace, size_t workspace_bytes,
+                                    void *stream)
+{
+    (void)math;
+    if (!input || !offset_weight || !offset_bias || !weight || !bias || !output) return DLKA_ERR_INVALID_ARGUMENT;
+    if (group <= 0 || deformable_group <= 0 || im2col_step <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    ConvGeo g = make_geo(B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw, dild, dilh, dilw, group, deformable_group, 3);
+    if (bad_geo(g)) return DLKA_ERR_INVALID_ARGUMENT;
+    const int step = B < im2col_step ? B : im2col_step;
+    if (B % step != 0) return DLKA_ERR_INVALID_ARGUMENT;
+    // conv_offset ignores the dilation (synapse/deform_conv.py:80-85)
+    ConvGeo go = make_geo(B, C, D, H, W, deformable_group * 3 * g.K, kd, kh, kw, sd, sh, sw, pd, ph, pw, 1, 1, 1, 1, 1, 3);
+    if (bad_geo(go)) return DLKA_ERR_INVALID_ARGUMENT;
+    DLKA_TRY(check_device());
+    return run_pack(g, go, input, offset_weight, offset_bias, weight, bias, output, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t dlka_deform_conv_pack2d_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int sh, int sw, int ph, int pw,
+                                               int dilh, int dilw, int groups)
+{
+    ConvGeo g = make_geo(B, C, 1, H, W, Co, 1, kh, kw, 1, sh, sw, 0, ph, pw, 1, dilh, dilw, groups, 1, 2);
+    if (bad_geo(g)) return 0;
+    Arena ar(nullptr, 0);
+    PackPlan p;
+    plan_pack(ar, g, p);
+    return ar.off + 256;
+}
+
+int dlka_deform_conv_pack2d_forward(const float *input, const float *offset_weight, const float *offset_bias, const float *weight,
+                                    const float *bias, float *output, int B, int C, int H, int W, int Co, int kh, int kw, int sh,
+                                    int sw, int ph, int pw, int dilh, int dilw, int groups, int math, void *workspace,
+                                    size_t workspace_bytes, void *stream)
+{
+    (void)math;
+    if (!input || !offset_weight || !offset_bias || !weight || !output) return DLKA_ERR_INVALID_ARGUMENT;
+    if (groups <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    ConvGeo g = make_geo(B, C, 1, H, W, Co, 1, kh, kw, 1, sh, sw, 0, ph, pw, 1, dilh, dilw, groups, 1, 2);
+    if (bad_geo(g)) return DLKA_ERR_INVALID_ARGUMENT;
+    ConvGeo go = make_geo(B, C, 1, H, W, 2 * g.K, 1, kh, kw, 1, sh, sw, 0, ph, pw, 1, dilh, dilw, 1, 1, 2);
+    DLKA_TRY(check_device());
+    return run_pack(g, go, input, offset_weight, offset_bias, weight, bias, output, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------- 3D block
+size_t dlka_lka3d_deform_workspace_bytes(int B, int C, int D1, int D2, int D3)
+{
+    if (B <= 0 || C <= 0 || D1 <= 0 || D2 <= 0 || D3 <= 0) return 0;
+    Arena ar(nullptr, 0);
+    Block3dPlan p;
+    plan_block3d(ar, B, C, D1, D2, D3, p);
+    return ar.off + 256;
+}
+
+int dlka_lka3d_deform_forward(const dlkaBlock3dParams *params, const float *x, float *y, int B, int C, int D1, int D2, int D3,
+                              int math, void *workspace, size_t workspace_bytes, void *stream)
+{
+    (void)math;
+    if (null_params3d(params, false) || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
+    if (B <= 0 || C <= 0 || D1 <= 0 || D2 <= 0 || D3 <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    DLKA_TRY(check_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ar(workspace, workspace_bytes);
+    Block3dPlan p;
+    if (!plan_block3d(ar, B, C, D1, D2, D3, p)) return DLKA_ERR_WORKSPACE;
+    const i64 S = (i64)D1 * D2 * D3;
+    DLKA_TRY(transpose_cs_to_sc(x, p.t1, B, C, S, st));              // u = x (channels-last)
+    DLKA_TRY(run_lka3d_core(*params, p.t1, p, B, C, D1, D2, D3, st));  // gate -> t3
+    DLKA_TRY(transpose_sc_to_cs(p.t3, y, B, C, S, st));
+    return DLKA_OK;
+}
+
+size_t dlka_lka_attention3d_deform_workspace_bytes(int B, int C, int D1, int D2, int D3)
+{
+    return dlka_lka3d_deform_workspace_bytes(B, C, D1, D2, D3);
+}
+
+int dlka_lka_attention3d_deform_forward(const dlkaBlock3dParams *params, const float *x, float *y, int B, int C, int D1, int D2,
+                                        int D3, int math, void *workspace, size_t workspace_bytes, void *stream)
+{
+    (void)math;
+    if (null_params3d(params, true) || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
+    if (B <= 0 || C <= 0 || D1 <= 0 || D2 <= 0 || D3 <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    DLKA_TRY(check_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ar(workspace, workspace_bytes);
+    Block3dPlan p;
+    if (!plan_block3d(ar, B, C, D1, D2, D3, p)) return DLKA_ERR_WORKSPACE;
+    const i64 M = (i64)B * D1 * D2 * D3;
+    // tokens [B,N,C] are already channels-last over the Conv3d volume (transformerblock.py:665)
+    DLKA_TRY(pack_weight(params->proj_1_weight, p.wp_proj1, C, C, 1, 1, p.np_c, st));
+    IgemmArgs a1 = dense_args(x, C, M, C, C, p.wp_proj1, p.np_c, params->proj_1_bias, EPI_GELU, nullptr, 0, p.t1, C);
+    DLKA_TRY(igemm_simt(a1, st));
+    DLKA_TRY(run_lka3d_core(*params, p.t1, p, B, C, D1, D2, D3, st));  // gate -> t3
+    DLKA_TRY(pack_weight(params->proj_2_weight, p.wp_proj2, C, C, 1, 1, p.np_c, st));
+    IgemmArgs a2 = dense_args(p.t3, C, M, C, C, p.wp_proj2, p.np_c, params->proj_2_bias, EPI_ADD, x, C, y, C);
+    DLKA_TRY(igemm_simt(a2, st));
+    return DLKA_OK;
+}
+
+int dlka_lka_attention3d_deform_forward_host(const dlkaBlock3dParams *params, const float *x_host, float *y_host, int B, int C,
+                                             int D1, int D2, int D3, int math, void *dev_scratch, size_t dev_scratch_bytes,
+                                             void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!x_host || !y_host || !dev_scratch) return DLKA_ERR_INVALID_ARGUMENT;
+    if (B <= 0 || C <= 0 || D1 <= 0 || D2 <= 0 || D3 <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    const size_t n = (size_t)B * D1 * D2 * D3 * C;
+    if (dev_scratch_bytes < 2 * n * sizeof(float)) return DLKA_ERR_WORKSPACE;
+    DLKA_TRY(check_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    float *xd = (float *)dev_scratch, *yd = xd + n;
+    DLKA_CUDA_TRY(cudaMemcpyAsync(xd, x_host, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    DLKA_TRY(dlka_lka_attention3d_deform_forward(params, xd, yd, B, C, D1, D2, D3, math, workspace, workspace_bytes, stream));
+    DLKA_CUDA_TRY(cudaMemcpyAsync(y_host, yd, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    DLKA_CUDA_TRY(cudaStreamSynchronize(st));
+    return DLKA_OK;
+}
+
+// ---------------------------------------------------------------------------- 2D block
+size_t dlka_deformable_lka2d_workspace_bytes(int B, int C, int H, int W)
+{
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    Arena ar(nullptr, 0);
+    Block2dPlan p;
+    plan_block2d(ar, B, C, H, W, p);
+    return ar.off + 256;
+}
+
+int dlka_deformable_lka2d_forward(const dlkaBlock2dParams *params, const float *x, float *y, int B, int C, int H, int W, int math,
+                                  void *workspace, size_t workspace_bytes, void *stream)
+{
+    (void)math;
+    if (null_params2d(params, false) || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    DLKA_TRY(check_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ar(workspace, workspace_bytes);
+    Block2dPlan p;
+    if (!plan_block2d(ar, B, C, H, W, p)) return DLKA_ERR_WORKSPACE;
+    DLKA_TRY(transpose_cs_to_sc(x, p.x_cl, B, C, (i64)H * W, st));
+    DLKA_TRY(run_lka2d_core(*params, p.x_cl, p, B, C, H, W, st));  // gate -> t2
+    DLKA_TRY(transpose_sc_to_cs(p.t2, y, B, C, (i64)H * W, st));
+    return DLKA_OK;
+}
+
+size_t dlka_deformable_lka_attention2d_workspace_bytes(int B, int C, int H, int W)
+{
+    return dlka_deformable_lka2d_workspace_bytes(B, C, H, W);
+}
+
+int dlka_deformable_lka_attention2d_forward(const dlkaBlock2dParams *params, const float *x, float *y, int B, int C, int H, int W,
+                                            int math, void *workspace, size_t workspace_bytes, void *stream)
+{
+    (void)math;
+    if (null_params2d(params, true) || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    DLKA_TRY(check_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ar(workspace, workspace_bytes);
+    Block2dPlan p;
+    if (!plan_block2d(ar, B, C, H, W, p)) return DLKA_ERR_WORKSPACE;
+    const i64 M = (i64)B * H * W;
+    DLKA_TRY(transpose_cs_to_sc(x, p.x_cl, B, C, (i64)H * W, st));
+    DLKA_TRY(pack_weight(params->proj_1_weight, p.wp_proj1, C, C, 1, 1, p.np_c, st));
+    IgemmArgs a1 = dense_args(p.x_cl, C, M, C, C, p.wp_proj1, p.np_c, params->proj_1_bias, EPI_GELU, nullptr, 0, p.t1, C);
+    DLKA_TRY(igemm_simt(a1, st));
+    DLKA_TRY(run_lka2d_core(*params, p.t1, p, B, C, H, W, st));  // gate -> t2
+    DLKA_TRY(pack_weight(params->proj_2_weight, p.wp_proj2, C, C, 1, 1, p.np_c, st));
+    IgemmArgs a2 = dense_args(p.t2, C, M, C, C, p.wp_proj2, p.np_c, params->proj_2_bias, EPI_ADD, p.x_cl, C, p.t3, C);
+    DLKA_TRY(igemm_simt(a2, st));
+    DLKA_TRY(transpose_sc_to_cs(p.t3, y, B, C, (i64)H * W, st));
+    return DLKA_OK;
+}
+
+}  // extern "C"

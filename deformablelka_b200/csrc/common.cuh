@@ -1,0 +1,207 @@
+// common.cuh -- shared host/device helpers for libdlka_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dlka.h"
+
+typedef long long i64;
+
+// ---------------------------------------------------------------------------------------
+// host-side bookkeeping
+// ---------------------------------------------------------------------------------------
+namespace dlka {
+
+extern thread_local char g_last_cuda_error[256];
+void note_launch(int n = 1);
+int record_cuda_error(cudaError_t e, const char *what);
+
+#define DLKA_CUDA_TRY(expr)                                                   \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return dlka::record_cuda_error(_e, #expr);     \
+    } while (0)
+
+#define DLKA_CHECK_LAUNCH(name)                                               \
+    do {                                                                      \
+        dlka::note_launch();                                                  \
+        cudaError_t _e = cudaGetLastError();                                  \
+        if (_e != cudaSuccess) return dlka::record_cuda_error(_e, name);      \
+    } while (0)
+
+// Optional per-kernel CUDA-event timing (dlka_profile_enable): start/stop events on the launch stream.
+struct KernelScope {
+    const char *name;
+    cudaStream_t st;
+    cudaEvent_t a, b;
+    bool active;
+    KernelScope(const char *name, cudaStream_t st);
+    ~KernelScope();
+};
+
+#define DLKA_LAUNCH(name, st, ...)                                            \
+    do {                                                                      \
+        {                                                                     \
+            dlka::KernelScope _ks(name, st);                                  \
+            __VA_ARGS__;                                                      \
+        }                                                                     \
+        DLKA_CHECK_LAUNCH(name);                                              \
+    } while (0)
+
+#define DLKA_TRY(expr)                                                        \
+    do {                                                                      \
+        int _s = (expr);                                                      \
+        if (_s != DLKA_OK) return _s;                                         \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline i64 cdiv(i64 a, i64 b) { return (a + b - 1) / b; }
+
+// Bump allocator over the caller's workspace.
+struct Arena {
+    char *base;
+    size_t cap, off;
+    Arena(void *p, size_t bytes) : base((char *)p), cap(bytes), off(0) {}
+    template <typename T>
+    T *take(size_t n)
+    {
+        off = align_up(off, 256);
+        T *r = (T *)(base + off);
+        off += n * sizeof(T);
+        return r;
+    }
+    bool ok() const { return off <= cap && (base != nullptr || off == 0); }
+};
+
+// Geometry of a (deformable) convolution over a channels-last volume.  2D uses D = kd = 1.
+struct ConvGeo {
+    int B, C, D, H, W;     // input extent
+    int Co, Do, Ho, Wo;    // output extent
+    int kd, kh, kw, sd, sh, sw, pd, ph, pw, dd, dh, dw;
+    int K;                 // taps = kd*kh*kw
+    int groups, dg;        // weight groups, deformable (offset) groups
+    int ndim;              // 2 or 3: number of offset components per tap
+};
+
+static inline int out_extent(int in, int pad, int dil, int k, int stride)
+{
+    return (in + 2 * pad - (dil * (k - 1) + 1)) / stride + 1;  // deform_conv_cuda.cu:78-80
+}
+
+static inline ConvGeo make_geo(int B, int C, int D, int H, int W, int Co, int kd, int kh, int kw, int sd, int sh,
+                               int sw, int pd, int ph, int pw, int dd, int dh, int dw, int groups, int dg, int ndim)
+{
+    ConvGeo g;
+    g.B = B; g.C = C; g.D = D; g.H = H; g.W = W; g.Co = Co;
+    g.kd = kd; g.kh = kh; g.kw = kw; g.sd = sd; g.sh = sh; g.sw = sw;
+    g.pd = pd; g.ph = ph; g.pw = pw; g.dd = dd; g.dh = dh; g.dw = dw;
+    g.Do = out_extent(D, pd, dd, kd, sd); g.Ho = out_extent(H, ph, dh, kh, sh); g.Wo = out_extent(W, pw, dw, kw, sw);
+    g.K = kd * kh * kw; g.groups = groups; g.dg = dg; g.ndim = ndim;
+    return g;
+}
+
+}  // namespace dlka
+
+// ---------------------------------------------------------------------------------------
+// device: the sampler.  Restates the arithmetic of dmcn_im2col_bilinear and its caller
+// (3D/dcn/src/cuda/deform_im2col_cuda.cuh:26-72, :224-226, :245-248) for channels-last data.
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace dlka {
+
+// p = float(o*stride - pad + tap*dil) + delta : integer base first, then ONE fp32 add.
+__device__ __forceinline__ float sample_pos(int o, int stride, int pad, int tap, int dil, float delta)
+{
+    return __fadd_rn((float)(o * stride - pad + tap * dil), delta);
+}
+
+struct Sample3 {
+    int lo[3];     // floor(p) per axis (d, h, w)
+    float l[3];    // p - floor(p)
+    int mask;      // bit0: sample valid; bits 1..8: corner v1..v8 is read
+};
+
+__device__ __forceinline__ Sample3 make_sample3(float pd, float ph, float pw, int D, int H, int W)
+{
+    Sample3 s;
+    s.lo[0] = (int)floorf(pd); s.lo[1] = (int)floorf(ph); s.lo[2] = (int)floorf(pw);
+    s.l[0] = pd - (float)s.lo[0]; s.l[1] = ph - (float)s.lo[1]; s.l[2] = pw - (float)s.lo[2];
+    int m = 0;
+    if (pd > -1.f && ph > -1.f && pw > -1.f && pd < (float)D && ph < (float)H && pw < (float)W) {
+        const int dl = s.lo[0] >= 0, hl = s.lo[1] >= 0, wl = s.lo[2] >= 0;
+        const int dh = s.lo[0] + 1 <= D - 1, hh = s.lo[1] + 1 <= H - 1, wh = s.lo[2] + 1 <= W - 1;
+        m = 1 | ((dl & hl & wl) << 1) | ((dl & hl & wh) << 2) | ((dl & hh & wl) << 3) | ((dl & hh & wh) << 4) |
+            ((dh & hl & wl) << 5) | ((dh & hl & wh) << 6) | ((dh & hh & wl) << 7) | ((dh & hh & wh) << 8);
+    }
+    s.mask = m;
+    return s;
+}
+
+// 2D sampler (torchvision deform_conv2d bilinear_interpolate): same rules on (h, w).
+struct Sample2 {
+    int lo[2];
+    float l[2];
+    int mask;      // bit0 valid; bits 1..4 corners v1..v4
+};
+
+__device__ __forceinline__ Sample2 make_sample2(float ph, float pw, int H, int W)
+{
+    Sample2 s;
+    s.lo[0] = (int)floorf(ph); s.lo[1] = (int)floorf(pw);
+    s.l[0] = ph - (float)s.lo[0]; s.l[1] = pw - (float)s.lo[1];
+    int m = 0;
+    if (ph > -1.f && pw > -1.f && ph < (float)H && pw < (float)W) {
+        const int hl = s.lo[0] >= 0, wl = s.lo[1] >= 0, hh = s.lo[0] + 1 <= H - 1, wh = s.lo[1] + 1 <= W - 1;
+        m = 1 | ((hl & wl) << 1) | ((hl & wh) << 2) | ((hh & wl) << 3) | ((hh & wh) << 4);
+    }
+    s.mask = m;
+    return s;
+}
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void fma4(float4 &acc, float w, const float4 &v)
+{
+    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+}
+
+// Trilinear blend of 4 consecutive channels at a sample; `vol` points at channel c of sample b
+// (channels-last volume [D,H,W,C]).  Weight products follow cuh:67-68 (hd*hh*hw ...).
+__device__ __forceinline__ float4 trilinear4(const float *__restrict__ vol, const Sample3 &s, int H, int W, int C)
+{
+    float4 acc = f4zero();
+    if (!(s.mask & 1)) return acc;
+    const float ld = s.l[0], lh = s.l[1], lw = s.l[2];
+    const float hd = 1.f - ld, hh = 1.f - lh, hw = 1.f - lw;
+    const i64 sH = (i64)W * C, sD = (i64)H * sH;
+    const float *p000 = vol + (i64)s.lo[0] * sD + (i64)s.lo[1] * sH + (i64)s.lo[2] * C;
+    if (s.mask & (1 << 1)) fma4(acc, hd * hh * hw, ldg4(p000));
+    if (s.mask & (1 << 2)) fma4(acc, hd * hh * lw, ldg4(p000 + C));
+    if (s.mask & (1 << 3)) fma4(acc, hd * lh * hw, ldg4(p000 + sH));
+    if (s.mask & (1 << 4)) fma4(acc, hd * lh * lw, ldg4(p000 + sH + C));
+    if (s.mask & (1 << 5)) fma4(acc, ld * hh * hw, ldg4(p000 + sD));
+    if (s.mask & (1 << 6)) fma4(acc, ld * hh * lw, ldg4(p000 + sD + C));
+    if (s.mask & (1 << 7)) fma4(acc, ld * lh * hw, ldg4(p000 + sD + sH));
+    if (s.mask & (1 << 8)) fma4(acc, ld * lh * lw, ldg4(p000 + sD + sH + C));
+    return acc;
+}
+
+__device__ __forceinline__ float4 bilinear4(const float *__restrict__ img, const Sample2 &s, int W, int C)
+{
+    float4 acc = f4zero();
+    if (!(s.mask & 1)) return acc;
+    const float lh = s.l[0], lw = s.l[1], hh = 1.f - lh, hw = 1.f - lw;
+    const i64 sH = (i64)W * C;
+    const float *p00 = img + (i64)s.lo[0] * sH + (i64)s.lo[1] * C;
+    if (s.mask & (1 << 1)) fma4(acc, hh * hw, ldg4(p00));
+    if (s.mask & (1 << 2)) fma4(acc, hh * lw, ldg4(p00 + C));
+    if (s.mask & (1 << 3)) fma4(acc, lh * hw, ldg4(p00 + sH));
+    if (s.mask & (1 << 4)) fma4(acc, lh * lw, ldg4(p00 + sH + C));
+    return acc;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+}  // namespace dlka
+#endif

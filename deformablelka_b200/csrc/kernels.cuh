@@ -1,0 +1,53 @@
+// kernels.cuh -- internal launcher interface between api.cu and the kernel translation units.
+// Internal activation layout is channels-last fp32: X[b][d][h][w][c] (2D: d = 0).
+#pragma once
+#include "common.cuh"
+
+namespace dlka {
+
+// ---------------- implicit GEMM (SIMT fp32 and tensor-core variants share the argument block) ----
+enum IgemmMode { IGEMM_DENSE = 0, IGEMM_CONV = 1, IGEMM_DEFORM = 2 };
+enum EpiMode { EPI_NONE = 0, EPI_GELU = 1, EPI_MUL = 2, EPI_ADD = 3 };
+
+struct IgemmArgs {
+    int mode;          // IgemmMode
+    int epi;           // EpiMode
+    ConvGeo geo;       // input/output geometry (dense: only C, Co, groups=1 matter)
+    i64 M;             // output rows = B*Do*Ho*Wo
+    int Ktot;          // taps * C/groups
+    int Npad;          // padded columns of Wp per group
+    const float *X;    // input, channels-last; dense: row stride ldX
+    int ldX;
+    const float *Off;  // deformable: offsets [M][dg*ndim*K]
+    const float *Mask; // deformable 2D (DCNv2) modulation [M][dg*K] or null
+    const float *Wp;   // packed weights [groups][Ktot][Npad]
+    const float *bias; // [Co] or null
+    const float *E;    // epilogue operand (gate / residual) [M][ldE] or null
+    int ldE;
+    float *Y;          // output [M][ldY]
+    int ldY;
+};
+
+int igemm_simt_npad(int n_per_group);
+int pack_weight(const float *w, float *wp, int Co, int Cg, int taps, int groups, int Npad, cudaStream_t st);
+int igemm_simt(const IgemmArgs &a, cudaStream_t st);
+
+// ---------------- layout ----------------
+// [B][C][S] -> [B][S][C]  and back (S = spatial size)
+int transpose_cs_to_sc(const float *in, float *out, int B, int C, i64 S, cudaStream_t st);
+int transpose_sc_to_cs(const float *in, float *out, int B, int C, i64 S, cudaStream_t st);
+
+// ---------------- depthwise (regular) conv, channels-last, "same" output extent, stride 1 ----------
+// w: PyTorch layout [C][1][kd][kh][kw]; bias [C] or null.  pad = dil*(k-1)/2 on each axis.
+int dwconv_cl(const float *x, const float *w, const float *bias, float *y, int B, int C, int D, int H, int W, int kd,
+              int kh, int kw, int dil, float *w_packed /*[K][C]*/, cudaStream_t st);
+
+// ---------------- depthwise deformable conv (groups == C == Co), channels-last ----------------------
+// w: [C][1][taps] PyTorch layout; Off [M][dg*ndim*K]; Mask optional; bias optional.
+int deform_dwconv_cl(const float *x, const float *off, const float *mask, const float *w, const float *bias, float *y,
+                     const ConvGeo &g, float *w_packed /*[K][C]*/, cudaStream_t st);
+
+// ---------------- sampler integer planes (parity K4) ----------------
+int sample_indices(const float *off_cf, int32_t *low, int32_t *mask, const ConvGeo &g, cudaStream_t st);
+
+}  // namespace dlka

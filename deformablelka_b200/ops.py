@@ -1,0 +1,321 @@
+"""Functional host API over the C ABI (include/dlka.h).  Tensors are fp32 CUDA tensors; every
+function runs on the caller's current CUDA stream and allocates only its output (+ a cached
+workspace)."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Block2dParams, Block3dParams, Workspace, check, dptr, lib, stream_ptr
+
+
+def _triple(v):
+    return tuple(int(i) for i in v) if isinstance(v, (tuple, list)) else (int(v),) * 3
+
+
+def _pair(v):
+    return tuple(int(i) for i in v) if isinstance(v, (tuple, list)) else (int(v),) * 2
+
+
+def _out_extent(n, pad, dil, k, stride):
+    return (n + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+
+
+def _math(math) -> int:
+    return _lib.default_math() if math is None else _lib.math_mode(math)
+
+
+# ----------------------------------------------------------------------------------------------
+# 3D operator: D3D.deform_conv_forward (3D/dcn/src/deform_conv.h:10-47)
+# ----------------------------------------------------------------------------------------------
+def deform_conv3d_forward(input: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, offset: torch.Tensor,
+                          kernel_size, stride, padding, dilation, group: int, deformable_group: int,
+                          im2col_step: int = 64, math=None) -> torch.Tensor:
+    """Same argument meaning and error behaviour as ``D3D.deform_conv_forward``."""
+    if not input.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")  # deform_conv.h:46
+    if not input.is_contiguous():
+        raise RuntimeError("input tensor has to be contiguous")  # deform_conv_cuda.cu:41
+    if not weight.is_contiguous():
+        raise RuntimeError("weight tensor has to be contiguous")  # :42
+    if input.dim() != 5 or weight.dim() != 5:
+        raise RuntimeError("input and weight must be 5-D (NCDHW / OIDHW)")
+    kd, kh, kw = _triple(kernel_size)
+    sd, sh, sw = _triple(stride)
+    pd, ph, pw = _triple(padding)
+    dd, dh, dw = _triple(dilation)
+    B, C, D, H, W = input.shape
+    Co, Cg, kd_, kh_, kw_ = weight.shape
+    if (kd_, kh_, kw_) != (kd, kh, kw):
+        raise RuntimeError(f"Input shape and kernel shape wont match: ({kh} x {kw} x {kd} vs {kh_} x {kw_} x {kd_}).")  # :73
+    if C != Cg * group:
+        raise RuntimeError(f"Input shape and kernel channels wont match: ({C} vs {Cg * group}).")  # :76
+    if C % group or Co % group:
+        raise RuntimeError(f"channels({C}) and channels_out({Co}) must divide group({group})")  # :65
+    step = min(B, im2col_step)
+    if B % step:
+        raise RuntimeError(f"batch({B}) must divide im2col_step({step})")  # :63
+    Do, Ho, Wo = _out_extent(D, pd, dd, kd, sd), _out_extent(H, ph, dh, kh, sh), _out_extent(W, pw, dw, kw, sw)
+    K = kd * kh * kw
+    if tuple(offset.shape) != (B, deformable_group * 3 * K, Do, Ho, Wo):
+        raise RuntimeError(f"offset shape {tuple(offset.shape)} does not match "
+                           f"{(B, deformable_group * 3 * K, Do, Ho, Wo)}")
+    if bias is None or bias.numel() != Co:
+        raise RuntimeError("bias must be a tensor with channels_out elements")  # modules/deform_conv.py:39
+    offset = offset.contiguous()  # the reference reads raw pointers; callers already pass contiguous
+    out = torch.empty(B, Co, Do, Ho, Wo, dtype=torch.float32, device=input.device)
+    ws_bytes = lib.dlka_deform_conv3d_workspace_bytes(B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw,
+                                                      dd, dh, dw, group, deformable_group)
+    ws = Workspace.get(input.device, ws_bytes)
+    with torch.cuda.device(input.device):
+        st = lib.dlka_deform_conv3d_forward(
+            dptr(input, "input"), dptr(weight, "weight"), dptr(bias.contiguous(), "bias"), dptr(offset, "offset"),
+            dptr(out), B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw, dd, dh, dw, group, deformable_group,
+            im2col_step, _math(math), ws.data_ptr(), ws.numel(), stream_ptr(input.device))
+    check(st, "dlka_deform_conv3d_forward")
+    return out
+
+
+def deform_conv3d_sample_indices(offset: torch.Tensor, in_size, kernel_size, stride=1, padding=0, dilation=1,
+                                 deformable_group: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    D, H, W = in_size
+    kd, kh, kw = _triple(kernel_size); sd, sh, sw = _triple(stride); pd, ph, pw = _triple(padding); dd, dh, dw = _triple(dilation)
+    offset = offset.contiguous()
+    B = offset.shape[0]
+    Vo = offset.shape[2] * offset.shape[3] * offset.shape[4]
+    K = kd * kh * kw
+    low = torch.empty(B * deformable_group, Vo, K, 3, dtype=torch.int32, device=offset.device)
+    mask = torch.empty(B * deformable_group, Vo, K, dtype=torch.int32, device=offset.device)
+    with torch.cuda.device(offset.device):
+        st = lib.dlka_deform_conv3d_sample_indices(dptr(offset, "offset"), low.data_ptr(), mask.data_ptr(), B, D, H, W,
+                                                   kd, kh, kw, sd, sh, sw, pd, ph, pw, dd, dh, dw, deformable_group,
+                                                   stream_ptr(offset.device))
+    check(st, "dlka_deform_conv3d_sample_indices")
+    return low, mask
+
+
+# ----------------------------------------------------------------------------------------------
+# 2D operator: torchvision.ops.deform_conv2d (torchvision/ops/deform_conv.py:14-107)
+# ----------------------------------------------------------------------------------------------
+def deform_conv2d(input: torch.Tensor, offset: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                  stride=(1, 1), padding=(0, 0), dilation=(1, 1), mask: Optional[torch.Tensor] = None, math=None) -> torch.Tensor:
+    """Same signature and semantics as ``torchvision.ops.deform_conv2d``."""
+    if not input.is_cuda:
+        raise RuntimeError("Not implemented on the CPU (deformablelka_b200 is CUDA-only)")
+    sh, sw = _pair(stride); ph, pw = _pair(padding); dh, dw = _pair(dilation)
+    B, C, H, W = input.shape
+    Co, Cg, kh, kw = weight.shape
+    n_off = offset.shape[1] // (2 * kh * kw)
+    n_wg = C // Cg
+    if n_off == 0:
+        raise RuntimeError(
+            "the shape of the offset tensor at dimension 1 is not valid. It should "
+            "be a multiple of 2 * weight.size[2] * weight.size[3].\n"
+            f"Got offset.shape[1]={offset.shape[1]}, while 2 * weight.size[2] * weight.size[3]={2 * kh * kw}")
+    Ho, Wo = _out_extent(H, ph, dh, kh, sh), _out_extent(W, pw, dw, kw, sw)
+    if tuple(offset.shape) != (B, n_off * 2 * kh * kw, Ho, Wo):
+        raise RuntimeError(f"offset shape {tuple(offset.shape)} does not match {(B, n_off * 2 * kh * kw, Ho, Wo)}")
+    if mask is not None and tuple(mask.shape) != (B, n_off * kh * kw, Ho, Wo):
+        raise RuntimeError(f"mask shape {tuple(mask.shape)} does not match {(B, n_off * kh * kw, Ho, Wo)}")
+    input = input.contiguous(); offset = offset.contiguous(); weight = weight.contiguous()
+    out = torch.empty(B, Co, Ho, Wo, dtype=torch.float32, device=input.device)
+    ws_bytes = lib.dlka_deform_conv2d_workspace_bytes(B, C, H, W, Co, kh, kw, sh, sw, ph, pw, dh, dw, n_wg, n_off)
+    ws = Workspace.get(input.device, ws_bytes)
+    with torch.cuda.device(input.device):
+        st = lib.dlka_deform_conv2d_forward(
+            dptr(input, "input"), dptr(weight, "weight"), dptr(offset, "offset"),
+            dptr(None if mask is None else mask.contiguous(), "mask"),
+            dptr(None if bias is None else bias.contiguous(), "bias"), dptr(out),
+            B, C, H, W, Co, kh, kw, sh, sw, ph, pw, dh, dw, n_wg, n_off, _math(math),
+            ws.data_ptr(), ws.numel(), stream_ptr(input.device))
+    check(st, "dlka_deform_conv2d_forward")
+    return out
+
+
+def deform_conv2d_sample_indices(offset, in_size, kernel_size, stride=1, padding=0, dilation=1, n_offset_grps=1):
+    H, W = in_size
+    kh, kw = _pair(kernel_size); sh, sw = _pair(stride); ph, pw = _pair(padding); dh, dw = _pair(dilation)
+    offset = offset.contiguous()
+    B = offset.shape[0]
+    P = offset.shape[2] * offset.shape[3]
+    K = kh * kw
+    low = torch.empty(B * n_offset_grps, P, K, 2, dtype=torch.int32, device=offset.device)
+    mask = torch.empty(B * n_offset_grps, P, K, dtype=torch.int32, device=offset.device)
+    with torch.cuda.device(offset.device):
+        st = lib.dlka_deform_conv2d_sample_indices(dptr(offset, "offset"), low.data_ptr(), mask.data_ptr(), B, H, W,
+                                                   kh, kw, sh, sw, ph, pw, dh, dw, n_offset_grps, stream_ptr(offset.device))
+    check(st, "dlka_deform_conv2d_sample_indices")
+    return low, mask
+
+
+def deform_conv_pack3d(input, offset_weight, offset_bias, weight, bias, stride, padding, dilation, groups,
+                       deformable_groups, im2col_step=64, math=None) -> torch.Tensor:
+    """DeformConvPack.forward (synapse/deform_conv.py:93-105): conv_offset + deformable conv in one call."""
+    if not input.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    if input.dim() != 5:
+        raise RuntimeError("expected a 5-D NCDHW tensor")
+    input = input.contiguous()
+    sd, sh, sw = _triple(stride); pd, ph, pw = _triple(padding); dd, dh, dw = _triple(dilation)
+    B, C, D, H, W = input.shape
+    Co, Cg, kd, kh, kw = weight.shape
+    if C != Cg * groups:
+        raise RuntimeError(f"Input shape and kernel channels wont match: ({C} vs {Cg * groups}).")
+    step = min(B, im2col_step)
+    if B % step:
+        raise RuntimeError(f"batch({B}) must divide im2col_step({step})")
+    Do, Ho, Wo = _out_extent(D, pd, dd, kd, sd), _out_extent(H, ph, dh, kh, sh), _out_extent(W, pw, dw, kw, sw)
+    out = torch.empty(B, Co, Do, Ho, Wo, dtype=torch.float32, device=input.device)
+    ws = Workspace.get(input.device, lib.dlka_deform_conv_pack3d_workspace_bytes(
+        B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw, dd, dh, dw, groups, deformable_groups))
+    with torch.cuda.device(input.device):
+        st = lib.dlka_deform_conv_pack3d_forward(
+            dptr(input, "input"), dptr(offset_weight.contiguous(), "conv_offset.weight"),
+            dptr(offset_bias.contiguous(), "conv_offset.bias"), dptr(weight.contiguous(), "weight"),
+            dptr(bias.contiguous(), "bias"), dptr(out), B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw,
+            dd, dh, dw, groups, deformable_groups, im2col_step, _math(math), ws.data_ptr(), ws.numel(),
+            stream_ptr(input.device))
+    check(st, "dlka_deform_conv_pack3d_forward")
+    return out
+
+
+def deform_conv_pack2d(input, offset_weight, offset_bias, weight, bias, stride, padding, dilation, math=None) -> torch.Tensor:
+    """DeformConv.forward (2D/deformable_LKA/deformable_LKA.py:27-30): offset_net + deformable conv in one call."""
+    if not input.is_cuda:
+        raise RuntimeError("Not implemented on the CPU (deformablelka_b200 is CUDA-only)")
+    if input.dim() != 4:
+        raise RuntimeError("expected a 4-D NCHW tensor")
+    input = input.contiguous()
+    sh, sw = _pair(stride); ph, pw = _pair(padding); dh, dw = _pair(dilation)
+    B, C, H, W = input.shape
+    Co, Cg, kh, kw = weight.shape
+    groups = C // Cg
+    Ho, Wo = _out_extent(H, ph, dh, kh, sh), _out_extent(W, pw, dw, kw, sw)
+    out = torch.empty(B, Co, Ho, Wo, dtype=torch.float32, device=input.device)
+    ws = Workspace.get(input.device, lib.dlka_deform_conv_pack2d_workspace_bytes(B, C, H, W, Co, kh, kw, sh, sw, ph, pw, dh, dw, groups))
+    with torch.cuda.device(input.device):
+        st = lib.dlka_deform_conv_pack2d_forward(
+            dptr(input, "input"), dptr(offset_weight.contiguous(), "offset_net.weight"),
+            dptr(offset_bias.contiguous(), "offset_net.bias"), dptr(weight.contiguous(), "weight"),
+            dptr(None if bias is None else bias.contiguous(), "bias"), dptr(out),
+            B, C, H, W, Co, kh, kw, sh, sw, ph, pw, dh, dw, groups, _math(math), ws.data_ptr(), ws.numel(),
+            stream_ptr(input.device))
+    check(st, "dlka_deform_conv_pack2d_forward")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# blocks
+# ----------------------------------------------------------------------------------------------
+def _params_struct(cls, tensors: dict):
+    keep = []
+    s = cls()
+    for name, _ in cls._fields_:
+        t = tensors.get(name)
+        if t is None:
+            setattr(s, name, None)
+            continue
+        t = t.detach()
+        if not t.is_contiguous():
+            t = t.contiguous()
+        keep.append(t)
+        setattr(s, name, dptr(t, name))
+    return s, keep
+
+
+def lka3d_deform_forward(params: dict, x: torch.Tensor, math=None) -> torch.Tensor:
+    """LKA3d_deform.forward on NCDHW input (transformerblock.py:644-652)."""
+    if x.dim() != 5:
+        raise RuntimeError("expected a 5-D NCDHW tensor")
+    x = x.contiguous()
+    B, C, D1, D2, D3 = x.shape
+    y = torch.empty_like(x)
+    s, keep = _params_struct(Block3dParams, params)
+    ws = Workspace.get(x.device, lib.dlka_lka3d_deform_workspace_bytes(B, C, D1, D2, D3))
+    with torch.cuda.device(x.device):
+        st = lib.dlka_lka3d_deform_forward(ctypes.byref(s), dptr(x, "x"), dptr(y), B, C, D1, D2, D3, _math(math),
+                                           ws.data_ptr(), ws.numel(), stream_ptr(x.device))
+    check(st, "dlka_lka3d_deform_forward")
+    return y
+
+
+def lka_attention3d_deform_forward(params: dict, x: torch.Tensor, B: int, C: int, H: int, W: int, D: int,
+                                   math=None) -> torch.Tensor:
+    """LKA_Attention3d_deform.forward on tokens [B, N, C], N = H*W*D (transformerblock.py:664-673)."""
+    if x.dim() != 3 or x.shape[0] != B or x.shape[1] != H * W * D or x.shape[2] != C:
+        raise RuntimeError(f"expected tokens of shape {(B, H * W * D, C)}, got {tuple(x.shape)}")
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    s, keep = _params_struct(Block3dParams, params)
+    ws = Workspace.get(x.device, lib.dlka_lka_attention3d_deform_workspace_bytes(B, C, H, W, D))
+    with torch.cuda.device(x.device):
+        st = lib.dlka_lka_attention3d_deform_forward(ctypes.byref(s), dptr(x, "x"), dptr(y), B, C, H, W, D, _math(math),
+                                                     ws.data_ptr(), ws.numel(), stream_ptr(x.device))
+    check(st, "dlka_lka_attention3d_deform_forward")
+    return y
+
+
+def lka_attention3d_deform_forward_host(params: dict, x_host: torch.Tensor, y_host: torch.Tensor, B, C, H, W, D,
+                                        device, math=None) -> torch.Tensor:
+    """Host-buffer variant: x_host / y_host are CPU (ideally pinned) fp32 tensors; parameters live on `device`."""
+    assert x_host.device.type == "cpu" and y_host.device.type == "cpu" and x_host.is_contiguous() and y_host.is_contiguous()
+    device = torch.device(device)
+    n = B * H * W * D * C
+    s, keep = _params_struct(Block3dParams, params)
+    dev_scratch = _HostScratch.get(device, 2 * n * 4)
+    ws = Workspace.get(device, lib.dlka_lka_attention3d_deform_workspace_bytes(B, C, H, W, D))
+    with torch.cuda.device(device):
+        st = lib.dlka_lka_attention3d_deform_forward_host(
+            ctypes.byref(s), x_host.data_ptr(), y_host.data_ptr(), B, C, H, W, D, _math(math),
+            dev_scratch.data_ptr(), dev_scratch.numel(), ws.data_ptr(), ws.numel(), stream_ptr(device))
+    check(st, "dlka_lka_attention3d_deform_forward_host")
+    return y_host
+
+
+class _HostScratch:
+    _bufs = {}
+
+    @classmethod
+    def get(cls, device, nbytes):
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        b = cls._bufs.get(key)
+        if b is None or b.numel() < nbytes:
+            cls._bufs[key] = None
+            b = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            cls._bufs[key] = b
+        return b
+
+
+def deformable_lka2d_forward(params: dict, x: torch.Tensor, math=None) -> torch.Tensor:
+    """deformable_LKA.forward on NCHW input (deformable_LKA.py:98-104)."""
+    if x.dim() != 4:
+        raise RuntimeError("expected a 4-D NCHW tensor")
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    y = torch.empty_like(x)
+    s, keep = _params_struct(Block2dParams, params)
+    ws = Workspace.get(x.device, lib.dlka_deformable_lka2d_workspace_bytes(B, C, H, W))
+    with torch.cuda.device(x.device):
+        st = lib.dlka_deformable_lka2d_forward(ctypes.byref(s), dptr(x, "x"), dptr(y), B, C, H, W, _math(math),
+                                               ws.data_ptr(), ws.numel(), stream_ptr(x.device))
+    check(st, "dlka_deformable_lka2d_forward")
+    return y
+
+
+def deformable_lka_attention2d_forward(params: dict, x: torch.Tensor, math=None) -> torch.Tensor:
+    """deformable_LKA_Attention.forward on NCHW input (deformable_LKA.py:133-140)."""
+    if x.dim() != 4:
+        raise RuntimeError("expected a 4-D NCHW tensor")
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    y = torch.empty_like(x)
+    s, keep = _params_struct(Block2dParams, params)
+    ws = Workspace.get(x.device, lib.dlka_deformable_lka_attention2d_workspace_bytes(B, C, H, W))
+    with torch.cuda.device(x.device):
+        st = lib.dlka_deformable_lka_attention2d_forward(ctypes.byref(s), dptr(x, "x"), dptr(y), B, C, H, W, _math(math),
+                                                         ws.data_ptr(), ws.numel(), stream_ptr(x.device))
+    check(st, "dlka_deformable_lka_attention2d_forward")
+    return y

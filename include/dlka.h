@@ -1,0 +1,215 @@
+/*
+ * dlka.h -- C ABI of libdlka_b200.so: B200 (sm_100a) Deformable-LKA forward operators.
+ *
+ * Drop-in boundary for the D-LKA hot path of xmindflow/deformableLKA.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All tensors are fp32, contiguous.
+ *   - pointers are DEVICE pointers unless the function name ends in `_host`.
+ *   - the library allocates nothing on the device: the caller passes a workspace whose size
+ *     is returned by the matching `*_workspace_bytes` query (0 is a legal answer).
+ *   - `stream` is a cudaStream_t passed as void* (the reference launches on the caller's
+ *     current stream: 3D/dcn/src/cuda/deform_conv_cuda.cu:97).
+ *   - return value: DLKA_OK (0) or a negative dlkaStatus; `dlka_status_string` gives the text the
+ *     Python host raises as RuntimeError (the reference raises c10::Error -> RuntimeError,
+ *     3D/dcn/src/cuda/deform_conv_cuda.cu:41-76).
+ *   - there is NO CPU path: without a CUDA device every compute entry point returns
+ *     DLKA_ERR_NO_DEVICE (the reference's 3D op is CUDA-only too: 3D/dcn/src/deform_conv.h:46).
+ *   - 64-bit addressing throughout (the reference's int32 index math overflows at
+ *     (2,96,64,128,128): 3D/dcn/src/cuda/deform_im2col_cuda.cuh:228).
+ */
+#ifndef DLKA_H_
+#define DLKA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLKA_VERSION 100 /* major*1000 + minor*10 */
+
+#if defined(__GNUC__)
+#define DLKA_API __attribute__((visibility("default")))
+#else
+#define DLKA_API
+#endif
+
+typedef enum dlkaStatus {
+    DLKA_OK = 0,
+    DLKA_ERR_INVALID_ARGUMENT = -1, /* bad shape / null pointer / size mismatch            */
+    DLKA_ERR_UNSUPPORTED = -2,      /* legal in the reference, not implemented here (loud) */
+    DLKA_ERR_WORKSPACE = -3,        /* workspace missing or too small                      */
+    DLKA_ERR_NO_DEVICE = -4,        /* no CUDA device / not sm_100                         */
+    DLKA_ERR_CUDA = -5              /* a CUDA runtime call or launch failed                */
+} dlkaStatus;
+
+/* Arithmetic used for the channel contractions (1x1 projections, offset conv, deformable GEMM).
+ * Sampling positions / interpolation weights / depthwise stencils are always fp32.           */
+typedef enum dlkaMath {
+    DLKA_MATH_FP32_SIMT = 0, /* fp32 FMA on CUDA cores (validation path, slow)                       */
+    DLKA_MATH_BF16X3 = 1     /* tcgen05 tensor cores, bf16 hi/lo split (3 MMAs), fp32 accumulate     */
+} dlkaMath;
+
+DLKA_API int dlka_version(void);
+DLKA_API const char *dlka_status_string(int status);
+/* last CUDA error text seen by this thread (empty string if none) */
+DLKA_API const char *dlka_last_cuda_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
+DLKA_API uint64_t dlka_launch_count(void);
+/* Optional per-kernel timing: while enabled every kernel launch is bracketed by CUDA events on its
+ * stream; dlka_profile_summary synchronises them and writes "name launches total_ms\n" lines.  */
+DLKA_API int dlka_profile_enable(int on);
+DLKA_API int dlka_profile_summary(char *buf, size_t buf_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator: 3D deformable convolution forward.
+ * Replaces  D3D.deform_conv_forward  (3D/dcn/src/vision.cpp:4-7, 3D/dcn/src/deform_conv.h:10-47,
+ *           3D/dcn/src/cuda/deform_conv_cuda.cu:18-126) as called by DeformConvFunction.forward
+ *           (3D/dcn/functions/deform_conv_func.py:17-36).
+ *   input  [B, C, D, H, W]            weight [Co, C/group, kd, kh, kw]     bias [Co] (required)
+ *   offset [B, dg*3*K, Do, Ho, Wo]    channel 3t+{0,1,2} = (dd,dh,dw) of tap t=(i*kh+j)*kw+k
+ *   output [B, Co, Do, Ho, Wo]        Do = (D + 2*pd - (dild*(kd-1)+1))/sd + 1  (cu:78-80)
+ * `im2col_step` is accepted for signature parity; only its divisibility rule is enforced
+ * (batch % min(batch, im2col_step) == 0, cu:61-63): no im2col buffer exists here.
+ * ------------------------------------------------------------------------------------------ */
+DLKA_API size_t dlka_deform_conv3d_workspace_bytes(int B, int C, int D, int H, int W, int Co,
+                                          int kd, int kh, int kw, int sd, int sh, int sw,
+                                          int pd, int ph, int pw, int dild, int dilh, int dilw,
+                                          int group, int deformable_group);
+DLKA_API int dlka_deform_conv3d_forward(const float *input, const float *weight, const float *bias,
+                               const float *offset, float *output,
+                               int B, int C, int D, int H, int W, int Co,
+                               int kd, int kh, int kw, int sd, int sh, int sw,
+                               int pd, int ph, int pw, int dild, int dilh, int dilw,
+                               int group, int deformable_group, int im2col_step, int math,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
+/* Integer planes of the 3D sampler for bit-exact parity checks:
+ *   low [B*dg, Vo, K, 3] int32 = floor(p) per axis,  mask [B*dg, Vo, K] int32:
+ *   bit0 = sample valid (cuh:248), bits 1..8 = corner v1..v8 read (cuh:43-65).
+ * Uses the same device function as the convolution kernels.                                  */
+DLKA_API int dlka_deform_conv3d_sample_indices(const float *offset, int32_t *low, int32_t *mask,
+                                      int B, int D, int H, int W, int kd, int kh, int kw,
+                                      int sd, int sh, int sw, int pd, int ph, int pw,
+                                      int dild, int dilh, int dilw, int deformable_group, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator: 3D DeformConvPack forward = conv_offset (regular conv, dilation 1) + deformable conv.
+ * Replaces  DeformConvPack.forward  (3D/d_lka_former/network_architecture/synapse/deform_conv.py:93-105;
+ *           identical 3D/dcn/modules/deform_conv.py:88-100).
+ *   offset_weight [dg*3*K, C, kd, kh, kw], offset_bias [dg*3*K]; other arguments as the 3D operator.
+ * ------------------------------------------------------------------------------------------ */
+DLKA_API size_t dlka_deform_conv_pack3d_workspace_bytes(int B, int C, int D, int H, int W, int Co,
+                                               int kd, int kh, int kw, int sd, int sh, int sw,
+                                               int pd, int ph, int pw, int dild, int dilh, int dilw,
+                                               int group, int deformable_group);
+DLKA_API int dlka_deform_conv_pack3d_forward(const float *input, const float *offset_weight, const float *offset_bias,
+                                    const float *weight, const float *bias, float *output,
+                                    int B, int C, int D, int H, int W, int Co,
+                                    int kd, int kh, int kw, int sd, int sh, int sw,
+                                    int pd, int ph, int pw, int dild, int dilh, int dilw,
+                                    int group, int deformable_group, int im2col_step, int math,
+                                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator: 2D deformable convolution forward (DCNv1 when mask == NULL, DCNv2 otherwise).
+ * Replaces  torch.ops.torchvision.deform_conv2d  as called from
+ *           2D/deformable_LKA/deformable_LKA.py:18-25,29 (torchvision/ops/deform_conv.py:92-107).
+ *   input [B,C,H,W]  weight [Co, C/n_weight_grps, kh, kw]  offset [B, n_offset_grps*2*K, Ho, Wo]
+ *   (channel 2t = dy, 2t+1 = dx, t = i*kw+j)   mask [B, n_offset_grps*K, Ho, Wo] or NULL
+ *   bias [Co] or NULL    output [B, Co, Ho, Wo]
+ * ------------------------------------------------------------------------------------------ */
+DLKA_API size_t dlka_deform_conv2d_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw,
+                                          int sh, int sw, int ph, int pw, int dilh, int dilw,
+                                          int n_weight_grps, int n_offset_grps);
+DLKA_API int dlka_deform_conv2d_forward(const float *input, const float *weight, const float *offset,
+                               const float *mask, const float *bias, float *output,
+                               int B, int C, int H, int W, int Co, int kh, int kw,
+                               int sh, int sw, int ph, int pw, int dilh, int dilw,
+                               int n_weight_grps, int n_offset_grps, int math,
+                               void *workspace, size_t workspace_bytes, void *stream);
+DLKA_API int dlka_deform_conv2d_sample_indices(const float *offset, int32_t *low, int32_t *mask,
+                                      int B, int H, int W, int kh, int kw, int sh, int sw,
+                                      int ph, int pw, int dilh, int dilw, int n_offset_grps, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator: 2D DeformConv wrapper forward = offset_net (regular conv with the SAME kernel / stride /
+ * padding / dilation) + deformable conv without mask.
+ * Replaces  DeformConv.forward  (2D/deformable_LKA/deformable_LKA.py:27-30).
+ *   offset_weight [2*K, C, kh, kw], offset_bias [2*K]; weight [Co, C/groups, kh, kw]; bias [Co] or NULL.
+ * ------------------------------------------------------------------------------------------ */
+DLKA_API size_t dlka_deform_conv_pack2d_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw,
+                                               int sh, int sw, int ph, int pw, int dilh, int dilw, int groups);
+DLKA_API int dlka_deform_conv_pack2d_forward(const float *input, const float *offset_weight, const float *offset_bias,
+                                    const float *weight, const float *bias, float *output,
+                                    int B, int C, int H, int W, int Co, int kh, int kw,
+                                    int sh, int sw, int ph, int pw, int dilh, int dilw, int groups, int math,
+                                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Block: 3D D-LKA.  Parameters in the reference's state_dict layout (device pointers).
+ * Replaces  LKA3d_deform.forward            (3D/d_lka_former/network_architecture/synapse/transformerblock.py:644-652)
+ *      and  LKA_Attention3d_deform.forward  (same file :664-673).
+ * The attention parameters (proj_1 / proj_2) are ignored by dlka_lka3d_deform_forward.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dlkaBlock3dParams {
+    const float *proj_1_weight, *proj_1_bias;             /* [C,C,1,1,1], [C]   transformerblock.py:659 */
+    const float *conv0_weight, *conv0_bias;               /* [C,1,5,5,5], [C]   :637 (pad 2)            */
+    const float *conv_spatial_weight, *conv_spatial_bias; /* [C,1,7,7,7], [C]   :638 (pad 9, dil 3)     */
+    const float *conv_offset_weight, *conv_offset_bias;   /* [81,C,3,3,3], [81] synapse/deform_conv.py:80-85 */
+    const float *deform_weight, *deform_bias;             /* [C,C,3,3,3], [C]   synapse/deform_conv.py:37-39 */
+    const float *conv1_weight, *conv1_bias;               /* [C,C,1,1,1], [C]   :641                    */
+    const float *proj_2_weight, *proj_2_bias;             /* [C,C,1,1,1], [C]   :662                    */
+} dlkaBlock3dParams;
+
+/* x, y: [B, C, D1, D2, D3] (NCDHW as nn.Conv3d sees it). */
+DLKA_API size_t dlka_lka3d_deform_workspace_bytes(int B, int C, int D1, int D2, int D3);
+DLKA_API int dlka_lka3d_deform_forward(const dlkaBlock3dParams *params, const float *x, float *y,
+                              int B, int C, int D1, int D2, int D3, int math,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
+/* x, y: tokens [B, N, C] with N = D1*D2*D3 (the reference calls the three axes H, W, D; token
+ * n = (i1*D2 + i2)*D3 + i3, i.e. channels-last over the Conv3d volume [D1,D2,D3]).            */
+DLKA_API size_t dlka_lka_attention3d_deform_workspace_bytes(int B, int C, int D1, int D2, int D3);
+DLKA_API int dlka_lka_attention3d_deform_forward(const dlkaBlock3dParams *params, const float *x, float *y,
+                                        int B, int C, int D1, int D2, int D3, int math,
+                                        void *workspace, size_t workspace_bytes, void *stream);
+/* Same call with HOST buffers (x_host, y_host pinned or pageable): H2D, compute, D2H on `stream`,
+ * then stream-synchronised.  `params` still holds device pointers; `dev_scratch` must hold
+ * 2*B*N*C floats in addition to the workspace (x and y staging).                               */
+DLKA_API int dlka_lka_attention3d_deform_forward_host(const dlkaBlock3dParams *params, const float *x_host,
+                                             float *y_host, int B, int C, int D1, int D2, int D3, int math,
+                                             void *dev_scratch, size_t dev_scratch_bytes,
+                                             void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Block: 2D D-LKA.
+ * Replaces  deformable_LKA.forward            (2D/deformable_LKA/deformable_LKA.py:98-104)
+ *      and  deformable_LKA_Attention.forward  (2D/deformable_LKA/deformable_LKA.py:133-140).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dlkaBlock2dParams {
+    const float *proj_1_weight, *proj_1_bias;                   /* [C,C,1,1], [C]        :127 */
+    const float *conv0_offset_weight, *conv0_offset_bias;       /* [50,C,5,5], [50]      :10-16,93 */
+    const float *conv0_deform_weight;                           /* [C,1,5,5] (no bias)   :18-25 */
+    const float *conv_spatial_offset_weight, *conv_spatial_offset_bias; /* [98,C,7,7], [98] (dil 3, pad 9) :94 */
+    const float *conv_spatial_deform_weight;                    /* [C,1,7,7]                  */
+    const float *conv1_weight, *conv1_bias;                     /* [C,C,1,1], [C]        :95  */
+    const float *proj_2_weight, *proj_2_bias;                   /* [C,C,1,1], [C]        :130 */
+} dlkaBlock2dParams;
+
+DLKA_API size_t dlka_deformable_lka2d_workspace_bytes(int B, int C, int H, int W);
+DLKA_API int dlka_deformable_lka2d_forward(const dlkaBlock2dParams *params, const float *x, float *y,
+                                  int B, int C, int H, int W, int math,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+DLKA_API size_t dlka_deformable_lka_attention2d_workspace_bytes(int B, int C, int H, int W);
+DLKA_API int dlka_deformable_lka_attention2d_forward(const dlkaBlock2dParams *params, const float *x, float *y,
+                                            int B, int C, int H, int W, int math,
+                                            void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLKA_H_ */

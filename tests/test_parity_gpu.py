@@ -1,0 +1,286 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, the golden vectors of the
+unmodified reference 2D module, and size-independent properties at full size.
+
+Tolerance (north_star): outputs within 1e-3 relative fp32, measured as max|got-ref| / max|ref|;
+integer sampling planes bit-exact.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+DEV = "cuda:0"
+
+
+def rel_err(got, ref):
+    got = got.detach().float().cpu(); ref = ref.detach().float().cpu()
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def dl():
+    import deformablelka_b200 as d
+    return d
+
+
+MATHS = ["fp32", "bf16x3"]
+
+
+@pytest.fixture(params=MATHS)
+def math(request, monkeypatch):
+    monkeypatch.setenv("DLKA_MATH", request.param)
+    return request.param
+
+
+# ----------------------------------------------------------------------------- golden (reference 2D module)
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref2d_*.npz"))), ids=os.path.basename)
+def test_golden_2d(dl, path, math):
+    z = np.load(path)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    x, y = torch.from_numpy(z["x"]), torch.from_numpy(z["y"])
+    cls = dl.deformable_LKA if "_lka_" in os.path.basename(path) else dl.deformable_LKA_Attention
+    m = cls(x.shape[1])
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        got = m(x.to(DEV))
+    assert got.shape == y.shape
+    assert rel_err(got, y) < TOL
+
+
+# ----------------------------------------------------------------------------- 2D operator vs torchvision (CPU)
+@pytest.mark.parametrize("C,Co,wg,og,k,stride,pad,dil,use_mask,use_bias", [
+    (8, 8, 1, 1, (3, 3), 1, 1, 1, False, True),
+    (16, 16, 16, 1, (5, 5), 1, 2, 1, False, False),       # depthwise, as conv0
+    (16, 16, 16, 1, (7, 7), 1, 9, 3, False, False),       # depthwise dilated, as conv_spatial
+    (16, 8, 2, 2, (3, 5), (1, 2), (2, 3), (2, 1), True, True),
+    (8, 8, 8, 2, (3, 3), 2, 1, 1, True, True),             # depthwise + 2 offset groups + mask
+])
+def test_deform_conv2d_vs_torchvision(dl, C, Co, wg, og, k, stride, pad, dil, use_mask, use_bias):
+    import torchvision
+    torch.manual_seed(0)
+    B, H, W = 2, 13, 11
+    kh, kw = k
+    x = torch.randn(B, C, H, W)
+    w = torch.randn(Co, C // wg, kh, kw)
+    b = torch.randn(Co) if use_bias else None
+    from oracle import oracle as o
+    sh, sw = o._pair(stride); ph, pw = o._pair(pad); dh, dw = o._pair(dil)
+    Ho, Wo = o.out_extent(H, ph, dh, kh, sh), o.out_extent(W, pw, dw, kw, sw)
+    off = torch.randn(B, og * 2 * kh * kw, Ho, Wo) * 3
+    mask = torch.rand(B, og * kh * kw, Ho, Wo) if use_mask else None
+    ref = torchvision.ops.deform_conv2d(x, off, w, b, stride, pad, dil, mask)
+    got = dl.ops.deform_conv2d(x.to(DEV), off.to(DEV), w.to(DEV), None if b is None else b.to(DEV), stride, pad, dil,
+                               None if mask is None else mask.to(DEV))
+    assert rel_err(got, ref) < TOL
+
+
+def test_deform_conv2d_module_mirrors_torchvision_module(dl):
+    import torchvision
+    torch.manual_seed(1)
+    ref = torchvision.ops.DeformConv2d(8, 8, 3, padding=1, groups=8, bias=False)
+    mine = dl.DeformConv2d(8, 8, 3, padding=1, groups=8, bias=False)
+    mine.load_state_dict(ref.state_dict())
+    x = torch.randn(1, 8, 9, 9); off = torch.randn(1, 18, 9, 9)
+    assert rel_err(mine.to(DEV)(x.to(DEV), off.to(DEV)), ref(x, off)) < TOL
+
+
+# ----------------------------------------------------------------------------- 3D operator vs oracle
+@pytest.mark.parametrize("C,Co,g,dg,k,stride,pad,dil,scale", [
+    (8, 8, 1, 1, 3, 1, 1, 1, 0.0),      # K1: zero offsets == plain conv
+    (8, 8, 1, 1, 3, 1, 1, 1, 1.0),
+    (16, 12, 1, 1, 3, 1, 1, 1, 8.0),    # many samples out of bounds
+    (16, 16, 2, 2, (3, 2, 3), (1, 2, 1), (1, 0, 2), (1, 2, 1), 2.0),
+    (8, 8, 8, 1, 5, 1, 2, 1, 1.5),      # depthwise deformable 3D (3D/dcn/test.py:28)
+])
+def test_deform_conv3d_vs_oracle(dl, oracle, C, Co, g, dg, k, stride, pad, dil, scale):
+    torch.manual_seed(2)
+    B, D, H, W = 2, 6, 7, 9
+    kd, kh, kw = oracle._triple(k)
+    sd, sh, sw = oracle._triple(stride); pd, ph, pw = oracle._triple(pad); dd, dh, dw = oracle._triple(dil)
+    Do, Ho, Wo = oracle.out_extent(D, pd, dd, kd, sd), oracle.out_extent(H, ph, dh, kh, sh), oracle.out_extent(W, pw, dw, kw, sw)
+    x = torch.randn(B, C, D, H, W)
+    w = torch.randn(Co, C // g, kd, kh, kw) * 0.2
+    b = torch.randn(Co)
+    off = torch.randn(B, dg * 3 * kd * kh * kw, Do, Ho, Wo) * scale
+    ref = oracle.deform_conv3d(x, off, w, b, stride, pad, dil, g, dg)
+    got = dl.ops.deform_conv3d_forward(x.to(DEV), w.to(DEV), b.to(DEV), off.to(DEV), (kd, kh, kw), stride, pad, dil, g, dg, 64)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < TOL
+    if scale == 0.0:
+        assert rel_err(got, F.conv3d(x, w, b, stride, pad, dil, g)) < TOL
+
+
+def test_deform_conv3d_module_and_function(dl, oracle):
+    torch.manual_seed(3)
+    m = dl.DeformConv3d(8, 8, 3, 1, 1).to(DEV)
+    x = torch.randn(1, 8, 5, 6, 7); off = torch.randn(1, 81, 5, 6, 7)
+    got = m(x.to(DEV), off.to(DEV))
+    ref = oracle.deform_conv3d(x, off, m.weight.detach().cpu(), m.bias.detach().cpu(), 1, 1, 1)
+    assert rel_err(got, ref) < TOL
+    got2 = dl.DeformConvFunction.apply(x.to(DEV), off.to(DEV), m.weight, m.bias, 1, 1, 1, 1, 1, 64)
+    assert torch.equal(got, got2)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        dl.ops.deform_conv3d_forward(x.to(DEV).transpose(3, 4), m.weight, m.bias, off.to(DEV), 3, 1, 1, 1, 1, 1)
+    with pytest.raises(RuntimeError, match="must divide im2col_step"):
+        dl.ops.deform_conv3d_forward(x.to(DEV).repeat(3, 1, 1, 1, 1), m.weight, m.bias, off.to(DEV).repeat(3, 1, 1, 1, 1),
+                                     3, 1, 1, 1, 1, 1, im2col_step=2)
+
+
+def test_k3_fresh_pack_equals_conv3d(dl):
+    torch.manual_seed(4)
+    m = dl.DeformConvPack(8, 8, (3, 3, 3), 1, 1).to(DEV)
+    x = torch.randn(2, 8, 5, 6, 7)
+    got = m(x.to(DEV))
+    ref = F.conv3d(x, m.weight.detach().cpu(), m.bias.detach().cpu(), 1, 1)
+    assert rel_err(got, ref) < TOL
+
+
+def test_pack3d_vs_oracle(dl, oracle):
+    torch.manual_seed(5)
+    m = dl.DeformConvPack(8, 12, (3, 3, 3), 1, 1)
+    oracle.randomize_offsets_(m, std=0.1, bias_range=1.5)
+    om = oracle.DeformConvPack3D(8, 12, (3, 3, 3), 1, 1)
+    om.load_state_dict(m.state_dict())
+    x = torch.randn(2, 8, 6, 5, 7)
+    with torch.no_grad():
+        ref = om(x)
+        got = m.to(DEV)(x.to(DEV))
+    assert rel_err(got, ref) < TOL
+
+
+def test_pack2d_vs_oracle(dl, oracle):
+    torch.manual_seed(6)
+    m = dl.DeformConv(8, groups=8, kernel_size=(7, 7), padding=9, dilation=3)
+    om = oracle.DeformConv2D(8, groups=8, kernel_size=(7, 7), padding=9, dilation=3)
+    om.load_state_dict(m.state_dict())
+    x = torch.randn(2, 8, 20, 17)
+    with torch.no_grad():
+        ref = om(x)
+        got = m.to(DEV)(x.to(DEV))
+    assert rel_err(got, ref) < TOL
+
+
+# ----------------------------------------------------------------------------- K4: integer planes, bit exact
+@pytest.mark.parametrize("scale", [0.5, 3.0, 40.0])
+def test_sample_indices3d_bit_exact(dl, oracle, scale):
+    torch.manual_seed(7)
+    D, H, W = 5, 6, 7
+    off = torch.randn(2, 2 * 81, D, H, W) * scale
+    off[0, :, 0, 0, 0] = torch.round(off[0, :, 0, 0, 0])  # exactly integral positions
+    off[0, :3, 1, 1, 1] = torch.tensor([-1.0, -1.0, -1.0])  # p == -1 boundary on tap 0 at voxel (1,1,1): p = 1-1-1 = -1
+    lo_ref, m_ref = oracle.sample_indices3d(off, (D, H, W), 3, 1, 1, 1, deformable_groups=2)
+    lo, m = dl.ops.deform_conv3d_sample_indices(off.to(DEV), (D, H, W), 3, 1, 1, 1, deformable_group=2)
+    assert torch.equal(m.cpu(), m_ref)
+    valid = (m_ref & 1).bool()
+    assert valid.any() and (~valid).any()
+    assert torch.equal(lo.cpu()[valid], lo_ref[valid])
+
+
+def test_sample_indices2d_bit_exact(dl, oracle):
+    torch.manual_seed(8)
+    H, W = 9, 8
+    off = torch.randn(2, 98, H, W) * 4
+    lo_ref, m_ref = oracle.sample_indices2d(off, (H, W), 7, 1, 9, 3)
+    lo, m = dl.ops.deform_conv2d_sample_indices(off.to(DEV), (H, W), 7, 1, 9, 3)
+    assert torch.equal(m.cpu(), m_ref)
+    valid = (m_ref & 1).bool()
+    assert torch.equal(lo.cpu()[valid], lo_ref[valid])
+
+
+# ----------------------------------------------------------------------------- blocks vs oracle
+def _scale_offset_nets(m, scale):
+    with torch.no_grad():
+        for name, mod in m.named_modules():
+            if name.endswith("offset_net"):
+                mod.weight.mul_(scale); mod.bias.mul_(scale)
+
+
+@pytest.mark.parametrize("C,H,W,scale", [(8, 14, 12, 1.0), (64, 20, 24, 1.0), (96, 12, 10, 4.0), (12, 9, 21, 8.0)])
+def test_block2d_vs_oracle(dl, oracle, C, H, W, scale, math):
+    torch.manual_seed(9)
+    ref_m = oracle.deformable_LKA_Attention(C).eval()
+    _scale_offset_nets(ref_m, scale)
+    m = dl.deformable_LKA_Attention(C)
+    m.load_state_dict(ref_m.state_dict())
+    x = torch.randn(2, C, H, W)
+    with torch.no_grad():
+        ref = ref_m(x)
+        got = m.to(DEV)(x.to(DEV))
+        ref_l = ref_m.spatial_gating_unit(x)
+        got_l = m.spatial_gating_unit(x.to(DEV))
+    assert rel_err(got, ref) < TOL
+    assert rel_err(got_l, ref_l) < TOL
+
+
+@pytest.mark.parametrize("C,dims,std,br", [(8, (6, 5, 4), 0.0, 0.0), (32, (8, 8, 8), 0.05, 1.0), (64, (4, 6, 5), 0.05, 1.0),
+                                           (96, (5, 9, 8), 0.1, 6.0), (128, (4, 4, 4), 0.05, 1.0), (256, (4, 4, 4), 0.05, 1.0)])
+def test_block3d_vs_oracle(dl, oracle, C, dims, std, br, math):
+    torch.manual_seed(10)
+    H, W, D = dims
+    B = 2
+    ref_m = oracle.LKA_Attention3d_deform(C).eval()
+    if std > 0:
+        oracle.randomize_offsets_(ref_m, std=std, bias_range=br)
+    m = dl.LKA_Attention3d_deform(C)
+    m.load_state_dict(ref_m.state_dict())
+    m = m.to(DEV)
+    x = torch.randn(B, H * W * D, C)
+    with torch.no_grad():
+        ref = ref_m(x, B, C, H, W, D)
+        got = m(x.to(DEV), B, C, H, W, D)
+        xv = torch.randn(B, C, H, W, D)
+        ref_l = ref_m.spatial_gating_unit(xv)
+        got_l = m.spatial_gating_unit(xv.to(DEV))
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < TOL
+    assert rel_err(got_l, ref_l) < TOL
+
+
+# ----------------------------------------------------------------------------- properties at larger size
+def test_block3d_batch_shard_consistency_and_identity(dl, oracle, math):
+    """Size-independent properties on a mid-size volume: (a) B=2 equals two B=1 runs (the data-parallel
+    split of SURVEY.md 8e is exact); (b) zero-initialised conv_offset == the same block with a plain
+    Conv3d run by torch on the GPU (K3 at block level)."""
+    torch.manual_seed(11)
+    C, H, W, D = 32, 24, 20, 28
+    m = dl.LKA_Attention3d_deform(C).to(DEV)
+    x = torch.randn(2, H * W * D, C, device=DEV)
+    with torch.no_grad():
+        y = m(x, 2, C, H, W, D)
+        y0 = m(x[:1].contiguous(), 1, C, H, W, D)
+        y1 = m(x[1:].contiguous(), 1, C, H, W, D)
+        assert torch.equal(y, torch.cat([y0, y1]))
+        sg = m.spatial_gating_unit
+        xx = x.permute(0, 2, 1).reshape(2, C, H, W, D)
+        prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            t = F.gelu(m.proj_1(xx))
+            a = F.conv3d(sg.conv_spatial(sg.conv0(t)), sg.deform_conv.weight, sg.deform_conv.bias, 1, 1)
+            ref = (m.proj_2(t * sg.conv1(a)) + xx).reshape(2, C, -1).permute(0, 2, 1)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    assert rel_err(y, ref) < TOL
+
+
+def test_streams_and_noncontiguous_inputs(dl):
+    torch.manual_seed(12)
+    m = dl.deformable_LKA_Attention(16).to(DEV)
+    x = torch.randn(2, 16, 10, 12, device=DEV)
+    y = m(x)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        y2 = m(x)
+    s.synchronize()
+    assert torch.equal(y, y2)
+    xt = x.permute(0, 1, 3, 2)  # non-contiguous view: the host makes it contiguous like nn.Conv2d would accept
+    assert torch.equal(m(xt), m(xt.contiguous()))
+    assert dl.launch_count() > 0

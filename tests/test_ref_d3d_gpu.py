@@ -1,0 +1,62 @@
+"""Pin the oracle AND the product against the reference's own D3D extension, compiled for sm_100a by
+oracle/build_ref.py into oracle/_ref/ (two-token torch-2 patch, see that file).  D3D is CUDA-only, so
+this runs on the GPU box only; it is skipped when oracle/_ref was not built."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def d3d():
+    from oracle import build_ref
+    mod = build_ref.load_d3d()
+    if mod is None:
+        pytest.skip("oracle/_ref/D3D*.so not built")
+    return mod
+
+
+def _ref(d3d, x, w, b, off, k, s, p, d, g, dg):
+    k = (k,) * 3 if isinstance(k, int) else k
+    s = (s,) * 3 if isinstance(s, int) else s
+    p = (p,) * 3 if isinstance(p, int) else p
+    d = (d,) * 3 if isinstance(d, int) else d
+    return d3d.deform_conv_forward(x, w, b, off, *k, *s, *p, *d, g, dg, 64)
+
+
+def rel_err(a, b):
+    a = a.float().cpu(); b = b.float().cpu()
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+@pytest.mark.parametrize("C,Co,g,dg,k,s,p,d,scale", [
+    (8, 8, 1, 1, 3, 1, 1, 1, 1.0),
+    (16, 12, 1, 1, 3, 1, 1, 1, 8.0),
+    (16, 16, 2, 2, (3, 2, 3), (1, 2, 1), (1, 0, 2), (1, 2, 1), 2.0),
+])
+def test_oracle_matches_compiled_reference(d3d, oracle, C, Co, g, dg, k, s, p, d, scale):
+    torch.manual_seed(0)
+    B, D, H, W = 2, 6, 7, 9
+    kd, kh, kw = oracle._triple(k); sd, sh, sw = oracle._triple(s); pd, ph, pw = oracle._triple(p); dd, dh, dw = oracle._triple(d)
+    Do, Ho, Wo = oracle.out_extent(D, pd, dd, kd, sd), oracle.out_extent(H, ph, dh, kh, sh), oracle.out_extent(W, pw, dw, kw, sw)
+    x = torch.randn(B, C, D, H, W); w = torch.randn(Co, C // g, kd, kh, kw) * 0.2; b = torch.randn(Co)
+    off = torch.randn(B, dg * 3 * kd * kh * kw, Do, Ho, Wo) * scale
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = _ref(d3d, x.to(DEV), w.to(DEV), b.to(DEV), off.to(DEV), k, s, p, d, g, dg)
+    ora = oracle.deform_conv3d(x, off, w, b, s, p, d, g, dg)
+    assert rel_err(ora, ref) < 1e-5
+
+
+def test_product_matches_compiled_reference_at_c3_shape(d3d):
+    """BASELINE config 3: (2,64,32,64,64), k=3 -- the largest shape class the reference's int32 indexing survives."""
+    import deformablelka_b200 as dl
+    torch.manual_seed(1)
+    B, C, D, H, W = 2, 64, 32, 64, 64
+    x = torch.randn(B, C, D, H, W, device=DEV); w = torch.randn(C, C, 3, 3, 3, device=DEV) * 0.05
+    b = torch.randn(C, device=DEV); off = torch.randn(B, 81, D, H, W, device=DEV)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = _ref(d3d, x, w, b, off, 3, 1, 1, 1, 1, 1)
+    for math in ("fp32", "bf16x3"):
+        got = dl.ops.deform_conv3d_forward(x, w, b, off, 3, 1, 1, 1, 1, 1, 64, math=math)
+        assert rel_err(got, ref) < 1e-3, math
