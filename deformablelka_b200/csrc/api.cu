@@ -88,6 +88,28 @@ IgemmArgs conv_args(int mode, const ConvGeo &g, const float *X, const float *Off
     return a;
 }
 
+// One channel contraction: packs the weight (reference layout [Co][C/g][taps]) into `wscratch` and runs the
+// tensor-core kernel (DLKA_MATH_BF16X3, when the shape qualifies) or the exact fp32 SIMT kernel.
+size_t contraction_scratch_floats(int Co, int C, int taps, int groups)
+{
+    const size_t simt = (size_t)groups * taps * (C / groups) * igemm_simt_npad(Co / groups);
+    const size_t tc = (groups == 1 && tc_kc(C) != 0) ? tc_packed_weight_bytes(Co, C, taps) / sizeof(float) : 0;
+    return (simt > tc ? simt : tc) + 64;
+}
+
+int contraction(IgemmArgs a, const float *w, int math, float *wscratch, cudaStream_t st)
+{
+    const ConvGeo &g = a.geo;
+    if (math == DLKA_MATH_BF16X3 && tc_supported(a)) {
+        DLKA_TRY(tc_pack_weight(w, wscratch, g.Co, g.C, g.K, st));
+        return igemm_tc(a, wscratch, st);
+    }
+    a.Npad = igemm_simt_npad(g.Co / g.groups);
+    a.Wp = wscratch;
+    DLKA_TRY(pack_weight(w, wscratch, g.Co, g.C / g.groups, g.K, g.groups, a.Npad, st));
+    return igemm_simt(a, st);
+}
+
 bool bad_geo(const ConvGeo &g)
 {
     return g.B <= 0 || g.C <= 0 || g.Co <= 0 || g.D <= 0 || g.H <= 0 || g.W <= 0 || g.kd <= 0 || g.kh <= 0 || g.kw <= 0 ||
@@ -110,20 +132,17 @@ bool plan_deform_op(Arena &ar, const ConvGeo &g, bool has_mask, DeformOpPlan &p)
     p.off_cl = ar.take<float>((size_t)M * g.dg * g.ndim * g.K);
     p.mask_cl = has_mask ? ar.take<float>((size_t)M * g.dg * g.K) : nullptr;
     p.y_cl = ar.take<float>((size_t)M * g.Co);
-    if (is_depthwise(g)) {
-        p.Npad = 0;
+    p.Npad = 0;
+    if (is_depthwise(g))
         p.wp = ar.take<float>((size_t)g.K * g.C);
-    } else {
-        p.Npad = igemm_simt_npad(g.Co / g.groups);
-        p.wp = ar.take<float>((size_t)g.groups * g.K * (g.C / g.groups) * p.Npad);
-    }
+    else
+        p.wp = ar.take<float>(contraction_scratch_floats(g.Co, g.C, g.K, g.groups));
     return ar.ok();
 }
 
 int run_deform_op(const ConvGeo &g, const float *input, const float *weight, const float *bias, const float *offset,
                   const float *mask, float *output, int math, void *workspace, size_t workspace_bytes, cudaStream_t st)
 {
-    (void)math;  // the operator-level entry currently always runs the exact fp32 path
     Arena ar(workspace, workspace_bytes);
     DeformOpPlan p;
     if (!plan_deform_op(ar, g, mask != nullptr, p)) return DLKA_ERR_WORKSPACE;
@@ -135,9 +154,8 @@ int run_deform_op(const ConvGeo &g, const float *input, const float *weight, con
         DLKA_TRY(deform_dwconv_cl(p.x_cl, p.off_cl, p.mask_cl, weight, bias, p.y_cl, g, p.wp, st));
     } else {
         if ((g.C / g.groups) % 4 != 0 || (g.C / g.dg) % 4 != 0) return DLKA_ERR_UNSUPPORTED;
-        DLKA_TRY(pack_weight(weight, p.wp, g.Co, g.C / g.groups, g.K, g.groups, p.Npad, st));
-        IgemmArgs a = conv_args(IGEMM_DEFORM, g, p.x_cl, p.off_cl, p.mask_cl, p.wp, p.Npad, bias, EPI_NONE, nullptr, 0, p.y_cl, g.Co);
-        DLKA_TRY(igemm_simt(a, st));
+        IgemmArgs a = conv_args(IGEMM_DEFORM, g, p.x_cl, p.off_cl, p.mask_cl, nullptr, 0, bias, EPI_NONE, nullptr, 0, p.y_cl, g.Co);
+        DLKA_TRY(contraction(a, weight, math, p.wp, st));
     }
     DLKA_TRY(transpose_sc_to_cs(p.y_cl, output, g.B, g.Co, Vo, st));
     return DLKA_OK;
@@ -153,17 +171,16 @@ struct Block3dPlan {
 bool plan_block3d(Arena &ar, int B, int C, int D1, int D2, int D3, Block3dPlan &p)
 {
     const size_t M = (size_t)B * D1 * D2 * D3;
-    p.np_c = igemm_simt_npad(C);
-    p.np_off = igemm_simt_npad(81);
+    p.np_c = p.np_off = 0;
     p.t1 = ar.take<float>(M * C);
     p.t2 = ar.take<float>(M * C);
     p.t3 = ar.take<float>(M * C);
     p.off = ar.take<float>(M * 81);
-    p.wp_proj1 = ar.take<float>((size_t)C * p.np_c);
-    p.wp_conv1 = ar.take<float>((size_t)C * p.np_c);
-    p.wp_proj2 = ar.take<float>((size_t)C * p.np_c);
-    p.wp_off = ar.take<float>((size_t)27 * C * p.np_off);
-    p.wp_dcn = ar.take<float>((size_t)27 * C * p.np_c);
+    p.wp_proj1 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
+    p.wp_conv1 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
+    p.wp_proj2 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
+    p.wp_off = ar.take<float>(contraction_scratch_floats(81, C, 27, 1));
+    p.wp_dcn = ar.take<float>(contraction_scratch_floats(C, C, 27, 1));
     p.wp_dw5 = ar.take<float>((size_t)125 * C);
     p.wp_dw7 = ar.take<float>((size_t)343 * C);
     return ar.ok();
@@ -171,26 +188,22 @@ bool plan_block3d(Arena &ar, int B, int C, int D1, int D2, int D3, Block3dPlan &
 
 // u (channels-last, = GELU(proj_1 x) or x itself) -> gate = u * conv1(deform(dw7(dw5(u)))) into p.t3
 int run_lka3d_core(const dlkaBlock3dParams &P, const float *u, Block3dPlan &p, int B, int C, int D1, int D2, int D3,
-                   cudaStream_t st)
+                   int math, cudaStream_t st)
 {
     const i64 M = (i64)B * D1 * D2 * D3;
     DLKA_TRY(dwconv_cl(u, P.conv0_weight, P.conv0_bias, p.t2, B, C, D1, D2, D3, 5, 5, 5, 1, p.wp_dw5, st));
     DLKA_TRY(dwconv_cl(p.t2, P.conv_spatial_weight, P.conv_spatial_bias, p.t3, B, C, D1, D2, D3, 7, 7, 7, 3, p.wp_dw7, st));
     // conv_offset: Conv3d(C -> 81, k3, stride 1, pad 1)  (synapse/deform_conv.py:80-85)
     const ConvGeo go = make_geo(B, C, D1, D2, D3, 81, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3);
-    DLKA_TRY(pack_weight(P.conv_offset_weight, p.wp_off, 81, C, 27, 1, p.np_off, st));
-    IgemmArgs ao = conv_args(IGEMM_CONV, go, p.t3, nullptr, nullptr, p.wp_off, p.np_off, P.conv_offset_bias, EPI_NONE, nullptr, 0,
-                             p.off, 81);
-    DLKA_TRY(igemm_simt(ao, st));
+    IgemmArgs ao = conv_args(IGEMM_CONV, go, p.t3, nullptr, nullptr, nullptr, 0, P.conv_offset_bias, EPI_NONE, nullptr, 0, p.off, 81);
+    DLKA_TRY(contraction(ao, P.conv_offset_weight, math, p.wp_off, st));
     // deformable 3x3x3 conv C -> C, groups 1, dg 1 (transformerblock.py:639)
     const ConvGeo gd = make_geo(B, C, D1, D2, D3, C, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3);
-    DLKA_TRY(pack_weight(P.deform_weight, p.wp_dcn, C, C, 27, 1, p.np_c, st));
-    IgemmArgs ad = conv_args(IGEMM_DEFORM, gd, p.t3, p.off, nullptr, p.wp_dcn, p.np_c, P.deform_bias, EPI_NONE, nullptr, 0, p.t2, C);
-    DLKA_TRY(igemm_simt(ad, st));
+    IgemmArgs ad = conv_args(IGEMM_DEFORM, gd, p.t3, p.off, nullptr, nullptr, 0, P.deform_bias, EPI_NONE, nullptr, 0, p.t2, C);
+    DLKA_TRY(contraction(ad, P.deform_weight, math, p.wp_dcn, st));
     // conv1 (1x1x1) then gate with u
-    DLKA_TRY(pack_weight(P.conv1_weight, p.wp_conv1, C, C, 1, 1, p.np_c, st));
-    IgemmArgs a1 = dense_args(p.t2, C, M, C, C, p.wp_conv1, p.np_c, P.conv1_bias, EPI_MUL, u, C, p.t3, C);
-    DLKA_TRY(igemm_simt(a1, st));
+    IgemmArgs a1 = dense_args(p.t2, C, M, C, C, nullptr, 0, P.conv1_bias, EPI_MUL, u, C, p.t3, C);
+    DLKA_TRY(contraction(a1, P.conv1_weight, math, p.wp_conv1, st));
     return DLKA_OK;
 }
 
@@ -214,48 +227,43 @@ struct Block2dPlan {
 bool plan_block2d(Arena &ar, int B, int C, int H, int W, Block2dPlan &p)
 {
     const size_t M = (size_t)B * H * W;
-    p.np_c = igemm_simt_npad(C);
-    p.np_off0 = igemm_simt_npad(50);
-    p.np_off1 = igemm_simt_npad(98);
+    p.np_c = p.np_off0 = p.np_off1 = 0;
     p.x_cl = ar.take<float>(M * C);
     p.t1 = ar.take<float>(M * C);
     p.t2 = ar.take<float>(M * C);
     p.t3 = ar.take<float>(M * C);
     p.off = ar.take<float>(M * 98);
-    p.wp_proj1 = ar.take<float>((size_t)C * p.np_c);
-    p.wp_conv1 = ar.take<float>((size_t)C * p.np_c);
-    p.wp_proj2 = ar.take<float>((size_t)C * p.np_c);
-    p.wp_off0 = ar.take<float>((size_t)25 * C * p.np_off0);
-    p.wp_off1 = ar.take<float>((size_t)49 * C * p.np_off1);
+    p.wp_proj1 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
+    p.wp_conv1 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
+    p.wp_proj2 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
+    p.wp_off0 = ar.take<float>(contraction_scratch_floats(50, C, 25, 1));
+    p.wp_off1 = ar.take<float>(contraction_scratch_floats(98, C, 49, 1));
     p.wp_dw0 = ar.take<float>((size_t)25 * C);
     p.wp_dw1 = ar.take<float>((size_t)49 * C);
     return ar.ok();
 }
 
 // u channels-last -> u * conv1(conv_spatial(conv0(u))) into p.t2
-int run_lka2d_core(const dlkaBlock2dParams &P, const float *u, Block2dPlan &p, int B, int C, int H, int W, cudaStream_t st)
+int run_lka2d_core(const dlkaBlock2dParams &P, const float *u, Block2dPlan &p, int B, int C, int H, int W, int math,
+                   cudaStream_t st)
 {
     const i64 M = (i64)B * H * W;
     // conv0: offset_net Conv2d(C->50, k5, pad 2) + depthwise deformable k5 (deformable_LKA.py:93)
     ConvGeo g0 = make_geo(B, C, 1, H, W, 50, 1, 5, 5, 1, 1, 1, 0, 2, 2, 1, 1, 1, 1, 1, 2);
-    DLKA_TRY(pack_weight(P.conv0_offset_weight, p.wp_off0, 50, C, 25, 1, p.np_off0, st));
-    IgemmArgs a0 = conv_args(IGEMM_CONV, g0, u, nullptr, nullptr, p.wp_off0, p.np_off0, P.conv0_offset_bias, EPI_NONE, nullptr, 0,
-                             p.off, 50);
-    DLKA_TRY(igemm_simt(a0, st));
+    IgemmArgs a0 = conv_args(IGEMM_CONV, g0, u, nullptr, nullptr, nullptr, 0, P.conv0_offset_bias, EPI_NONE, nullptr, 0, p.off, 50);
+    DLKA_TRY(contraction(a0, P.conv0_offset_weight, math, p.wp_off0, st));
     ConvGeo d0 = make_geo(B, C, 1, H, W, C, 1, 5, 5, 1, 1, 1, 0, 2, 2, 1, 1, 1, C, 1, 2);
     DLKA_TRY(deform_dwconv_cl(u, p.off, nullptr, P.conv0_deform_weight, nullptr, p.t2, d0, p.wp_dw0, st));
     // conv_spatial: offset_net Conv2d(C->98, k7, dil 3, pad 9) + depthwise deformable k7 dil 3 (:94)
     ConvGeo g1 = make_geo(B, C, 1, H, W, 98, 1, 7, 7, 1, 1, 1, 0, 9, 9, 1, 3, 3, 1, 1, 2);
-    DLKA_TRY(pack_weight(P.conv_spatial_offset_weight, p.wp_off1, 98, C, 49, 1, p.np_off1, st));
-    IgemmArgs a1 = conv_args(IGEMM_CONV, g1, p.t2, nullptr, nullptr, p.wp_off1, p.np_off1, P.conv_spatial_offset_bias, EPI_NONE,
-                             nullptr, 0, p.off, 98);
-    DLKA_TRY(igemm_simt(a1, st));
+    IgemmArgs a1 = conv_args(IGEMM_CONV, g1, p.t2, nullptr, nullptr, nullptr, 0, P.conv_spatial_offset_bias, EPI_NONE, nullptr, 0,
+                             p.off, 98);
+    DLKA_TRY(contraction(a1, P.conv_spatial_offset_weight, math, p.wp_off1, st));
     ConvGeo d1 = make_geo(B, C, 1, H, W, C, 1, 7, 7, 1, 1, 1, 0, 9, 9, 1, 3, 3, C, 1, 2);
     DLKA_TRY(deform_dwconv_cl(p.t2, p.off, nullptr, P.conv_spatial_deform_weight, nullptr, p.t3, d1, p.wp_dw1, st));
     // conv1 1x1 and the gate
-    DLKA_TRY(pack_weight(P.conv1_weight, p.wp_conv1, C, C, 1, 1, p.np_c, st));
-    IgemmArgs ac = dense_args(p.t3, C, M, C, C, p.wp_conv1, p.np_c, P.conv1_bias, EPI_MUL, u, C, p.t2, C);
-    DLKA_TRY(igemm_simt(ac, st));
+    IgemmArgs ac = dense_args(p.t3, C, M, C, C, nullptr, 0, P.conv1_bias, EPI_MUL, u, C, p.t2, C);
+    DLKA_TRY(contraction(ac, P.conv1_weight, math, p.wp_conv1, st));
     return DLKA_OK;
 }
 
@@ -415,21 +423,19 @@ bool plan_pack(Arena &ar, const ConvGeo &g, PackPlan &p)
     p.x_cl = ar.take<float>((size_t)g.B * Vi * g.C);
     p.off_cl = ar.take<float>((size_t)M * noff);
     p.y_cl = ar.take<float>((size_t)M * g.Co);
-    p.np_off = igemm_simt_npad(noff);
-    p.wp_off = ar.take<float>((size_t)g.K * g.C * p.np_off);
-    if (is_depthwise(g)) {
-        p.np = 0;
+    p.np_off = p.np = 0;
+    p.wp_off = ar.take<float>(contraction_scratch_floats(noff, g.C, g.K, 1));
+    if (is_depthwise(g))
         p.wp = ar.take<float>((size_t)g.K * g.C);
-    } else {
-        p.np = igemm_simt_npad(g.Co / g.groups);
-        p.wp = ar.take<float>((size_t)g.groups * g.K * (g.C / g.groups) * p.np);
-    }
+    else
+        p.wp = ar.take<float>(contraction_scratch_floats(g.Co, g.C, g.K, g.groups));
     return ar.ok();
 }
 
 // g: geometry of the deformable conv; go: geometry of the offset conv (same taps, its own dilation)
 int run_pack(const ConvGeo &g, const ConvGeo &go, const float *input, const float *offset_weight, const float *offset_bias,
-             const float *weight, const float *bias, float *output, void *workspace, size_t workspace_bytes, cudaStream_t st)
+             const float *weight, const float *bias, float *output, int math, void *workspace, size_t workspace_bytes,
+             cudaStream_t st)
 {
     if (go.Do != g.Do || go.Ho != g.Ho || go.Wo != g.Wo) return DLKA_ERR_INVALID_ARGUMENT;
     if (g.C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
@@ -439,17 +445,14 @@ int run_pack(const ConvGeo &g, const ConvGeo &go, const float *input, const floa
     const i64 Vi = (i64)g.D * g.H * g.W, Vo = (i64)g.Do * g.Ho * g.Wo;
     const int noff = g.dg * g.ndim * g.K;
     DLKA_TRY(transpose_cs_to_sc(input, p.x_cl, g.B, g.C, Vi, st));
-    DLKA_TRY(pack_weight(offset_weight, p.wp_off, noff, g.C, g.K, 1, p.np_off, st));
-    IgemmArgs ao = conv_args(IGEMM_CONV, go, p.x_cl, nullptr, nullptr, p.wp_off, p.np_off, offset_bias, EPI_NONE, nullptr, 0,
-                             p.off_cl, noff);
-    DLKA_TRY(igemm_simt(ao, st));
+    IgemmArgs ao = conv_args(IGEMM_CONV, go, p.x_cl, nullptr, nullptr, nullptr, 0, offset_bias, EPI_NONE, nullptr, 0, p.off_cl, noff);
+    DLKA_TRY(contraction(ao, offset_weight, math, p.wp_off, st));
     if (is_depthwise(g)) {
         DLKA_TRY(deform_dwconv_cl(p.x_cl, p.off_cl, nullptr, weight, bias, p.y_cl, g, p.wp, st));
     } else {
         if ((g.C / g.groups) % 4 != 0 || (g.C / g.dg) % 4 != 0) return DLKA_ERR_UNSUPPORTED;
-        DLKA_TRY(pack_weight(weight, p.wp, g.Co, g.C / g.groups, g.K, g.groups, p.np, st));
-        IgemmArgs a = conv_args(IGEMM_DEFORM, g, p.x_cl, p.off_cl, nullptr, p.wp, p.np, bias, EPI_NONE, nullptr, 0, p.y_cl, g.Co);
-        DLKA_TRY(igemm_simt(a, st));
+        IgemmArgs a = conv_args(IGEMM_DEFORM, g, p.x_cl, p.off_cl, nullptr, nullptr, 0, bias, EPI_NONE, nullptr, 0, p.y_cl, g.Co);
+        DLKA_TRY(contraction(a, weight, math, p.wp, st));
     }
     DLKA_TRY(transpose_sc_to_cs(p.y_cl, output, g.B, g.Co, Vo, st));
     return DLKA_OK;
@@ -474,7 +477,6 @@ int dlka_deform_conv_pack3d_forward(const float *input, const float *offset_weig
                                     int deformable_group, int im2col_step, int math, void *workspace, size_t workspace_bytes,
                                     void *stream)
 {
-    (void)math;
     if (!input || !offset_weight || !offset_bias || !weight || !bias || !output) return DLKA_ERR_INVALID_ARGUMENT;
     if (group <= 0 || deformable_group <= 0 || im2col_step <= 0) return DLKA_ERR_INVALID_ARGUMENT;
     ConvGeo g = make_geo(B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw, dild, dilh, dilw, group, deformable_group, 3);
@@ -485,7 +487,8 @@ int dlka_deform_conv_pack3d_forward(const float *input, const float *offset_weig
     ConvGeo go = make_geo(B, C, D, H, W, deformable_group * 3 * g.K, kd, kh, kw, sd, sh, sw, pd, ph, pw, 1, 1, 1, 1, 1, 3);
     if (bad_geo(go)) return DLKA_ERR_INVALID_ARGUMENT;
     DLKA_TRY(check_device());
-    return run_pack(g, go, input, offset_weight, offset_bias, weight, bias, output, workspace, workspace_bytes, (cudaStream_t)stream);
+    return run_pack(g, go, input, offset_weight, offset_bias, weight, bias, output, math, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
 }
 
 size_t dlka_deform_conv_pack2d_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int sh, int sw, int ph, int pw,
@@ -504,14 +507,14 @@ int dlka_deform_conv_pack2d_forward(const float *input, const float *offset_weig
                                     int sw, int ph, int pw, int dilh, int dilw, int groups, int math, void *workspace,
                                     size_t workspace_bytes, void *stream)
 {
-    (void)math;
     if (!input || !offset_weight || !offset_bias || !weight || !output) return DLKA_ERR_INVALID_ARGUMENT;
     if (groups <= 0) return DLKA_ERR_INVALID_ARGUMENT;
     ConvGeo g = make_geo(B, C, 1, H, W, Co, 1, kh, kw, 1, sh, sw, 0, ph, pw, 1, dilh, dilw, groups, 1, 2);
     if (bad_geo(g)) return DLKA_ERR_INVALID_ARGUMENT;
     ConvGeo go = make_geo(B, C, 1, H, W, 2 * g.K, 1, kh, kw, 1, sh, sw, 0, ph, pw, 1, dilh, dilw, 1, 1, 2);
     DLKA_TRY(check_device());
-    return run_pack(g, go, input, offset_weight, offset_bias, weight, bias, output, workspace, workspace_bytes, (cudaStream_t)stream);
+    return run_pack(g, go, input, offset_weight, offset_bias, weight, bias, output, math, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------- 3D block
@@ -527,7 +530,6 @@ size_t dlka_lka3d_deform_workspace_bytes(int B, int C, int D1, int D2, int D3)
 int dlka_lka3d_deform_forward(const dlkaBlock3dParams *params, const float *x, float *y, int B, int C, int D1, int D2, int D3,
                               int math, void *workspace, size_t workspace_bytes, void *stream)
 {
-    (void)math;
     if (null_params3d(params, false) || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
     if (B <= 0 || C <= 0 || D1 <= 0 || D2 <= 0 || D3 <= 0) return DLKA_ERR_INVALID_ARGUMENT;
     if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
@@ -538,7 +540,7 @@ int dlka_lka3d_deform_forward(const dlkaBlock3dParams *params, const float *x, f
     if (!plan_block3d(ar, B, C, D1, D2, D3, p)) return DLKA_ERR_WORKSPACE;
     const i64 S = (i64)D1 * D2 * D3;
     DLKA_TRY(transpose_cs_to_sc(x, p.t1, B, C, S, st));              // u = x (channels-last)
-    DLKA_TRY(run_lka3d_core(*params, p.t1, p, B, C, D1, D2, D3, st));  // gate -> t3
+    DLKA_TRY(run_lka3d_core(*params, p.t1, p, B, C, D1, D2, D3, math, st));  // gate -> t3
     DLKA_TRY(transpose_sc_to_cs(p.t3, y, B, C, S, st));
     return DLKA_OK;
 }
@@ -551,7 +553,6 @@ size_t dlka_lka_attention3d_deform_workspace_bytes(int B, int C, int D1, int D2,
 int dlka_lka_attention3d_deform_forward(const dlkaBlock3dParams *params, const float *x, float *y, int B, int C, int D1, int D2,
                                         int D3, int math, void *workspace, size_t workspace_bytes, void *stream)
 {
-    (void)math;
     if (null_params3d(params, true) || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
     if (B <= 0 || C <= 0 || D1 <= 0 || D2 <= 0 || D3 <= 0) return DLKA_ERR_INVALID_ARGUMENT;
     if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
@@ -562,13 +563,11 @@ int dlka_lka_attention3d_deform_forward(const dlkaBlock3dParams *params, const f
     if (!plan_block3d(ar, B, C, D1, D2, D3, p)) return DLKA_ERR_WORKSPACE;
     const i64 M = (i64)B * D1 * D2 * D3;
     // tokens [B,N,C] are already channels-last over the Conv3d volume (transformerblock.py:665)
-    DLKA_TRY(pack_weight(params->proj_1_weight, p.wp_proj1, C, C, 1, 1, p.np_c, st));
-    IgemmArgs a1 = dense_args(x, C, M, C, C, p.wp_proj1, p.np_c, params->proj_1_bias, EPI_GELU, nullptr, 0, p.t1, C);
-    DLKA_TRY(igemm_simt(a1, st));
-    DLKA_TRY(run_lka3d_core(*params, p.t1, p, B, C, D1, D2, D3, st));  // gate -> t3
-    DLKA_TRY(pack_weight(params->proj_2_weight, p.wp_proj2, C, C, 1, 1, p.np_c, st));
-    IgemmArgs a2 = dense_args(p.t3, C, M, C, C, p.wp_proj2, p.np_c, params->proj_2_bias, EPI_ADD, x, C, y, C);
-    DLKA_TRY(igemm_simt(a2, st));
+    IgemmArgs a1 = dense_args(x, C, M, C, C, nullptr, 0, params->proj_1_bias, EPI_GELU, nullptr, 0, p.t1, C);
+    DLKA_TRY(contraction(a1, params->proj_1_weight, math, p.wp_proj1, st));
+    DLKA_TRY(run_lka3d_core(*params, p.t1, p, B, C, D1, D2, D3, math, st));  // gate -> t3
+    IgemmArgs a2 = dense_args(p.t3, C, M, C, C, nullptr, 0, params->proj_2_bias, EPI_ADD, x, C, y, C);
+    DLKA_TRY(contraction(a2, params->proj_2_weight, math, p.wp_proj2, st));
     return DLKA_OK;
 }
 
@@ -603,7 +602,6 @@ size_t dlka_deformable_lka2d_workspace_bytes(int B, int C, int H, int W)
 int dlka_deformable_lka2d_forward(const dlkaBlock2dParams *params, const float *x, float *y, int B, int C, int H, int W, int math,
                                   void *workspace, size_t workspace_bytes, void *stream)
 {
-    (void)math;
     if (null_params2d(params, false) || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return DLKA_ERR_INVALID_ARGUMENT;
     if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
@@ -613,7 +611,7 @@ int dlka_deformable_lka2d_forward(const dlkaBlock2dParams *params, const float *
     Block2dPlan p;
     if (!plan_block2d(ar, B, C, H, W, p)) return DLKA_ERR_WORKSPACE;
     DLKA_TRY(transpose_cs_to_sc(x, p.x_cl, B, C, (i64)H * W, st));
-    DLKA_TRY(run_lka2d_core(*params, p.x_cl, p, B, C, H, W, st));  // gate -> t2
+    DLKA_TRY(run_lka2d_core(*params, p.x_cl, p, B, C, H, W, math, st));  // gate -> t2
     DLKA_TRY(transpose_sc_to_cs(p.t2, y, B, C, (i64)H * W, st));
     return DLKA_OK;
 }
@@ -626,7 +624,6 @@ size_t dlka_deformable_lka_attention2d_workspace_bytes(int B, int C, int H, int 
 int dlka_deformable_lka_attention2d_forward(const dlkaBlock2dParams *params, const float *x, float *y, int B, int C, int H, int W,
                                             int math, void *workspace, size_t workspace_bytes, void *stream)
 {
-    (void)math;
     if (null_params2d(params, true) || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return DLKA_ERR_INVALID_ARGUMENT;
     if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
@@ -637,13 +634,11 @@ int dlka_deformable_lka_attention2d_forward(const dlkaBlock2dParams *params, con
     if (!plan_block2d(ar, B, C, H, W, p)) return DLKA_ERR_WORKSPACE;
     const i64 M = (i64)B * H * W;
     DLKA_TRY(transpose_cs_to_sc(x, p.x_cl, B, C, (i64)H * W, st));
-    DLKA_TRY(pack_weight(params->proj_1_weight, p.wp_proj1, C, C, 1, 1, p.np_c, st));
-    IgemmArgs a1 = dense_args(p.x_cl, C, M, C, C, p.wp_proj1, p.np_c, params->proj_1_bias, EPI_GELU, nullptr, 0, p.t1, C);
-    DLKA_TRY(igemm_simt(a1, st));
-    DLKA_TRY(run_lka2d_core(*params, p.t1, p, B, C, H, W, st));  // gate -> t2
-    DLKA_TRY(pack_weight(params->proj_2_weight, p.wp_proj2, C, C, 1, 1, p.np_c, st));
-    IgemmArgs a2 = dense_args(p.t2, C, M, C, C, p.wp_proj2, p.np_c, params->proj_2_bias, EPI_ADD, p.x_cl, C, p.t3, C);
-    DLKA_TRY(igemm_simt(a2, st));
+    IgemmArgs a1 = dense_args(p.x_cl, C, M, C, C, nullptr, 0, params->proj_1_bias, EPI_GELU, nullptr, 0, p.t1, C);
+    DLKA_TRY(contraction(a1, params->proj_1_weight, math, p.wp_proj1, st));
+    DLKA_TRY(run_lka2d_core(*params, p.t1, p, B, C, H, W, math, st));  // gate -> t2
+    IgemmArgs a2 = dense_args(p.t2, C, M, C, C, nullptr, 0, params->proj_2_bias, EPI_ADD, p.x_cl, C, p.t3, C);
+    DLKA_TRY(contraction(a2, params->proj_2_weight, math, p.wp_proj2, st));
     DLKA_TRY(transpose_sc_to_cs(p.t3, y, B, C, (i64)H * W, st));
     return DLKA_OK;
 }

@@ -32,6 +32,14 @@ int igemm_simt_npad(int n_per_group);
 int pack_weight(const float *w, float *wp, int Co, int Cg, int taps, int groups, int Npad, cudaStream_t st);
 int igemm_simt(const IgemmArgs &a, cudaStream_t st);
 
+// tensor-core (tcgen05, bf16 hi/lo split) variant -- mma_tc.cu
+bool tc_supported(const IgemmArgs &a);
+int tc_kc(int C);
+int tc_nt(int Co);
+size_t tc_packed_weight_bytes(int Co, int C, int taps);
+int tc_pack_weight(const float *w, void *bp, int Co, int C, int taps, cudaStream_t st);
+int igemm_tc(const IgemmArgs &a, const void *bp, cudaStream_t st);
+
 // ---------------- layout ----------------
 // [B][C][S] -> [B][S][C]  and back (S = spatial size)
 int transpose_cs_to_sc(const float *in, float *out, int B, int C, i64 S, cudaStream_t st);
