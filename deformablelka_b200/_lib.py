@@ -14,7 +14,8 @@ from typing import Optional
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdlka_b200.so")
+# DLKA_LIB selects an experimental build variant of the same library (never a different backend)
+LIB_PATH = os.environ.get("DLKA_LIB") or os.path.join(HERE, "libdlka_b200.so")
 
 MATH_FP32_SIMT = 0
 MATH_BF16X3 = 1

@@ -100,6 +100,7 @@ size_t contraction_scratch_floats(int Co, int C, int taps, int groups)
 int contraction(IgemmArgs a, const float *w, int math, float *wscratch, cudaStream_t st)
 {
     const ConvGeo &g = a.geo;
+    if (math == DLKA_MATH_BF16X3 && a.mode == IGEMM_CONV && conv_tiled_supported(a)) return conv_tiled(a, w, wscratch, st);
     if (math == DLKA_MATH_BF16X3 && tc_supported(a)) {
         DLKA_TRY(tc_pack_weight(w, wscratch, g.Co, g.C, g.K, st));
         return igemm_tc(a, wscratch, st);
@@ -162,6 +163,7 @@ int run_deform_op(const ConvGeo &g, const float *input, const float *weight, con
 }
 
 // ---- 3D block ---------------------------------------------------------------------------
+constexpr int OFF3D_LD = 84;  // row stride of the [M][81] offset buffer (16-byte aligned rows)
 struct Block3dPlan {
     float *t1, *t2, *t3, *off;
     float *wp_proj1, *wp_off, *wp_dcn, *wp_conv1, *wp_proj2, *wp_dw5, *wp_dw7;
@@ -175,7 +177,7 @@ bool plan_block3d(Arena &ar, int B, int C, int D1, int D2, int D3, Block3dPlan &
     p.t1 = ar.take<float>(M * C);
     p.t2 = ar.take<float>(M * C);
     p.t3 = ar.take<float>(M * C);
-    p.off = ar.take<float>(M * 81);
+    p.off = ar.take<float>(M * OFF3D_LD);
     p.wp_proj1 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
     p.wp_conv1 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
     p.wp_proj2 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
@@ -195,11 +197,13 @@ int run_lka3d_core(const dlkaBlock3dParams &P, const float *u, Block3dPlan &p, i
     DLKA_TRY(dwconv_cl(p.t2, P.conv_spatial_weight, P.conv_spatial_bias, p.t3, B, C, D1, D2, D3, 7, 7, 7, 3, p.wp_dw7, st));
     // conv_offset: Conv3d(C -> 81, k3, stride 1, pad 1)  (synapse/deform_conv.py:80-85)
     const ConvGeo go = make_geo(B, C, D1, D2, D3, 81, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3);
-    IgemmArgs ao = conv_args(IGEMM_CONV, go, p.t3, nullptr, nullptr, nullptr, 0, P.conv_offset_bias, EPI_NONE, nullptr, 0, p.off, 81);
+    IgemmArgs ao = conv_args(IGEMM_CONV, go, p.t3, nullptr, nullptr, nullptr, 0, P.conv_offset_bias, EPI_NONE, nullptr, 0, p.off,
+                             OFF3D_LD);
     DLKA_TRY(contraction(ao, P.conv_offset_weight, math, p.wp_off, st));
     // deformable 3x3x3 conv C -> C, groups 1, dg 1 (transformerblock.py:639)
     const ConvGeo gd = make_geo(B, C, D1, D2, D3, C, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3);
     IgemmArgs ad = conv_args(IGEMM_DEFORM, gd, p.t3, p.off, nullptr, nullptr, 0, P.deform_bias, EPI_NONE, nullptr, 0, p.t2, C);
+    ad.ldOff = OFF3D_LD;
     DLKA_TRY(contraction(ad, P.deform_weight, math, p.wp_dcn, st));
     // conv1 (1x1x1) then gate with u
     IgemmArgs a1 = dense_args(p.t2, C, M, C, C, nullptr, 0, P.conv1_bias, EPI_MUL, u, C, p.t3, C);

@@ -53,14 +53,14 @@ __device__ __forceinline__ float4 load_a4(const IgemmArgs &a, const RowPos &r, i
             const int dgi = c / (g.C / g.dg);
             const float *vol = a.X + (i64)r.b * g.D * g.H * g.W * g.C + c;
             if (g.ndim == 3) {
-                const float *off = a.Off + m * (i64)(g.dg * 3 * g.K) + (dgi * g.K + tap) * 3;
+                const float *off = a.Off + m * (i64)(a.ldOff ? a.ldOff : g.dg * 3 * g.K) + (dgi * g.K + tap) * 3;
                 const float pd = sample_pos(r.d, g.sd, g.pd, ii, g.dd, __ldg(off));
                 const float ph = sample_pos(r.h, g.sh, g.ph, jj, g.dh, __ldg(off + 1));
                 const float pw = sample_pos(r.w, g.sw, g.pw, kk, g.dw, __ldg(off + 2));
                 const Sample3 s = make_sample3(pd, ph, pw, g.D, g.H, g.W);
                 return trilinear4(vol, s, g.H, g.W, g.C);
             } else {
-                const float *off = a.Off + m * (i64)(g.dg * 2 * g.K) + (dgi * g.K + tap) * 2;
+                const float *off = a.Off + m * (i64)(a.ldOff ? a.ldOff : g.dg * 2 * g.K) + (dgi * g.K + tap) * 2;
                 const float ph = sample_pos(r.h, g.sh, g.ph, jj, g.dh, __ldg(off));
                 const float pw = sample_pos(r.w, g.sw, g.pw, kk, g.dw, __ldg(off + 1));
                 const Sample2 s = make_sample2(ph, pw, g.H, g.W);

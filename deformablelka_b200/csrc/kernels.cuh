@@ -18,7 +18,8 @@ struct IgemmArgs {
     int Npad;          // padded columns of Wp per group
     const float *X;    // input, channels-last; dense: row stride ldX
     int ldX;
-    const float *Off;  // deformable: offsets [M][dg*ndim*K]
+    const float *Off;  // deformable: offsets [M][ldOff], first dg*ndim*K columns used
+    int ldOff;         // row stride of Off (0 = dg*ndim*K)
     const float *Mask; // deformable 2D (DCNv2) modulation [M][dg*K] or null
     const float *Wp;   // packed weights [groups][Ktot][Npad]
     const float *bias; // [Co] or null
@@ -39,6 +40,11 @@ int tc_nt(int Co);
 size_t tc_packed_weight_bytes(int Co, int C, int taps);
 int tc_pack_weight(const float *w, void *bp, int Co, int C, int taps, cudaStream_t st);
 int igemm_tc(const IgemmArgs &a, const void *bp, cudaStream_t st);
+
+// zero-copy tiled regular conv on tcgen05 (stride 1, groups 1, no epilogue operand) -- conv_tc.cu
+bool conv_tiled_supported(const IgemmArgs &a);
+size_t conv_tiled_packed_bytes(int Co, int C, int taps);
+int conv_tiled(const IgemmArgs &a, const float *w, void *bp, cudaStream_t st);
 
 // ---------------- layout ----------------
 // [B][C][S] -> [B][S][C]  and back (S = spatial size)

@@ -26,7 +26,10 @@ namespace {
 using namespace ptx;
 
 constexpr int SA = 2, SB = 2;           // A / B ring depth
-constexpr int A_PAD = 0;                // extra bytes on LBO_A (bank-conflict padding experiment)
+#ifndef DLKA_A_PAD
+#define DLKA_A_PAD 0
+#endif
+constexpr int A_PAD = DLKA_A_PAD;       // extra bytes on LBO_A (bank-conflict padding experiment)
 constexpr int LBO_A = 2048 + A_PAD;     // bytes between 16-byte K chunks of an A slot (128 rows)
 constexpr int CTRL_WARPS = 4;
 
@@ -83,7 +86,7 @@ __device__ __forceinline__ void make_params(const TcArgs &a, const RowInfo &ri, 
     float4 w0 = f4zero(), w1 = f4zero();
     if (row_valid) {
         const int kk = tap % g.kw, jj = (tap / g.kw) % g.kh, ii = tap / (g.kw * g.kh);
-        const float *off = a.g.Off + m * (i64)(3 * g.K) + tap * 3;
+        const float *off = a.g.Off + m * (i64)(a.g.ldOff ? a.g.ldOff : 3 * g.K) + tap * 3;
         const float pd = sample_pos(ri.d, g.sd, g.pd, ii, g.dd, __ldg(off));
         const float ph = sample_pos(ri.h, g.sh, g.ph, jj, g.dh, __ldg(off + 1));
         const float pw = sample_pos(ri.w, g.sw, g.pw, kk, g.dw, __ldg(off + 2));
