@@ -206,10 +206,8 @@ def main():
         ms = e0.elapsed_time(e1)
         launches = dl.launch_count() - n0
         clocks = sampler.stop() if rank == 0 else None
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = t.item()
+        from deformablelka_b200.dist import max_over_ranks
+        ms_total = max_over_ranks(ms, dev)
 
         # per-kernel durations over the same K steps (CUDA events on the launch stream, inside the library)
         dl._lib.profile_enable(True)
@@ -234,10 +232,8 @@ def main():
                 yh.copy_(m(xh.to(dev, non_blocking=True), B, C, D1, D2, D3), non_blocking=True)
             f1.record()
             barrier()
-            t2 = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-            e2e = {"value": world * vox * ksteps / (t2.item() * 1e-3) / 1e9, "unit": "GVoxel/s",
+            e2e_ms = max_over_ranks(f0.elapsed_time(f1), dev)
+            e2e = {"value": world * vox * ksteps / (e2e_ms * 1e-3) / 1e9, "unit": "GVoxel/s",
                    "h2d_bytes_per_step": xh.numel() * 4, "d2h_bytes_per_step": yh.numel() * 4, "steps": ksteps}
 
     if rank != 0:
@@ -257,8 +253,8 @@ def main():
     # tensor-bound roofline on the dominant kernel when it is a contraction kernel, else HBM-bound
     per_launch_flop = {
         "igemm_simt_deform": 2 * 27 * C * C * vox, "igemm_simt_conv": 2 * 27 * C * 81 * vox,
-        "tc_deform": 2 * 27 * C * C * vox, "tc_conv_offset": 2 * 27 * C * 81 * vox,
-        "tc_deform_fused": (2 * 27 * C * C + 2 * 2 * C * C) * vox,
+        "tc_deform": 2 * 27 * C * C * vox, "tc_conv": 2 * 27 * C * 81 * vox, "tc_conv_tiled": 2 * 27 * C * 81 * vox,
+        "tc_deform3d": 2 * 27 * C * C * vox, "tc_deform3d_chain": (2 * 27 * C * C + 2 * 2 * C * C) * vox,
     }
     if dom_name in per_launch_flop:
         ach = per_launch_flop[dom_name] / (dom_avg_ms * 1e-3) / 1e12

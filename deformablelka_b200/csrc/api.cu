@@ -101,6 +101,7 @@ int contraction(IgemmArgs a, const float *w, int math, float *wscratch, cudaStre
 {
     const ConvGeo &g = a.geo;
     if (math == DLKA_MATH_BF16X3 && a.mode == IGEMM_CONV && conv_tiled_supported(a)) return conv_tiled(a, w, wscratch, st);
+    if (math == DLKA_MATH_BF16X3 && a.mode == IGEMM_DEFORM && deform3d_tc_supported(a)) return deform3d_tc(a, w, wscratch, st);
     if (math == DLKA_MATH_BF16X3 && tc_supported(a)) {
         DLKA_TRY(tc_pack_weight(w, wscratch, g.Co, g.C, g.K, st));
         return igemm_tc(a, wscratch, st);

@@ -1,0 +1,349 @@
+// deform_tc.cu -- 3D deformable convolution (groups 1, dg 1, stride 1) on tcgen05, L1-resident gather.
+//
+// Replaces the hot loop of D3D.deform_conv_forward (deformable_im2col_gpu_kernel + at::addmm,
+// 3D/dcn/src/cuda/deform_im2col_cuda.cuh:192-265, deform_conv_cuda.cu:113-119) without any im2col buffer.
+//
+// Design (what the first ncu pass taught): the trilinear gather reads 8 corners x 27 taps x C channels per
+// output voxel; served from L2 it saturates the L2 fabric (~12 TB/s measured).  So
+//   * a CTA owns a compact 4 x 4 x 8 brick of output voxels (128 MMA rows), not 128 consecutive voxels,
+//   * K is walked chunk-major: 32 channels (= one 128-byte line per voxel) over all taps, then the next 32,
+//     so the working set of a pass (brick + halo, one line per voxel, ~100 KB) stays in L1,
+//   * shared memory is kept under ~100 KB so the L1 carve-out is large.
+// Roles: warp 0 MMA issuer, warp 1 weight loader (cp.async.bulk), warps 4-7 sample-parameter producers
+// (positions, clamped corner offsets, masked trilinear weights: 64 B per (row, tap)) and later the epilogue,
+// warps 8-23 gather/blend/convert producers that fill the UMMA A slots.
+#include <cuda_bf16.h>
+
+#include "kernels.cuh"
+#include "tc_ptx.cuh"
+
+namespace dlka {
+namespace {
+
+using namespace ptx;
+
+constexpr int DF_KC = 32;                 // channels per K step (one 128-byte line per voxel)
+#ifndef DLKA_DF_SA
+#define DLKA_DF_SA 3
+#define DLKA_DF_SB 3
+#define DLKA_DF_SP 4
+#endif
+constexpr int DF_SA = DLKA_DF_SA, DF_SB = DLKA_DF_SB, DF_SP = DLKA_DF_SP;
+constexpr int DF_LBO = 2048 + 32;         // A plane stride (bank-spread padding; see profiles/r01 notes)
+constexpr int DF_APLANE = (DF_KC / 8) * DF_LBO;
+constexpr int DF_ASLOT = 2 * DF_APLANE;
+constexpr int DF_PARAM_WARPS = 4, DF_GATHER_WARPS = 16;
+constexpr int DF_THREADS = (4 + DF_PARAM_WARPS + DF_GATHER_WARPS) * 32;
+constexpr int DF_BD = 4, DF_BH = 4, DF_BW = 8;  // brick
+
+struct DeformTcArgs {
+    ConvGeo g;
+    const float *X;      // [B][D][H][W][C]
+    const float *Off;    // [M][ldOff]
+    int ldOff;
+    const uint8_t *Bp;   // [n_tile][chunk][tap][hi|lo][4 planes][NT][8 bf16]
+    const float *bias;
+    float *Y;            // [M][ldY]
+    int ldY;
+    int NT;
+    int tiles_d, tiles_h, tiles_w;
+    i64 vol_c;
+};
+
+struct DfRow {
+    int b, d, h, w;
+    int m;       // linear output row or -1
+    int pad[3];
+};
+
+__device__ __forceinline__ void df_make_params(const DeformTcArgs &a, const DfRow &ri, int tap, int4 *prm)
+{
+    const ConvGeo &g = a.g;
+    int4 o0 = make_int4(0, 0, 0, 0), o1 = o0;
+    float4 w0 = f4zero(), w1 = f4zero();
+    if (ri.m >= 0) {
+        const int kk = tap % g.kw, jj = (tap / g.kw) % g.kh, ii = tap / (g.kw * g.kh);
+        const float *off = a.Off + (i64)ri.m * a.ldOff + tap * 3;
+        const float pd = sample_pos(ri.d, g.sd, g.pd, ii, g.dd, __ldg(off));
+        const float ph = sample_pos(ri.h, g.sh, g.ph, jj, g.dh, __ldg(off + 1));
+        const float pw = sample_pos(ri.w, g.sw, g.pw, kk, g.dw, __ldg(off + 2));
+        const Sample3 s = make_sample3(pd, ph, pw, g.D, g.H, g.W);
+        if (s.mask & 1) {
+            const float ld = s.l[0], lh = s.l[1], lw = s.l[2], hd = 1.f - ld, hh = 1.f - lh, hw = 1.f - lw;
+            const int d0 = max(s.lo[0], 0), d1 = min(s.lo[0] + 1, g.D - 1);
+            const int h0 = max(s.lo[1], 0), h1 = min(s.lo[1] + 1, g.H - 1);
+            const int x0 = max(s.lo[2], 0), x1 = min(s.lo[2] + 1, g.W - 1);
+            const int sH = g.W * g.C, sD = g.H * sH;
+            o0.x = d0 * sD + h0 * sH + x0 * g.C; o0.y = d0 * sD + h0 * sH + x1 * g.C;
+            o0.z = d0 * sD + h1 * sH + x0 * g.C; o0.w = d0 * sD + h1 * sH + x1 * g.C;
+            o1.x = d1 * sD + h0 * sH + x0 * g.C; o1.y = d1 * sD + h0 * sH + x1 * g.C;
+            o1.z = d1 * sD + h1 * sH + x0 * g.C; o1.w = d1 * sD + h1 * sH + x1 * g.C;
+            w0.x = (s.mask & (1 << 1)) ? hd * hh * hw : 0.f; w0.y = (s.mask & (1 << 2)) ? hd * hh * lw : 0.f;
+            w0.z = (s.mask & (1 << 3)) ? hd * lh * hw : 0.f; w0.w = (s.mask & (1 << 4)) ? hd * lh * lw : 0.f;
+            w1.x = (s.mask & (1 << 5)) ? ld * hh * hw : 0.f; w1.y = (s.mask & (1 << 6)) ? ld * hh * lw : 0.f;
+            w1.z = (s.mask & (1 << 7)) ? ld * lh * hw : 0.f; w1.w = (s.mask & (1 << 8)) ? ld * lh * lw : 0.f;
+        }
+    }
+    prm[0] = o0; prm[1] = o1;
+    *reinterpret_cast<float4 *>(prm + 2) = w0;
+    *reinterpret_cast<float4 *>(prm + 3) = w1;
+}
+
+__global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const DeformTcArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const ConvGeo &g = a.g;
+    const int NT = a.NT;
+    const int B_PLANE = (DF_KC / 8) * NT * 16, B_SLOT = 2 * B_PLANE;
+    uint8_t *sA = smem;
+    uint8_t *sB = sA + DF_SA * DF_ASLOT;
+    int4 *sPrm = reinterpret_cast<int4 *>(sB + DF_SB * B_SLOT);                 // [SP][128][4]
+    DfRow *sRow = reinterpret_cast<DfRow *>(sPrm + DF_SP * 128 * 4);            // [128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sRow + 128);
+    constexpr int NBARS = 2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
+    const uint32_t bar0 = smem_u32(bars);
+    auto fullA = [&](int s) { return bar0 + 8u * s; };
+    auto emptyA = [&](int s) { return bar0 + 8u * (DF_SA + s); };
+    auto fullB = [&](int s) { return bar0 + 8u * (2 * DF_SA + s); };
+    auto emptyB = [&](int s) { return bar0 + 8u * (2 * DF_SA + DF_SB + s); };
+    auto fullP = [&](int s) { return bar0 + 8u * (2 * DF_SA + 2 * DF_SB + s); };
+    auto emptyP = [&](int s) { return bar0 + 8u * (2 * DF_SA + 2 * DF_SB + DF_SP + s); };
+    const uint32_t accFull = bar0 + 8u * (NBARS - 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tile = blockIdx.y;
+    int bid = blockIdx.x;
+    const int tw = bid % a.tiles_w; bid /= a.tiles_w;
+    const int th = bid % a.tiles_h; bid /= a.tiles_h;
+    const int td = bid % a.tiles_d;
+    const int b = bid / a.tiles_d;
+    const int nchunks = g.C / DF_KC, K = g.K, KS = nchunks * K;
+    const uint32_t tmem_cols = NT <= 32 ? 32u : NT <= 64 ? 64u : NT <= 128 ? 128u : 256u;
+
+    if (tid == 0) {
+        for (int s = 0; s < DF_SA; ++s) { mbar_init(fullA(s), DF_GATHER_WARPS); mbar_init(emptyA(s), 1); }
+        for (int s = 0; s < DF_SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+        for (int s = 0; s < DF_SP; ++s) { mbar_init(fullP(s), DF_PARAM_WARPS); mbar_init(emptyP(s), DF_GATHER_WARPS); }
+        mbar_init(accFull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+        tmem_relinquish();
+    }
+    if (warp >= 4 && warp < 8) {  // brick row decode
+        const int r = tid - 128;
+        const int d = td * DF_BD + (r >> 5), h = th * DF_BH + ((r >> 3) & 3), w = tw * DF_BW + (r & 7);
+        DfRow ri;
+        ri.b = b; ri.d = d; ri.h = h; ri.w = w;
+        ri.m = (d < g.Do && h < g.Ho && w < g.Wo) ? (int)((((i64)b * g.Do + d) * g.Ho + h) * g.Wo + w) : -1;
+        ri.pad[0] = ri.pad[1] = ri.pad[2] = 0;
+        sRow[r] = ri;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(128, NT);
+            for (int ks = 0; ks < KS; ++ks) {
+                const int bs = ks % DF_SB, as = ks % DF_SA;
+                mbar_wait(fullB(bs), (ks / DF_SB) & 1);
+                mbar_wait(fullA(as), (ks / DF_SA) & 1);
+                tc_fence_after();
+                const uint32_t ahi = smem_u32(sA + as * DF_ASLOT), alo = ahi + DF_APLANE;
+                const uint32_t bhi = smem_u32(sB + bs * B_SLOT), blo = bhi + B_PLANE;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t ab = pass == 1 ? alo : ahi, bb = pass == 2 ? blo : bhi;
+#pragma unroll
+                    for (int kk = 0; kk < DF_KC / 16; ++kk) {
+                        const uint64_t ad = make_smem_desc(ab + kk * 2 * DF_LBO, DF_LBO, 128);
+                        const uint64_t bd = make_smem_desc(bb + kk * 2 * NT * 16, NT * 16, 128);
+                        umma_bf16(tmem_base, ad, bd, idesc, (ks | pass | kk) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(emptyA(as));
+                umma_commit(emptyB(bs));
+            }
+            umma_commit(accFull);
+        }
+    } else if (warp == 1) {
+        // ===================== weight loader =====================
+        if (elect_one()) {
+            const uint8_t *src = a.Bp + (i64)n_tile * KS * B_SLOT;
+            for (int ks = 0; ks < KS; ++ks) {
+                const int bs = ks % DF_SB;
+                mbar_wait(emptyB(bs), ((ks / DF_SB) & 1) ^ 1);
+                mbar_arrive_expect_tx(fullB(bs), (uint32_t)B_SLOT);
+                bulk_g2s(smem_u32(sB + bs * B_SLOT), src + (i64)ks * B_SLOT, (uint32_t)B_SLOT, fullB(bs));
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== sample-parameter producers (one thread per brick row) =====================
+        const int r = tid - 128;
+        const DfRow ri = sRow[r];
+        for (int ks = 0; ks < KS; ++ks) {
+            const int ps = ks % DF_SP, tap = ks % K;
+            mbar_wait(emptyP(ps), ((ks / DF_SP) & 1) ^ 1);
+            df_make_params(a, ri, tap, sPrm + (ps * 128 + r) * 4);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(fullP(ps));
+        }
+        // ===================== epilogue =====================
+        mbar_wait(accFull, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const DfRow ro = sRow[q * 32 + lane];
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool vec_y = (a.ldY & 3) == 0;
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + c0, v);
+            if (ro.m < 0) continue;
+            const int nb = n_tile * NT + c0;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const int n = nb + j4 * 4;
+                if (n >= g.Co) break;
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int ne = n + e < g.Co ? n + e : g.Co - 1;
+                    o[e] = v[j4 * 4 + e] + (a.bias ? __ldg(a.bias + ne) : 0.f);
+                }
+                float *yp = a.Y + (i64)ro.m * a.ldY + n;
+                if (vec_y && n + 3 < g.Co) {
+                    *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (n + e < g.Co) yp[e] = o[e];
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== gather / blend / convert producers =====================
+        const int gt = tid - 256;                      // 0..511
+        const int cg = gt & 7;                         // float4 of the 32-channel chunk
+        const float *Xb = a.X + (i64)b * a.vol_c + cg * 4;
+        for (int ks = 0; ks < KS; ++ks) {
+            const int as = ks % DF_SA, ps = ks % DF_SP, chunk = ks / K;
+            mbar_wait(fullP(ps), (ks / DF_SP) & 1);
+            mbar_wait(emptyA(as), ((ks / DF_SA) & 1) ^ 1);
+            uint8_t *slot = sA + as * DF_ASLOT;
+            const float *base = Xb + chunk * DF_KC;
+            float4 acc[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int row = (gt >> 3) + s * 64;
+                const int4 *prm = sPrm + (ps * 128 + row) * 4;
+                const int4 o0 = prm[0], o1 = prm[1];
+                const float4 w0 = *reinterpret_cast<const float4 *>(prm + 2), w1 = *reinterpret_cast<const float4 *>(prm + 3);
+                const float4 v0 = ldg4(base + o0.x), v1 = ldg4(base + o0.y), v2 = ldg4(base + o0.z), v3 = ldg4(base + o0.w);
+                const float4 v4 = ldg4(base + o1.x), v5 = ldg4(base + o1.y), v6 = ldg4(base + o1.z), v7 = ldg4(base + o1.w);
+                float4 r = f4zero();
+                fma4(r, w0.x, v0); fma4(r, w0.y, v1); fma4(r, w0.z, v2); fma4(r, w0.w, v3);
+                fma4(r, w1.x, v4); fma4(r, w1.y, v5); fma4(r, w1.z, v6); fma4(r, w1.w, v7);
+                acc[s] = r;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(emptyP(ps));    // parameters consumed
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int row = (gt >> 3) + s * 64;
+                uint2 hi, lo;
+                split_bf16x4(acc[s], hi, lo);
+                const int boff = (cg >> 1) * DF_LBO + row * 16 + (cg & 1) * 8;
+                *reinterpret_cast<uint2 *>(slot + boff) = hi;
+                *reinterpret_cast<uint2 *>(slot + DF_APLANE + boff) = lo;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(fullA(as));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// weight [Co][C][taps] -> Bp[n_tile][chunk][tap][hi|lo][4 planes][NT][8]
+__global__ void pack_weight_df_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ bp, int Co, int C, int taps, int NT,
+                                      int n_tiles)
+{
+    const int nch = C / DF_KC;
+    const i64 total = (i64)n_tiles * nch * taps * DF_KC * NT;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+        const int e = (int)(i % 8);
+        const int n = (int)((i / 8) % NT);
+        const int p = (int)((i / (8 * NT)) % (DF_KC / 8));
+        const int tap = (int)((i / ((i64)DF_KC * NT)) % taps);
+        const int ch = (int)((i / ((i64)DF_KC * NT * taps)) % nch);
+        const int nt = (int)(i / ((i64)DF_KC * NT * taps * nch));
+        const int c = ch * DF_KC + p * 8 + e, co = nt * NT + n;
+        const float v = co < Co ? w[((i64)co * C + c) * taps + tap] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const i64 slot = ((i64)(nt * nch + ch) * taps + tap) * (2 * DF_KC * NT);
+        bp[slot + ((i64)p * NT + n) * 8 + e] = hi;
+        bp[slot + (i64)DF_KC * NT + ((i64)p * NT + n) * 8 + e] = lo;
+    }
+}
+
+size_t df_smem_bytes(int NT)
+{
+    return (size_t)DF_SA * DF_ASLOT + (size_t)DF_SB * 2 * (DF_KC / 8) * NT * 16 + (size_t)DF_SP * 128 * 64 + 128 * sizeof(DfRow) +
+           (2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1) * 8 + 16 + 128;
+}
+
+}  // namespace
+
+bool deform3d_tc_supported(const IgemmArgs &a)
+{
+    const ConvGeo &g = a.geo;
+    if (a.mode != IGEMM_DEFORM || g.ndim != 3 || g.groups != 1 || g.dg != 1 || a.Mask) return false;
+    if (g.C % DF_KC != 0 || a.epi != EPI_NONE) return false;
+    if ((i64)g.D * g.H * g.W * g.C >= ((i64)1 << 31)) return false;
+    if ((i64)g.B * g.Do * g.Ho * g.Wo >= ((i64)1 << 31)) return false;
+    return true;
+}
+
+int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, cudaStream_t st)
+{
+    if (!deform3d_tc_supported(ga)) return DLKA_ERR_UNSUPPORTED;
+    const ConvGeo &g = ga.geo;
+    if (ga.M <= 0) return DLKA_OK;
+    DeformTcArgs a;
+    a.g = g; a.X = ga.X; a.Off = ga.Off; a.ldOff = ga.ldOff ? ga.ldOff : 3 * g.K; a.bias = ga.bias; a.Y = ga.Y; a.ldY = ga.ldY;
+    a.NT = tc_nt(g.Co);
+    const int n_tiles = (int)cdiv(g.Co, a.NT);
+    a.tiles_d = (int)cdiv(g.Do, DF_BD); a.tiles_h = (int)cdiv(g.Ho, DF_BH); a.tiles_w = (int)cdiv(g.Wo, DF_BW);
+    a.vol_c = (i64)g.D * g.H * g.W * g.C;
+    {
+        const i64 total = (i64)n_tiles * g.K * g.C * a.NT;
+        const int blocks = (int)(cdiv(total, 256) < 148 * 8 ? cdiv(total, 256) : 148 * 8);
+        DLKA_LAUNCH("pack_weight_df", st,
+                    pack_weight_df_kernel<<<blocks, 256, 0, st>>>(w, (__nv_bfloat16 *)bp, g.Co, g.C, g.K, a.NT, n_tiles));
+    }
+    a.Bp = (const uint8_t *)bp;
+    const size_t smem = df_smem_bytes(a.NT);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        DLKA_CUDA_TRY(cudaFuncSetAttribute(deform3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)((i64)g.B * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)n_tiles);
+    DLKA_LAUNCH("tc_deform3d", st, (deform3d_tc_kernel<<<grid, DF_THREADS, smem, st>>>(a)));
+    return DLKA_OK;
+}
+
+}  // namespace dlka

@@ -41,6 +41,10 @@ size_t tc_packed_weight_bytes(int Co, int C, int taps);
 int tc_pack_weight(const float *w, void *bp, int Co, int C, int taps, cudaStream_t st);
 int igemm_tc(const IgemmArgs &a, const void *bp, cudaStream_t st);
 
+// 3D deformable conv, brick tiles + chunk-major K (L1-resident gather) -- deform_tc.cu
+bool deform3d_tc_supported(const IgemmArgs &a);
+int deform3d_tc(const IgemmArgs &a, const float *w, void *bp, cudaStream_t st);
+
 // zero-copy tiled regular conv on tcgen05 (stride 1, groups 1, no epilogue operand) -- conv_tc.cu
 bool conv_tiled_supported(const IgemmArgs &a);
 size_t conv_tiled_packed_bytes(int Co, int C, int taps);
