@@ -101,7 +101,7 @@ int contraction(IgemmArgs a, const float *w, int math, float *wscratch, cudaStre
 {
     const ConvGeo &g = a.geo;
     if (math == DLKA_MATH_BF16X3 && a.mode == IGEMM_CONV && conv_tiled_supported(a)) return conv_tiled(a, w, wscratch, st);
-    if (math == DLKA_MATH_BF16X3 && a.mode == IGEMM_DEFORM && deform3d_tc_supported(a)) return deform3d_tc(a, w, wscratch, st);
+    if (math == DLKA_MATH_BF16X3 && a.mode == IGEMM_DEFORM && deform3d_tc_supported(a)) return deform3d_tc(a, w, wscratch, nullptr, st);
     if (math == DLKA_MATH_BF16X3 && tc_supported(a)) {
         DLKA_TRY(tc_pack_weight(w, wscratch, g.Co, g.C, g.K, st));
         return igemm_tc(a, wscratch, st);
@@ -190,8 +190,9 @@ bool plan_block3d(Arena &ar, int B, int C, int D1, int D2, int D3, Block3dPlan &
 }
 
 // u (channels-last, = GELU(proj_1 x) or x itself) -> gate = u * conv1(deform(dw7(dw5(u)))) into p.t3
+// returns DLKA_OK with the gate in p.t3, or 1 when (fuse_proj2) proj_2 + shortcut were fused and y_final is complete
 int run_lka3d_core(const dlkaBlock3dParams &P, const float *u, Block3dPlan &p, int B, int C, int D1, int D2, int D3,
-                   int math, cudaStream_t st)
+                   int math, cudaStream_t st, bool fuse_proj2 = false, const float *resid = nullptr, float *y_final = nullptr)
 {
     const i64 M = (i64)B * D1 * D2 * D3;
     DLKA_TRY(dwconv_cl(u, P.conv0_weight, P.conv0_bias, p.t2, B, C, D1, D2, D3, 5, 5, 5, 1, p.wp_dw5, st));
@@ -205,6 +206,26 @@ int run_lka3d_core(const dlkaBlock3dParams &P, const float *u, Block3dPlan &p, i
     const ConvGeo gd = make_geo(B, C, D1, D2, D3, C, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3);
     IgemmArgs ad = conv_args(IGEMM_DEFORM, gd, p.t3, p.off, nullptr, nullptr, 0, P.deform_bias, EPI_NONE, nullptr, 0, p.t2, C);
     ad.ldOff = OFF3D_LD;
+    if (math == DLKA_MATH_BF16X3 && deform3d_chain_supported(ad)) {
+        // deformable conv + conv1 + gate (+ proj_2 + shortcut) in ONE kernel: the 1x1 GEMMs run on the accumulator tile
+        DeformChain ch;
+        memset(&ch, 0, sizeof(ch));
+        ch.stages = fuse_proj2 ? 2 : 1;
+        DLKA_TRY(tc_pack_weight(P.conv1_weight, p.wp_conv1, C, C, 1, st));
+        ch.W1p = p.wp_conv1; ch.b1 = P.conv1_bias; ch.U = u; ch.ldU = C;
+        if (fuse_proj2) {
+            DLKA_TRY(tc_pack_weight(P.proj_2_weight, p.wp_proj2, C, C, 1, st));
+            ch.W2p = p.wp_proj2; ch.b2 = P.proj_2_bias; ch.R = resid; ch.ldR = C;
+            ad.Y = y_final;
+        } else {
+            ad.Y = p.t2;  // must not alias the gather source t3
+        }
+        DLKA_TRY(deform3d_tc(ad, P.deform_weight, p.wp_dcn, &ch, st));
+        if (!fuse_proj2) {
+            float *tmp = p.t2; p.t2 = p.t3; p.t3 = tmp;  // callers find the gate in p.t3
+        }
+        return fuse_proj2 ? 1 : DLKA_OK;  // 1: the whole tail (proj_2 + shortcut) is already in y_final
+    }
     DLKA_TRY(contraction(ad, P.deform_weight, math, p.wp_dcn, st));
     // conv1 (1x1x1) then gate with u
     IgemmArgs a1 = dense_args(p.t2, C, M, C, C, nullptr, 0, P.conv1_bias, EPI_MUL, u, C, p.t3, C);
@@ -570,7 +591,9 @@ int dlka_lka_attention3d_deform_forward(const dlkaBlock3dParams *params, const f
     // tokens [B,N,C] are already channels-last over the Conv3d volume (transformerblock.py:665)
     IgemmArgs a1 = dense_args(x, C, M, C, C, nullptr, 0, params->proj_1_bias, EPI_GELU, nullptr, 0, p.t1, C);
     DLKA_TRY(contraction(a1, params->proj_1_weight, math, p.wp_proj1, st));
-    DLKA_TRY(run_lka3d_core(*params, p.t1, p, B, C, D1, D2, D3, math, st));  // gate -> t3
+    const int rc = run_lka3d_core(*params, p.t1, p, B, C, D1, D2, D3, math, st, true, x, y);  // gate -> t3, or everything -> y
+    if (rc == 1) return DLKA_OK;
+    if (rc != DLKA_OK) return rc;
     IgemmArgs a2 = dense_args(p.t3, C, M, C, C, nullptr, 0, params->proj_2_bias, EPI_ADD, x, C, y, C);
     DLKA_TRY(contraction(a2, params->proj_2_weight, math, p.wp_proj2, st));
     return DLKA_OK;

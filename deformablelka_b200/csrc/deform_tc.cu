@@ -48,6 +48,16 @@ struct DeformTcArgs {
     int NT;
     int tiles_d, tiles_h, tiles_w;
     i64 vol_c;
+    // fused epilogue chain (C == Co <= 96): stage 1 = conv1 (1x1) then gate with U; stage 2 = proj_2 (1x1) + residual R
+    int chain;            // 0 none, 1 conv1+gate, 2 conv1+gate+proj_2+residual
+    const uint8_t *W1p;   // tc_pack_weight layout, KC = C
+    const float *b1;
+    const float *U;
+    int ldU;
+    const uint8_t *W2p;
+    const float *b2;
+    const float *R;
+    int ldR;
 };
 
 struct DfRow {
@@ -100,7 +110,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     int4 *sPrm = reinterpret_cast<int4 *>(sB + DF_SB * B_SLOT);                 // [SP][128][4]
     DfRow *sRow = reinterpret_cast<DfRow *>(sPrm + DF_SP * 128 * 4);            // [128]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sRow + 128);
-    constexpr int NBARS = 2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1;
+    constexpr int NBARS = 2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
     const uint32_t bar0 = smem_u32(bars);
     auto fullA = [&](int s) { return bar0 + 8u * s; };
@@ -109,7 +119,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     auto emptyB = [&](int s) { return bar0 + 8u * (2 * DF_SA + DF_SB + s); };
     auto fullP = [&](int s) { return bar0 + 8u * (2 * DF_SA + 2 * DF_SB + s); };
     auto emptyP = [&](int s) { return bar0 + 8u * (2 * DF_SA + 2 * DF_SB + DF_SP + s); };
-    const uint32_t accFull = bar0 + 8u * (NBARS - 1);
+    const uint32_t accFull = bar0 + 8u * (NBARS - 7);
+    const uint32_t barW1 = accFull + 8, barE1 = accFull + 16, barC1 = accFull + 24, barW2 = accFull + 32, barE2 = accFull + 40,
+                   barC2 = accFull + 48;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tile = blockIdx.y;
@@ -119,13 +131,19 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     const int td = bid % a.tiles_d;
     const int b = bid / a.tiles_d;
     const int nchunks = g.C / DF_KC, K = g.K, KS = nchunks * K;
-    const uint32_t tmem_cols = NT <= 32 ? 32u : NT <= 64 ? 64u : NT <= 128 ? 128u : 256u;
+    const int tc_need = a.chain ? 2 * NT : NT;
+    const uint32_t tmem_cols = tc_need <= 32 ? 32u : tc_need <= 64 ? 64u : tc_need <= 128 ? 128u : 256u;
+    const int CP = g.C / 8;                               // chain: 16-byte K chunks per row
+    const uint32_t chainA_lo = (uint32_t)CP * DF_LBO;      // byte offset of the lo plane set in sA (chain layout)
+    const uint32_t chainB_lo = (uint32_t)CP * NT * 16;     // byte offset of the lo half in sB (chain layout)
 
     if (tid == 0) {
         for (int s = 0; s < DF_SA; ++s) { mbar_init(fullA(s), DF_GATHER_WARPS); mbar_init(emptyA(s), 1); }
         for (int s = 0; s < DF_SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
         for (int s = 0; s < DF_SP; ++s) { mbar_init(fullP(s), DF_PARAM_WARPS); mbar_init(emptyP(s), DF_GATHER_WARPS); }
         mbar_init(accFull, 1);
+        mbar_init(barW1, 1); mbar_init(barE1, DF_PARAM_WARPS + DF_GATHER_WARPS); mbar_init(barC1, 1);
+        mbar_init(barW2, 1); mbar_init(barE2, DF_PARAM_WARPS + DF_GATHER_WARPS); mbar_init(barC2, 1);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -171,6 +189,23 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                 umma_commit(emptyB(bs));
             }
             umma_commit(accFull);
+            // ---- fused 1x1 chain: A = epilogue-written rows in sA, B = whole weight matrix in sB ----
+            for (int stage = 1; stage <= a.chain; ++stage) {
+                mbar_wait(stage == 1 ? barW1 : barW2, 0);
+                mbar_wait(stage == 1 ? barE1 : barE2, 0);
+                tc_fence_after();
+                const uint32_t ahi = smem_u32(sA), alo = ahi + chainA_lo, bhi = smem_u32(sB), blo = bhi + chainB_lo;
+                const uint32_t d_tmem = tmem_base + (stage == 1 ? (uint32_t)NT : 0u);
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t ab = pass == 1 ? alo : ahi, bb = pass == 2 ? blo : bhi;
+                    for (int kk = 0; kk < g.C / 16; ++kk) {
+                        const uint64_t ad = make_smem_desc(ab + kk * 2 * DF_LBO, DF_LBO, 128);
+                        const uint64_t bd = make_smem_desc(bb + kk * 2 * NT * 16, NT * 16, 128);
+                        umma_bf16(d_tmem, ad, bd, idesc, (pass | kk) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(stage == 1 ? barC1 : barC2);
+            }
         }
     } else if (warp == 1) {
         // ===================== weight loader =====================
@@ -181,6 +216,17 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                 mbar_wait(emptyB(bs), ((ks / DF_SB) & 1) ^ 1);
                 mbar_arrive_expect_tx(fullB(bs), (uint32_t)B_SLOT);
                 bulk_g2s(smem_u32(sB + bs * B_SLOT), src + (i64)ks * B_SLOT, (uint32_t)B_SLOT, fullB(bs));
+            }
+            if (a.chain) {
+                const uint32_t wbytes = 2u * chainB_lo;
+                mbar_wait(accFull, 0);                      // every main-loop MMA has retired: sB is free
+                mbar_arrive_expect_tx(barW1, wbytes);
+                bulk_g2s(smem_u32(sB), a.W1p, wbytes, barW1);
+                if (a.chain == 2) {
+                    mbar_wait(barC1, 0);                    // conv1 MMAs done reading sB
+                    mbar_arrive_expect_tx(barW2, wbytes);
+                    bulk_g2s(smem_u32(sB), a.W2p, wbytes, barW2);
+                }
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -193,38 +239,6 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             df_make_params(a, ri, tap, sPrm + (ps * 128 + r) * 4);
             __syncwarp();
             if (lane == 0) mbar_arrive(fullP(ps));
-        }
-        // ===================== epilogue =====================
-        mbar_wait(accFull, 0);
-        tc_fence_after();
-        const int q = warp & 3;
-        const DfRow ro = sRow[q * 32 + lane];
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        const bool vec_y = (a.ldY & 3) == 0;
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + c0, v);
-            if (ro.m < 0) continue;
-            const int nb = n_tile * NT + c0;
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-                const int n = nb + j4 * 4;
-                if (n >= g.Co) break;
-                float o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int ne = n + e < g.Co ? n + e : g.Co - 1;
-                    o[e] = v[j4 * 4 + e] + (a.bias ? __ldg(a.bias + ne) : 0.f);
-                }
-                float *yp = a.Y + (i64)ro.m * a.ldY + n;
-                if (vec_y && n + 3 < g.Co) {
-                    *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (n + e < g.Co) yp[e] = o[e];
-                }
-            }
         }
     } else if (warp >= 8) {
         // ===================== gather / blend / convert producers =====================
@@ -267,6 +281,74 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             if (lane == 0) mbar_arrive(fullA(as));
         }
     }
+    if (warp >= 4) {
+        // ===================== epilogue: all 20 producer warps =====================
+        // TMEM lane quadrant q = warp % 4 (hardware rule); the 5 warps of a quadrant split the columns in chunks
+        // of 8, so each thread keeps only 2 x LDG.128 of the gate / residual operand in flight per chunk.
+        mbar_wait(accFull, 0);
+        tc_fence_after();
+        const int q = warp & 3, cc = (warp - 4) >> 2;  // cc = 0..4
+        const int row = q * 32 + lane;
+        const DfRow ro = sRow[row];
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool vec_y = (a.ldY & 3) == 0;
+        for (int stage = 0; stage <= a.chain; ++stage) {
+            if (stage == 1) mbar_wait(barC1, 0);
+            if (stage == 2) mbar_wait(barC2, 0);
+            if (stage) tc_fence_after();
+            const bool last = stage == a.chain;
+            const float *bias = stage == 0 ? a.bias : stage == 1 ? a.b1 : a.b2;
+            const uint32_t tcol = trow + (stage == 1 ? (uint32_t)NT : 0u);
+            for (int c0 = cc * 8; c0 < NT; c0 += 5 * 8) {
+                float v[8];
+                tmem_ld8(tcol + c0, v);
+                const int nb = n_tile * NT + c0;
+                float4 e0 = f4zero(), e1 = f4zero();
+                const bool live = ro.m >= 0 && nb < g.Co;
+                if (live && stage == 1) {
+                    e0 = ldg4(a.U + (i64)ro.m * a.ldU + nb); e1 = ldg4(a.U + (i64)ro.m * a.ldU + nb + 4);
+                } else if (live && stage == 2) {
+                    e0 = ldg4(a.R + (i64)ro.m * a.ldR + nb); e1 = ldg4(a.R + (i64)ro.m * a.ldR + nb + 4);
+                }
+                const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int ne = nb + e < g.Co ? nb + e : g.Co - 1;
+                    float t = live ? v[e] + (bias ? __ldg(bias + ne) : 0.f) : 0.f;
+                    if (stage == 1) t *= ev[e];
+                    else if (stage == 2) t += ev[e];
+                    o[e] = t;
+                }
+                if (last) {
+                    if (live) {
+                        float *yp = a.Y + (i64)ro.m * a.ldY + nb;
+                        if (vec_y && nb + 7 < g.Co) {
+                            *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4 *>(yp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (nb + e < g.Co) yp[e] = o[e];
+                        }
+                    }
+                } else {  // restage as the next GEMM's A operand: this thread's row, 16-byte chunk nb/8
+                    uint2 hi0, lo0, hi1, lo1;
+                    split_bf16x4(make_float4(o[0], o[1], o[2], o[3]), hi0, lo0);
+                    split_bf16x4(make_float4(o[4], o[5], o[6], o[7]), hi1, lo1);
+                    const int boff = (nb >> 3) * DF_LBO + row * 16;
+                    *reinterpret_cast<uint4 *>(sA + boff) = make_uint4(hi0.x, hi0.y, hi1.x, hi1.y);
+                    *reinterpret_cast<uint4 *>(sA + chainA_lo + boff) = make_uint4(lo0.x, lo0.y, lo1.x, lo1.y);
+                }
+            }
+            if (!last) {
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(stage == 0 ? barE1 : barE2);
+            }
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -302,7 +384,7 @@ __global__ void pack_weight_df_kernel(const float *__restrict__ w, __nv_bfloat16
 size_t df_smem_bytes(int NT)
 {
     return (size_t)DF_SA * DF_ASLOT + (size_t)DF_SB * 2 * (DF_KC / 8) * NT * 16 + (size_t)DF_SP * 128 * 64 + 128 * sizeof(DfRow) +
-           (2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1) * 8 + 16 + 128;
+           (2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6) * 8 + 16 + 128;
 }
 
 }  // namespace
@@ -317,9 +399,16 @@ bool deform3d_tc_supported(const IgemmArgs &a)
     return true;
 }
 
-int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, cudaStream_t st)
+bool deform3d_chain_supported(const IgemmArgs &a)
+{
+    const ConvGeo &g = a.geo;
+    return deform3d_tc_supported(a) && g.C == g.Co && g.C <= 96 && tc_kc(g.C) == g.C && tc_nt(g.Co) == g.Co;
+}
+
+int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, const DeformChain *chain, cudaStream_t st)
 {
     if (!deform3d_tc_supported(ga)) return DLKA_ERR_UNSUPPORTED;
+    if (chain && chain->stages && !deform3d_chain_supported(ga)) return DLKA_ERR_UNSUPPORTED;
     const ConvGeo &g = ga.geo;
     if (ga.M <= 0) return DLKA_OK;
     DeformTcArgs a;
@@ -328,6 +417,12 @@ int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, cudaStream_t st)
     const int n_tiles = (int)cdiv(g.Co, a.NT);
     a.tiles_d = (int)cdiv(g.Do, DF_BD); a.tiles_h = (int)cdiv(g.Ho, DF_BH); a.tiles_w = (int)cdiv(g.Wo, DF_BW);
     a.vol_c = (i64)g.D * g.H * g.W * g.C;
+    a.chain = 0; a.W1p = a.W2p = nullptr; a.b1 = a.b2 = a.U = a.R = nullptr; a.ldU = a.ldR = 0;
+    if (chain && chain->stages) {
+        a.chain = chain->stages;
+        a.W1p = (const uint8_t *)chain->W1p; a.b1 = chain->b1; a.U = chain->U; a.ldU = chain->ldU;
+        a.W2p = (const uint8_t *)chain->W2p; a.b2 = chain->b2; a.R = chain->R; a.ldR = chain->ldR;
+    }
     {
         const i64 total = (i64)n_tiles * g.K * g.C * a.NT;
         const int blocks = (int)(cdiv(total, 256) < 148 * 8 ? cdiv(total, 256) : 148 * 8);
@@ -342,7 +437,7 @@ int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, cudaStream_t st)
         configured = smem;
     }
     dim3 grid((unsigned)((i64)g.B * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)n_tiles);
-    DLKA_LAUNCH("tc_deform3d", st, (deform3d_tc_kernel<<<grid, DF_THREADS, smem, st>>>(a)));
+    DLKA_LAUNCH(a.chain ? "tc_deform3d_chain" : "tc_deform3d", st, (deform3d_tc_kernel<<<grid, DF_THREADS, smem, st>>>(a)));
     return DLKA_OK;
 }
 

@@ -154,6 +154,7 @@ int dwconv_cl(const float *x, const float *w, const float *bias, float *y, int B
     if (C % 4 != 0 || C / 4 > 256) return DLKA_ERR_UNSUPPORTED;
     if (kh != kw || (kd != kh && kd != 1)) return DLKA_ERR_UNSUPPORTED;
     DLKA_TRY(pack_dw(w, w_packed, C, kd * kh * kw, st));
+    if (dwconv_smem_supported(C, kd, kh, kw, dil)) return dwconv_smem(x, w_packed, bias, y, B, C, D, H, W, kh, dil, st);
     if (kh == 5 && dil == 1) return launch_dw<5, 1, 4>(x, w_packed, bias, y, B, C, D, H, W, kd, st);
     if (kh == 7 && dil == 3) return launch_dw<7, 3, 4>(x, w_packed, bias, y, B, C, D, H, W, kd, st);
     return DLKA_ERR_UNSUPPORTED;

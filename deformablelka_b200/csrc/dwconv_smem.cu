@@ -1,0 +1,185 @@
+// dwconv_smem.cu -- depthwise K^3 stencil with dilation L (5^3/L=1 and 7^3/L=3 of LKA3d_deform,
+// transformerblock.py:637-638) on CUDA cores, fp32, shared-memory plane streaming.
+//
+// A dilated conv with dilation L only couples voxels of the same residue mod L on every axis, so the volume is
+// processed as L^3 independent sub-lattices ("phases"), each a dense K^3 conv with halo (K-1)/2.
+// One CTA = (batch b, 32-channel chunk, phase, lattice tile TD x TH x TW).  Input planes of the tile
+// (TH+K-1) x (TW+K-1) voxels x 32 channels (128 B per voxel) stream through a cp.async double buffer; every
+// thread owns 4 channels (float4) x R outputs along w x TD outputs along d in registers, so each input row loaded
+// from shared memory feeds up to TD*K*R FMAs and each weight vector (broadcast across the warp) R FMAs.
+#include "kernels.cuh"
+
+namespace dlka {
+namespace {
+
+constexpr int DS_TD = 4, DS_TH = 8, DS_TW = 16, DS_R = 4;
+constexpr int DS_CCH = 32;                                     // channels per CTA
+constexpr int DS_THREADS = (DS_CCH / 4) * (DS_TW / DS_R) * DS_TH;  // 8 * 4 * 8 = 256
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int K, int L>
+__global__ void __launch_bounds__(DS_THREADS, 1) dwconv_smem_kernel(const float *__restrict__ x, const float *__restrict__ wp,
+                                                                    const float *__restrict__ bias, float *__restrict__ y,
+                                                                    int C, int D, int H, int W, int tiles_d, int tiles_h, int tiles_w)
+{
+    constexpr int P = (K - 1) / 2;
+    constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;   // plane extent (lattice voxels)
+    constexpr int PLANE_F4 = PH * PW * (DS_CCH / 4);         // float4 elements per plane
+    constexpr int NPLANES = DS_TD + K - 1;
+    extern __shared__ __align__(128) float4 smem4[];
+    float4 *sW = smem4;                                      // [K^3][8] float4 : weights of this channel chunk
+    float4 *sP = sW + K * K * K * (DS_CCH / 4);              // [2][PH][PW][8] float4
+
+    const int tid = threadIdx.x;
+    const int q = tid & 7, wr = (tid >> 3) & 3, hl = tid >> 5;
+    // CTA decomposition: x = tile, y = phase * nchunks + chunk, z = batch
+    int bid = blockIdx.x;
+    const int tw = bid % tiles_w; bid /= tiles_w;
+    const int th = bid % tiles_h; bid /= tiles_h;
+    const int td = bid;
+    const int nchunks = C / DS_CCH;
+    const int chunk = blockIdx.y % nchunks, phase = blockIdx.y / nchunks;
+    const int pw_ = phase % L, ph_ = (phase / L) % L, pd_ = phase / (L * L);
+    const int b = blockIdx.z;
+    const int c0 = chunk * DS_CCH;
+    // lattice tile origin and this thread's outputs
+    const int zd0 = td * DS_TD, zh0 = th * DS_TH, zw0 = tw * DS_TW;
+    const float *xb = x + (i64)b * D * H * W * C + c0;
+
+    // weights of the chunk -> smem ([tap][C] packed layout in global)
+    for (int i = tid; i < K * K * K * (DS_CCH / 4); i += DS_THREADS) {
+        const int tap = i >> 3, qq = i & 7;
+        sW[i] = ldg4(wp + (i64)tap * C + c0 + qq * 4);
+    }
+
+    auto load_plane = [&](int s, int buf) {
+        // lattice d index of plane s, real coordinate
+        const int zd = zd0 - P + s;
+        const int dr = pd_ + L * zd;
+        const bool dok = zd >= 0 && dr < D;
+        float4 *dst = sP + buf * PLANE_F4;
+        for (int i = tid; i < PLANE_F4; i += DS_THREADS) {
+            const int qq = i & 7, v = i >> 3;
+            const int ww = v % PW, hh = v / PW;
+            const int zh = zh0 - P + hh, zw = zw0 - P + ww;
+            const int hr = ph_ + L * zh, wrr = pw_ + L * zw;
+            const bool ok = dok && zh >= 0 && zw >= 0 && hr < H && wrr < W;
+            const float *src = ok ? xb + (((i64)dr * H + hr) * W + wrr) * C + qq * 4 : xb;
+            cp_async16(dst + i, src, ok);
+        }
+        cp_async_commit();
+    };
+
+    float4 acc[DS_TD][DS_R];
+    {
+        const float4 bv = bias ? ldg4(bias + c0 + q * 4) : f4zero();
+#pragma unroll
+        for (int t = 0; t < DS_TD; ++t)
+#pragma unroll
+            for (int r = 0; r < DS_R; ++r) acc[t][r] = bv;
+    }
+
+    load_plane(0, 0);
+#pragma unroll 1
+    for (int s = 0; s < NPLANES; ++s) {
+        if (s + 1 < NPLANES) {
+            load_plane(s + 1, (s + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float4 *pl = sP + (s & 1) * PLANE_F4;
+        // plane s contributes to output t with depth tap i = s - t
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            float4 in[DS_R + K - 1];
+            const float4 *row = pl + ((hl + j) * PW + wr * DS_R) * 8 + q;
+#pragma unroll
+            for (int e = 0; e < DS_R + K - 1; ++e) in[e] = row[e * 8];
+#pragma unroll
+            for (int t = 0; t < DS_TD; ++t) {
+                const int i = s - t;
+                if (i < 0 || i >= K) continue;  // uniform across the CTA
+                const float4 *wrow = sW + ((i * K + j) * K) * 8 + q;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float4 wv = wrow[k * 8];
+#pragma unroll
+                    for (int r = 0; r < DS_R; ++r) {
+                        acc[t][r].x = fmaf(wv.x, in[r + k].x, acc[t][r].x);
+                        acc[t][r].y = fmaf(wv.y, in[r + k].y, acc[t][r].y);
+                        acc[t][r].z = fmaf(wv.z, in[r + k].z, acc[t][r].z);
+                        acc[t][r].w = fmaf(wv.w, in[r + k].w, acc[t][r].w);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // plane buffer (s & 1) is refilled two iterations later
+    }
+
+    // store: real coordinates of this thread's outputs
+    const int hr = ph_ + L * (zh0 + hl);
+    if (hr < H) {
+#pragma unroll
+        for (int t = 0; t < DS_TD; ++t) {
+            const int dr = pd_ + L * (zd0 + t);
+            if (dr >= D) continue;
+#pragma unroll
+            for (int r = 0; r < DS_R; ++r) {
+                const int wrr = pw_ + L * (zw0 + wr * DS_R + r);
+                if (wrr < W)
+                    *reinterpret_cast<float4 *>(y + ((((i64)b * D + dr) * H + hr) * W + wrr) * C + c0 + q * 4) = acc[t][r];
+            }
+        }
+    }
+}
+
+template <int K, int L>
+int launch_ds(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, cudaStream_t st)
+{
+    constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;
+    const size_t smem = ((size_t)K * K * K * 8 + 2 * (size_t)PH * PW * 8) * sizeof(float4);
+    auto kern = dwconv_smem_kernel<K, L>;
+    static thread_local bool configured = false;
+    if (!configured) {
+        DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    // lattice extents of the largest phase
+    const int ld = (int)cdiv(D, L), lh = (int)cdiv(H, L), lw = (int)cdiv(W, L);
+    const int tiles_d = (int)cdiv(ld, DS_TD), tiles_h = (int)cdiv(lh, DS_TH), tiles_w = (int)cdiv(lw, DS_TW);
+    dim3 grid((unsigned)(tiles_d * tiles_h * tiles_w), (unsigned)(L * L * L * (C / DS_CCH)), (unsigned)B);
+    if (grid.y > 65535u || grid.z > 65535u) return DLKA_ERR_UNSUPPORTED;
+    DLKA_LAUNCH(K == 5 ? "dwconv3d_smem_k5" : "dwconv3d_smem_k7d3", st,
+                (kern<<<grid, DS_THREADS, smem, st>>>(x, wp, bias, y, C, D, H, W, tiles_d, tiles_h, tiles_w)));
+    return DLKA_OK;
+}
+
+}  // namespace
+
+bool dwconv_smem_supported(int C, int kd, int kh, int kw, int dil)
+{
+    if (C % DS_CCH != 0) return false;
+    return (kd == 5 && kh == 5 && kw == 5 && dil == 1) || (kd == 7 && kh == 7 && kw == 7 && dil == 3);
+}
+
+// wp: packed [taps][C] weights (pack_dw layout)
+int dwconv_smem(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, int k, int dil,
+                cudaStream_t st)
+{
+    if (k == 5 && dil == 1) return launch_ds<5, 1>(x, wp, bias, y, B, C, D, H, W, st);
+    if (k == 7 && dil == 3) return launch_ds<7, 3>(x, wp, bias, y, B, C, D, H, W, st);
+    return DLKA_ERR_UNSUPPORTED;
+}
+
+}  // namespace dlka

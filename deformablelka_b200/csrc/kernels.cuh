@@ -42,8 +42,15 @@ int tc_pack_weight(const float *w, void *bp, int Co, int C, int taps, cudaStream
 int igemm_tc(const IgemmArgs &a, const void *bp, cudaStream_t st);
 
 // 3D deformable conv, brick tiles + chunk-major K (L1-resident gather) -- deform_tc.cu
+// optional fused epilogue chain: conv1 (1x1) * U  [-> proj_2 (1x1) + R]; weights in tc_pack_weight layout
+struct DeformChain {
+    int stages;           // 1 or 2
+    const void *W1p; const float *b1; const float *U; int ldU;
+    const void *W2p; const float *b2; const float *R; int ldR;
+};
 bool deform3d_tc_supported(const IgemmArgs &a);
-int deform3d_tc(const IgemmArgs &a, const float *w, void *bp, cudaStream_t st);
+bool deform3d_chain_supported(const IgemmArgs &a);
+int deform3d_tc(const IgemmArgs &a, const float *w, void *bp, const DeformChain *chain, cudaStream_t st);
 
 // zero-copy tiled regular conv on tcgen05 (stride 1, groups 1, no epilogue operand) -- conv_tc.cu
 bool conv_tiled_supported(const IgemmArgs &a);
@@ -59,6 +66,11 @@ int transpose_sc_to_cs(const float *in, float *out, int B, int C, i64 S, cudaStr
 // w: PyTorch layout [C][1][kd][kh][kw]; bias [C] or null.  pad = dil*(k-1)/2 on each axis.
 int dwconv_cl(const float *x, const float *w, const float *bias, float *y, int B, int C, int D, int H, int W, int kd,
               int kh, int kw, int dil, float *w_packed /*[K][C]*/, cudaStream_t st);
+
+// shared-memory plane-streaming variant (C % 32 == 0; 5^3 dil 1 and 7^3 dil 3) -- dwconv_smem.cu
+bool dwconv_smem_supported(int C, int kd, int kh, int kw, int dil);
+int dwconv_smem(const float *x, const float *w_packed, const float *bias, float *y, int B, int C, int D, int H, int W, int k,
+                int dil, cudaStream_t st);
 
 // ---------------- depthwise deformable conv (groups == C == Co), channels-last ----------------------
 // w: [C][1][taps] PyTorch layout; Off [M][dg*ndim*K]; Mask optional; bias optional.
