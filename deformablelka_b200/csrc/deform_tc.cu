@@ -23,11 +23,21 @@ namespace {
 using namespace ptx;
 
 constexpr int DF_KC = 32;                 // channels per K step (one 128-byte line per voxel)
+#ifndef DLKA_DF_REGION
+#define DLKA_DF_REGION 0   // 0: gather through L1 (LDG, measured faster: 12.8 ms); 1: shared-memory staged region (14.0 ms: reload bubbles)
+#endif
 #ifndef DLKA_DF_SA
+#if DLKA_DF_REGION
+#define DLKA_DF_SA 2
+#define DLKA_DF_SB 2
+#define DLKA_DF_SP 3
+#else
 #define DLKA_DF_SA 3
 #define DLKA_DF_SB 3
 #define DLKA_DF_SP 4
 #endif
+#endif
+constexpr bool DF_REGION = DLKA_DF_REGION != 0;
 constexpr int DF_SA = DLKA_DF_SA, DF_SB = DLKA_DF_SB, DF_SP = DLKA_DF_SP;
 constexpr int DF_LBO = 2048 + 32;         // A plane stride (bank-spread padding; see profiles/r01 notes)
 constexpr int DF_APLANE = (DF_KC / 8) * DF_LBO;
@@ -35,6 +45,13 @@ constexpr int DF_ASLOT = 2 * DF_APLANE;
 constexpr int DF_PARAM_WARPS = 4, DF_GATHER_WARPS = 16;
 constexpr int DF_THREADS = (4 + DF_PARAM_WARPS + DF_GATHER_WARPS) * 32;
 constexpr int DF_BD = 4, DF_BH = 4, DF_BW = 8;  // brick
+// staged region = brick + halo: covers every corner of samples with |offset| <~ 1 (tap reach 1 + offset + 1);
+// samples that leave it take the guarded global path, so any offset stays correct.
+constexpr int DF_HALO = 2;
+constexpr int DF_RD = DF_BD + 2 * DF_HALO, DF_RH = DF_BH + 2 * DF_HALO, DF_RW = DF_BW + 2 * DF_HALO;
+constexpr int DF_RV = DF_RD * DF_RH * DF_RW;                       // 768 voxels x 128 B (32 fp32 channels)
+constexpr int DF_REGION_BYTES = DF_REGION ? DF_RV * 128 : 0;
+constexpr int DF_PSTRIDE = 5;                                      // int4 per parameter record (80 B: bank spread)
 
 struct DeformTcArgs {
     ConvGeo g;
@@ -66,28 +83,40 @@ struct DfRow {
     int pad[3];
 };
 
-__device__ __forceinline__ void df_make_params(const DeformTcArgs &a, const DfRow &ri, int tap, int4 *prm)
+// 8 corner offsets + 8 masked weights.  Region mode: offsets are byte offsets into the staged region when all 8
+// (clamped) corners lie inside it, else global element offsets with bit 31 of o0.x set (guarded global path).
+__device__ __forceinline__ void df_make_params(const DeformTcArgs &a, const DfRow &ri, int ii, int jj, int kk, float od, float oh,
+                                               float ow, int4 *prm, int rd0, int rh0, int rw0)
 {
     const ConvGeo &g = a.g;
     int4 o0 = make_int4(0, 0, 0, 0), o1 = o0;
     float4 w0 = f4zero(), w1 = f4zero();
     if (ri.m >= 0) {
-        const int kk = tap % g.kw, jj = (tap / g.kw) % g.kh, ii = tap / (g.kw * g.kh);
-        const float *off = a.Off + (i64)ri.m * a.ldOff + tap * 3;
-        const float pd = sample_pos(ri.d, g.sd, g.pd, ii, g.dd, __ldg(off));
-        const float ph = sample_pos(ri.h, g.sh, g.ph, jj, g.dh, __ldg(off + 1));
-        const float pw = sample_pos(ri.w, g.sw, g.pw, kk, g.dw, __ldg(off + 2));
+        const float pd = sample_pos(ri.d, g.sd, g.pd, ii, g.dd, od);
+        const float ph = sample_pos(ri.h, g.sh, g.ph, jj, g.dh, oh);
+        const float pw = sample_pos(ri.w, g.sw, g.pw, kk, g.dw, ow);
         const Sample3 s = make_sample3(pd, ph, pw, g.D, g.H, g.W);
         if (s.mask & 1) {
             const float ld = s.l[0], lh = s.l[1], lw = s.l[2], hd = 1.f - ld, hh = 1.f - lh, hw = 1.f - lw;
             const int d0 = max(s.lo[0], 0), d1 = min(s.lo[0] + 1, g.D - 1);
             const int h0 = max(s.lo[1], 0), h1 = min(s.lo[1] + 1, g.H - 1);
             const int x0 = max(s.lo[2], 0), x1 = min(s.lo[2] + 1, g.W - 1);
-            const int sH = g.W * g.C, sD = g.H * sH;
-            o0.x = d0 * sD + h0 * sH + x0 * g.C; o0.y = d0 * sD + h0 * sH + x1 * g.C;
-            o0.z = d0 * sD + h1 * sH + x0 * g.C; o0.w = d0 * sD + h1 * sH + x1 * g.C;
-            o1.x = d1 * sD + h0 * sH + x0 * g.C; o1.y = d1 * sD + h0 * sH + x1 * g.C;
-            o1.z = d1 * sD + h1 * sH + x0 * g.C; o1.w = d1 * sD + h1 * sH + x1 * g.C;
+            const int zd0 = d0 - rd0, zd1 = d1 - rd0, zh0 = h0 - rh0, zh1 = h1 - rh0, zx0 = x0 - rw0, zx1 = x1 - rw0;
+            const bool inside = DF_REGION && zd0 >= 0 && zd1 < DF_RD && zh0 >= 0 && zh1 < DF_RH && zx0 >= 0 && zx1 < DF_RW;
+            if (inside) {
+                const int sH = DF_RW * 128, sD = DF_RH * sH;
+                o0.x = zd0 * sD + zh0 * sH + zx0 * 128; o0.y = zd0 * sD + zh0 * sH + zx1 * 128;
+                o0.z = zd0 * sD + zh1 * sH + zx0 * 128; o0.w = zd0 * sD + zh1 * sH + zx1 * 128;
+                o1.x = zd1 * sD + zh0 * sH + zx0 * 128; o1.y = zd1 * sD + zh0 * sH + zx1 * 128;
+                o1.z = zd1 * sD + zh1 * sH + zx0 * 128; o1.w = zd1 * sD + zh1 * sH + zx1 * 128;
+            } else {
+                const int sH = g.W * g.C, sD = g.H * sH;
+                o0.x = d0 * sD + h0 * sH + x0 * g.C; o0.y = d0 * sD + h0 * sH + x1 * g.C;
+                o0.z = d0 * sD + h1 * sH + x0 * g.C; o0.w = d0 * sD + h1 * sH + x1 * g.C;
+                o1.x = d1 * sD + h0 * sH + x0 * g.C; o1.y = d1 * sD + h0 * sH + x1 * g.C;
+                o1.z = d1 * sD + h1 * sH + x0 * g.C; o1.w = d1 * sD + h1 * sH + x1 * g.C;
+                if (DF_REGION) o0.x |= (int)0x80000000;
+            }
             w0.x = (s.mask & (1 << 1)) ? hd * hh * hw : 0.f; w0.y = (s.mask & (1 << 2)) ? hd * hh * lw : 0.f;
             w0.z = (s.mask & (1 << 3)) ? hd * lh * hw : 0.f; w0.w = (s.mask & (1 << 4)) ? hd * lh * lw : 0.f;
             w1.x = (s.mask & (1 << 5)) ? ld * hh * hw : 0.f; w1.y = (s.mask & (1 << 6)) ? ld * hh * lw : 0.f;
@@ -107,11 +136,13 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     const int B_PLANE = (DF_KC / 8) * NT * 16, B_SLOT = 2 * B_PLANE;
     uint8_t *sA = smem;
     uint8_t *sB = sA + DF_SA * DF_ASLOT;
-    int4 *sPrm = reinterpret_cast<int4 *>(sB + DF_SB * B_SLOT);                 // [SP][128][4]
-    DfRow *sRow = reinterpret_cast<DfRow *>(sPrm + DF_SP * 128 * 4);            // [128]
+    int4 *sPrm = reinterpret_cast<int4 *>(sB + DF_SB * B_SLOT);                 // [SP][128][PSTRIDE]
+    DfRow *sRow = reinterpret_cast<DfRow *>(sPrm + DF_SP * 128 * DF_PSTRIDE);   // [128]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sRow + 128);
     constexpr int NBARS = 2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
+    uint8_t *sReg = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~(uintptr_t)127);  // region
+    uint8_t *sChainW = DF_REGION ? sReg : sB;   // chain weights: the region is free once the main loop is done
     const uint32_t bar0 = smem_u32(bars);
     auto fullA = [&](int s) { return bar0 + 8u * s; };
     auto emptyA = [&](int s) { return bar0 + 8u * (DF_SA + s); };
@@ -194,7 +225,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                 mbar_wait(stage == 1 ? barW1 : barW2, 0);
                 mbar_wait(stage == 1 ? barE1 : barE2, 0);
                 tc_fence_after();
-                const uint32_t ahi = smem_u32(sA), alo = ahi + chainA_lo, bhi = smem_u32(sB), blo = bhi + chainB_lo;
+                const uint32_t ahi = smem_u32(sA), alo = ahi + chainA_lo, bhi = smem_u32(sChainW), blo = bhi + chainB_lo;
                 const uint32_t d_tmem = tmem_base + (stage == 1 ? (uint32_t)NT : 0u);
                 for (int pass = 0; pass < 3; ++pass) {
                     const uint32_t ab = pass == 1 ? alo : ahi, bb = pass == 2 ? blo : bhi;
@@ -221,11 +252,11 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                 const uint32_t wbytes = 2u * chainB_lo;
                 mbar_wait(accFull, 0);                      // every main-loop MMA has retired: sB is free
                 mbar_arrive_expect_tx(barW1, wbytes);
-                bulk_g2s(smem_u32(sB), a.W1p, wbytes, barW1);
+                bulk_g2s(smem_u32(sChainW), a.W1p, wbytes, barW1);
                 if (a.chain == 2) {
                     mbar_wait(barC1, 0);                    // conv1 MMAs done reading sB
                     mbar_arrive_expect_tx(barW2, wbytes);
-                    bulk_g2s(smem_u32(sB), a.W2p, wbytes, barW2);
+                    bulk_g2s(smem_u32(sChainW), a.W2p, wbytes, barW2);
                 }
             }
         }
@@ -233,33 +264,73 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
         // ===================== sample-parameter producers (one thread per brick row) =====================
         const int r = tid - 128;
         const DfRow ri = sRow[r];
+        const float *offrow = a.Off + (i64)(ri.m >= 0 ? ri.m : 0) * a.ldOff;
+        // the 3 offsets of the NEXT (row, tap) are fetched one iteration ahead: their global latency overlaps this tap's math
+        float od = __ldg(offrow), oh = __ldg(offrow + 1), ow = __ldg(offrow + 2);
+        int ps = 0, tap = 0, ii = 0, jj = 0, kk = 0;
+        uint32_t ph = 1;
         for (int ks = 0; ks < KS; ++ks) {
-            const int ps = ks % DF_SP, tap = ks % K;
-            mbar_wait(emptyP(ps), ((ks / DF_SP) & 1) ^ 1);
-            df_make_params(a, ri, tap, sPrm + (ps * 128 + r) * 4);
+            const int ntap = tap + 1 == K ? 0 : tap + 1;
+            const float nod = __ldg(offrow + ntap * 3), noh = __ldg(offrow + ntap * 3 + 1), now = __ldg(offrow + ntap * 3 + 2);
+            mbar_wait(emptyP(ps), ph);
+            df_make_params(a, ri, ii, jj, kk, od, oh, ow, sPrm + (ps * 128 + r) * DF_PSTRIDE, td * DF_BD - DF_HALO,
+                           th * DF_BH - DF_HALO, tw * DF_BW - DF_HALO);
             __syncwarp();
             if (lane == 0) mbar_arrive(fullP(ps));
+            od = nod; oh = noh; ow = now;
+            tap = ntap;
+            if (++kk == g.kw) { kk = 0; if (++jj == g.kh) { jj = 0; if (++ii == g.kd) ii = 0; } }
+            if (++ps == DF_SP) { ps = 0; ph ^= 1; }
         }
     } else if (warp >= 8) {
         // ===================== gather / blend / convert producers =====================
         const int gt = tid - 256;                      // 0..511
         const int cg = gt & 7;                         // float4 of the 32-channel chunk
         const float *Xb = a.X + (i64)b * a.vol_c + cg * 4;
+        const uint8_t *rbase = sReg + cg * 16;
+        const int rd0 = td * DF_BD - DF_HALO, rh0 = th * DF_BH - DF_HALO, rw0 = tw * DF_BW - DF_HALO;
+        int as = 0, ps = 0, tap = 0, chunk = 0;
+        uint32_t phA = 1, phP = 0;                      // parities: emptyA starts "free", fullP starts "not ready"
         for (int ks = 0; ks < KS; ++ks) {
-            const int as = ks % DF_SA, ps = ks % DF_SP, chunk = ks / K;
-            mbar_wait(fullP(ps), (ks / DF_SP) & 1);
-            mbar_wait(emptyA(as), ((ks / DF_SA) & 1) ^ 1);
+            if (DF_REGION && tap == 0) {
+                // (re)stage the brick + halo region for this 32-channel chunk: 768 voxels x 128 B, zero outside the volume
+                asm volatile("bar.sync 2, %0;" ::"r"(DF_GATHER_WARPS * 32) : "memory");   // everyone done with the old chunk
+                for (int i = gt; i < DF_RV * 8; i += DF_GATHER_WARPS * 32) {
+                    const int qq = i & 7, v = i >> 3;
+                    const int rx = v % DF_RW, ry = (v / DF_RW) % DF_RH, rz = v / (DF_RW * DF_RH);
+                    const int d = rd0 + rz, h = rh0 + ry, w = rw0 + rx;
+                    const bool ok = (unsigned)d < (unsigned)g.D && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W;
+                    const float *src = ok ? a.X + (i64)b * a.vol_c + (((i64)d * g.H + h) * g.W + w) * g.C + chunk * DF_KC + qq * 4 : a.X;
+                    const unsigned dst = smem_u32(sReg + i * 16);
+                    const int sz = ok ? 16 : 0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                asm volatile("bar.sync 2, %0;" ::"r"(DF_GATHER_WARPS * 32) : "memory");
+            }
+            mbar_wait(fullP(ps), phP);
+            mbar_wait(emptyA(as), phA);
             uint8_t *slot = sA + as * DF_ASLOT;
             const float *base = Xb + chunk * DF_KC;
             float4 acc[2];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const int row = (gt >> 3) + s * 64;
-                const int4 *prm = sPrm + (ps * 128 + row) * 4;
+                const int4 *prm = sPrm + (ps * 128 + row) * DF_PSTRIDE;
                 const int4 o0 = prm[0], o1 = prm[1];
                 const float4 w0 = *reinterpret_cast<const float4 *>(prm + 2), w1 = *reinterpret_cast<const float4 *>(prm + 3);
-                const float4 v0 = ldg4(base + o0.x), v1 = ldg4(base + o0.y), v2 = ldg4(base + o0.z), v3 = ldg4(base + o0.w);
-                const float4 v4 = ldg4(base + o1.x), v5 = ldg4(base + o1.y), v6 = ldg4(base + o1.z), v7 = ldg4(base + o1.w);
+                float4 v0, v1, v2, v3, v4, v5, v6, v7;
+                if (DF_REGION && o0.x >= 0) {
+                    v0 = *reinterpret_cast<const float4 *>(rbase + o0.x); v1 = *reinterpret_cast<const float4 *>(rbase + o0.y);
+                    v2 = *reinterpret_cast<const float4 *>(rbase + o0.z); v3 = *reinterpret_cast<const float4 *>(rbase + o0.w);
+                    v4 = *reinterpret_cast<const float4 *>(rbase + o1.x); v5 = *reinterpret_cast<const float4 *>(rbase + o1.y);
+                    v6 = *reinterpret_cast<const float4 *>(rbase + o1.z); v7 = *reinterpret_cast<const float4 *>(rbase + o1.w);
+                } else {
+                    const int ox = o0.x & 0x7fffffff;
+                    v0 = ldg4(base + ox); v1 = ldg4(base + o0.y); v2 = ldg4(base + o0.z); v3 = ldg4(base + o0.w);
+                    v4 = ldg4(base + o1.x); v5 = ldg4(base + o1.y); v6 = ldg4(base + o1.z); v7 = ldg4(base + o1.w);
+                }
                 float4 r = f4zero();
                 fma4(r, w0.x, v0); fma4(r, w0.y, v1); fma4(r, w0.z, v2); fma4(r, w0.w, v3);
                 fma4(r, w1.x, v4); fma4(r, w1.y, v5); fma4(r, w1.z, v6); fma4(r, w1.w, v7);
@@ -279,6 +350,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(fullA(as));
+            if (++as == DF_SA) { as = 0; phA ^= 1; }
+            if (++ps == DF_SP) { ps = 0; phP ^= 1; }
+            if (++tap == K) { tap = 0; ++chunk; }
         }
     }
     if (warp >= 4) {
@@ -383,8 +457,8 @@ __global__ void pack_weight_df_kernel(const float *__restrict__ w, __nv_bfloat16
 
 size_t df_smem_bytes(int NT)
 {
-    return (size_t)DF_SA * DF_ASLOT + (size_t)DF_SB * 2 * (DF_KC / 8) * NT * 16 + (size_t)DF_SP * 128 * 64 + 128 * sizeof(DfRow) +
-           (2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6) * 8 + 16 + 128;
+    return (size_t)DF_SA * DF_ASLOT + (size_t)DF_SB * 2 * (DF_KC / 8) * NT * 16 + (size_t)DF_SP * 128 * DF_PSTRIDE * 16 +
+           128 * sizeof(DfRow) + (2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6) * 8 + 16 + 256 + DF_REGION_BYTES;
 }
 
 }  // namespace
