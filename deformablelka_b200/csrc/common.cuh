@@ -159,12 +159,9 @@ __device__ __forceinline__ Sample2 make_sample2(float ph, float pw, int H, int W
     return s;
 }
 
+__device__ __forceinline__ void fma4(float4 &acc, float w, const float4 &v);
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-__device__ __forceinline__ void fma4(float4 &acc, float w, const float4 &v)
-{
-    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
-}
 
 // Trilinear blend of 4 consecutive channels at a sample; `vol` points at channel c of sample b
 // (channels-last volume [D,H,W,C]).  Weight products follow cuh:67-68 (hd*hh*hw ...).
@@ -200,6 +197,38 @@ __device__ __forceinline__ float4 bilinear4(const float *__restrict__ img, const
     if (s.mask & (1 << 4)) fma4(acc, lh * lw, ldg4(p00 + sH + C));
     return acc;
 }
+
+// packed 2 x fp32 FMA (Blackwell FFMA2): acc += w * x element-wise on a float4 (2 instructions instead of 4)
+__device__ __forceinline__ void fma4v(float4 &acc, const float4 &w, const float4 &x)
+{
+    unsigned long long a0, a1, w0, w1, x0, x1;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(acc.x), "f"(acc.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(acc.z), "f"(acc.w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(w0) : "f"(w.x), "f"(w.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(w1) : "f"(w.z), "f"(w.w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x0) : "f"(x.x), "f"(x.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x1) : "f"(x.z), "f"(x.w));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(w0), "l"(x0));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(w1), "l"(x1));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.z), "=f"(acc.w) : "l"(a1));
+}
+// acc += s * x with a scalar weight (broadcast into both halves)
+__device__ __forceinline__ void fma4s(float4 &acc, float s, const float4 &x)
+{
+    unsigned long long a0, a1, sw, x0, x1;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(acc.x), "f"(acc.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(acc.z), "f"(acc.w));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(sw) : "f"(s));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x0) : "f"(x.x), "f"(x.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x1) : "f"(x.z), "f"(x.w));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(sw), "l"(x0));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(sw), "l"(x1));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.z), "=f"(acc.w) : "l"(a1));
+}
+
+__device__ __forceinline__ void fma4(float4 &acc, float w, const float4 &v) { fma4s(acc, w, v); }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 

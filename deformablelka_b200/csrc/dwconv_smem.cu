@@ -115,12 +115,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dwconv_smem_kernel(const float 
                 for (int k = 0; k < K; ++k) {
                     const float4 wv = wrow[k * 8];
 #pragma unroll
-                    for (int r = 0; r < DS_R; ++r) {
-                        acc[t][r].x = fmaf(wv.x, in[r + k].x, acc[t][r].x);
-                        acc[t][r].y = fmaf(wv.y, in[r + k].y, acc[t][r].y);
-                        acc[t][r].z = fmaf(wv.z, in[r + k].z, acc[t][r].z);
-                        acc[t][r].w = fmaf(wv.w, in[r + k].w, acc[t][r].w);
-                    }
+                    for (int r = 0; r < DS_R; ++r) fma4v(acc[t][r], wv, in[r + k]);
                 }
             }
         }
