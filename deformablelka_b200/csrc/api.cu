@@ -610,10 +610,44 @@ int dlka_lka_attention3d_deform_forward_host(const dlkaBlock3dParams *params, co
     DLKA_TRY(check_device());
     cudaStream_t st = (cudaStream_t)stream;
     float *xd = (float *)dev_scratch, *yd = xd + n;
-    DLKA_CUDA_TRY(cudaMemcpyAsync(xd, x_host, n * sizeof(float), cudaMemcpyHostToDevice, st));
-    DLKA_TRY(dlka_lka_attention3d_deform_forward(params, xd, yd, B, C, D1, D2, D3, math, workspace, workspace_bytes, stream));
-    DLKA_CUDA_TRY(cudaMemcpyAsync(y_host, yd, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    DLKA_CUDA_TRY(cudaStreamSynchronize(st));
+    // Per-sample software pipeline over three streams: H2D of sample b+1 and D2H of sample b-1 overlap the compute of
+    // sample b (samples are independent: SURVEY.md 8e).  Compute stays on the caller's stream.
+    static thread_local cudaStream_t s_in = nullptr, s_out = nullptr;
+    if (!s_in) {
+        DLKA_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        DLKA_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    }
+    const size_t n1 = n / B;
+    std::vector<cudaEvent_t> ev(2 * (size_t)B + 2);
+    for (auto &e : ev) DLKA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int rc = DLKA_OK;
+    do {
+        cudaEvent_t e_start = ev[2 * B], e_done = ev[2 * B + 1];
+        if (cudaEventRecord(e_start, st) != cudaSuccess || cudaStreamWaitEvent(s_in, e_start, 0) != cudaSuccess ||
+            cudaStreamWaitEvent(s_out, e_start, 0) != cudaSuccess) { rc = DLKA_ERR_CUDA; break; }
+        for (int b = 0; b < B && rc == DLKA_OK; ++b) {
+            if (cudaMemcpyAsync(xd + b * n1, x_host + b * n1, n1 * sizeof(float), cudaMemcpyHostToDevice, s_in) != cudaSuccess ||
+                cudaEventRecord(ev[b], s_in) != cudaSuccess) rc = DLKA_ERR_CUDA;
+        }
+        for (int b = 0; b < B && rc == DLKA_OK; ++b) {
+            if (cudaStreamWaitEvent(st, ev[b], 0) != cudaSuccess) { rc = DLKA_ERR_CUDA; break; }
+            rc = dlka_lka_attention3d_deform_forward(params, xd + b * n1, yd + b * n1, 1, C, D1, D2, D3, math, workspace,
+                                                     workspace_bytes, stream);
+            if (rc != DLKA_OK) break;
+            if (cudaEventRecord(ev[B + b], st) != cudaSuccess || cudaStreamWaitEvent(s_out, ev[B + b], 0) != cudaSuccess ||
+                cudaMemcpyAsync(y_host + b * n1, yd + b * n1, n1 * sizeof(float), cudaMemcpyDeviceToHost, s_out) != cudaSuccess)
+                rc = DLKA_ERR_CUDA;
+        }
+        if (rc != DLKA_OK) break;
+        if (cudaEventRecord(e_done, s_out) != cudaSuccess || cudaStreamWaitEvent(st, e_done, 0) != cudaSuccess) rc = DLKA_ERR_CUDA;
+    } while (0);
+    const cudaError_t se = cudaStreamSynchronize(st);
+    cudaStreamSynchronize(s_in);
+    cudaStreamSynchronize(s_out);
+    for (auto &e : ev) cudaEventDestroy(e);
+    if (rc == DLKA_ERR_CUDA) return record_cuda_error(cudaGetLastError(), "dlka_lka_attention3d_deform_forward_host");
+    if (rc != DLKA_OK) return rc;
+    if (se != cudaSuccess) return record_cuda_error(se, "cudaStreamSynchronize");
     return DLKA_OK;
 }
 

@@ -46,3 +46,13 @@ class LKA_Attention3d_deform(nn.Module):
 
     def forward(self, x, B, C, H, W, D):
         return ops.lka_attention3d_deform_forward(_block3d_params(self.spatial_gating_unit, self), x, B, C, H, W, D)
+
+    def forward_host(self, x_host, B, C, H, W, D, y_host=None):
+        """Same forward for HOST tokens (ideally pinned): the library pipelines per-sample H2D copies, compute and D2H
+        copies over three streams.  Parameters stay on the module's CUDA device; returns a host tensor."""
+        import torch
+        if y_host is None:
+            y_host = torch.empty_like(x_host, pin_memory=x_host.is_pinned())
+        dev = self.proj_1.weight.device
+        return ops.lka_attention3d_deform_forward_host(_block3d_params(self.spatial_gating_unit, self), x_host, y_host,
+                                                       B, C, H, W, D, dev)

@@ -284,3 +284,18 @@ def test_streams_and_noncontiguous_inputs(dl):
     xt = x.permute(0, 1, 3, 2)  # non-contiguous view: the host makes it contiguous like nn.Conv2d would accept
     assert torch.equal(m(xt), m(xt.contiguous()))
     assert dl.launch_count() > 0
+
+
+def test_forward_host_pipeline_matches_device_forward(dl, oracle, math):
+    """The host-buffer entry (per-sample H2D / compute / D2H pipeline over three streams) returns the same bits."""
+    torch.manual_seed(13)
+    C, H, W, D, B = 32, 12, 10, 9, 3
+    m = dl.LKA_Attention3d_deform(C)
+    oracle.randomize_offsets_(m)
+    m = m.to(DEV)
+    xh = torch.randn(B, H * W * D, C).pin_memory()
+    with torch.no_grad():
+        ref = m(xh.to(DEV), B, C, H, W, D).cpu()
+        got = m.forward_host(xh, B, C, H, W, D)
+        got2 = m.forward_host(xh, B, C, H, W, D, y_host=torch.empty_like(xh))  # pageable output buffer
+    assert got.device.type == "cpu" and torch.equal(got, ref) and torch.equal(got2, ref)
