@@ -27,7 +27,12 @@ using namespace ptx;
 
 constexpr int CT_CTRL_WARPS = 4;
 constexpr int CT_NPW = 8;          // producer / epilogue warps
-constexpr int CT_SB = 4;           // weight ring depth
+#ifndef DLKA_CT_SB
+#define DLKA_CT_SB 2
+#define DLKA_CT_MTMAX 2
+#define DLKA_CT_MINB 2
+#endif
+constexpr int CT_SB = DLKA_CT_SB;  // weight ring depth
 constexpr int CT_KCH = 16;         // channels per K chunk (= one UMMA K step)
 constexpr int CT_LPAD = 64;        // bytes added to the plane stride (bank spread between the 2 planes)
 
@@ -46,7 +51,7 @@ struct ConvTileArgs {
 };
 
 template <int MT>
-__global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, 1) conv_tiled_kernel(const ConvTileArgs a)
+__global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) conv_tiled_kernel(const ConvTileArgs a)
 {
     constexpr int NPT = CT_NPW * 32;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -270,7 +275,7 @@ bool ct_plan(const IgemmArgs &g, ConvTileArgs &a)
     a.g = geo; a.X = g.X; a.bias = g.bias; a.Y = g.Y; a.ldY = g.ldY;
     a.NT = tc_nt(geo.Co);
     const bool is3d = geo.ndim == 3;
-    for (int mt = 4; mt >= 1; mt >>= 1) {
+    for (int mt = DLKA_CT_MTMAX; mt >= 1; mt >>= 1) {
         a.MT = mt;
         a.RD = is3d ? mt + (geo.kd - 1) * geo.dd : 1;
         a.RH = (is3d ? 16 : 16 * mt) + (geo.kh - 1) * geo.dh;

@@ -12,7 +12,13 @@
 namespace dlka {
 namespace {
 
-constexpr int DS_TD = 4, DS_TH = 8, DS_TW = 16, DS_R = 4;
+#ifndef DLKA_DS_TD
+#define DLKA_DS_TD 2
+#define DLKA_DS_TH 16
+#define DLKA_DS_TW 16
+#define DLKA_DS_R 8
+#endif
+constexpr int DS_TD = DLKA_DS_TD, DS_TH = DLKA_DS_TH, DS_TW = DLKA_DS_TW, DS_R = DLKA_DS_R;
 constexpr int DS_CCH = 32;                                     // channels per CTA
 constexpr int DS_THREADS = (DS_CCH / 4) * (DS_TW / DS_R) * DS_TH;  // 8 * 4 * 8 = 256
 
@@ -40,7 +46,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dwconv_smem_kernel(const float 
     float4 *sP = sW + K * K * K * (DS_CCH / 4);              // [2][PH][PW][8] float4
 
     const int tid = threadIdx.x;
-    const int q = tid & 7, wr = (tid >> 3) & 3, hl = tid >> 5;
+    constexpr int WRUNS = DS_TW / DS_R;
+    const int q = tid & 7, wr = (tid >> 3) % WRUNS, hl = (tid >> 3) / WRUNS;
     // CTA decomposition: x = tile, y = phase * nchunks + chunk, z = batch
     int bid = blockIdx.x;
     const int tw = bid % tiles_w; bid /= tiles_w;

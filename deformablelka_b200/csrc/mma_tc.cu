@@ -25,7 +25,6 @@ namespace {
 
 using namespace ptx;
 
-constexpr int SA = 2, SB = 2;           // A / B ring depth
 #ifndef DLKA_A_PAD
 #define DLKA_A_PAD 0
 #endif
@@ -113,8 +112,9 @@ __device__ __forceinline__ void make_params(const TcArgs &a, const RowInfo &ri, 
     *reinterpret_cast<float4 *>(prm + 3) = w1;
 }
 
-template <int MODE, int KC, int MT, int NPW>
-__global__ void __launch_bounds__((CTRL_WARPS + NPW) * 32, 1) tc_igemm_kernel(const TcArgs a)
+// SA / SB: A / B ring depth.  Dense 1x1 launches use SA = MT, SB = 1 (a single K step) so two CTAs fit per SM.
+template <int MODE, int KC, int MT, int NPW, int SA, int SB>
+__global__ void __launch_bounds__((CTRL_WARPS + NPW) * 32, (MODE == IGEMM_DENSE && MT == 1) ? 2 : 1) tc_igemm_kernel(const TcArgs a)
 {
     constexpr int NPT = NPW * 32;
     constexpr int A_PLANE = a_plane_bytes<KC>();
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__((CTRL_WARPS + NPW) * 32, 1) tc_igemm_kernel(co
                     asm volatile("bar.sync 1, %0;" ::"r"(NPT) : "memory");
                 }
                 uint8_t *slot = sA + as * A_SLOT;
-#pragma unroll 2
+#pragma unroll 4
                 for (int u = ptid; u < UNITS; u += NPT) {
                     const int row = u / CG, cg = u - row * CG;
                     const i64 m = m0 + h * 128 + row;
@@ -339,14 +339,14 @@ __global__ void pack_weight_tc_kernel(const float *__restrict__ w, __nv_bfloat16
     }
 }
 
-template <int MODE, int KC, int MT, int NPW>
+template <int MODE, int KC, int MT, int NPW, int SA, int SB>
 int launch_tc(const TcArgs &a, int n_tiles, cudaStream_t st)
 {
     const int NT = a.NT;
     const size_t smem = (size_t)SA * 2 * a_plane_bytes<KC>() + (size_t)SB * 2 * (KC / 8) * NT * 16 +
                         (MODE == IGEMM_DEFORM ? (size_t)SA * 128 * 64 : 0) + (size_t)MT * 128 * sizeof(RowInfo) +
                         (2 * SA + 2 * SB + 1) * 8 + 16 + 128;
-    auto kern = tc_igemm_kernel<MODE, KC, MT, NPW>;
+    auto kern = tc_igemm_kernel<MODE, KC, MT, NPW, SA, SB>;
     static thread_local size_t configured = 0;
     if (smem > configured) {
         DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -362,10 +362,11 @@ template <int MODE, int KC>
 int launch_tc_mt(const TcArgs &a, int n_tiles, cudaStream_t st)
 {
     constexpr int NPW = MODE == IGEMM_DEFORM ? 16 : 8;
+    if (MODE == IGEMM_DENSE && a.KS == 1) return launch_tc<MODE, KC, 1, NPW, 1, 1>(a, n_tiles, st);  // streaming 1x1: 2 CTAs / SM
     const bool big = a.g.M >= (i64)2 * 128 * 148 * 2;
     // two 128-row halves per CTA share every weight tile (halves the L2 -> smem weight traffic)
-    if (big) return launch_tc<MODE, KC, 2, NPW>(a, n_tiles, st);
-    return launch_tc<MODE, KC, 1, NPW>(a, n_tiles, st);
+    if (big) return launch_tc<MODE, KC, 2, NPW, 2, 2>(a, n_tiles, st);
+    return launch_tc<MODE, KC, 1, NPW, 2, 2>(a, n_tiles, st);
 }
 
 template <int MODE>
