@@ -242,6 +242,10 @@ def main():
         return
 
     pk = peaks()
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
     ms_step = ms_total / args.steps
     value = world * vox / (ms_step * 1e-3) / 1e9
     # dominant kernel by device time
@@ -259,12 +263,12 @@ def main():
     if dom_name in per_launch_flop:
         ach = per_launch_flop[dom_name] / (dom_avg_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": dom_name, "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " bf16 burst",
+                "frac": ach / pk["bf16_tflops"], "traffic": traffic.get(dom_name), "peak_source": pk["source"] + " bf16 burst",
                 "avg_launch_ms": dom_avg_ms, "share_of_step": dom_ms / total_prof_ms if total_prof_ms else None}
     else:
         ach = HBM_BYTES_PER_VOXEL * vox / (dom_avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "frac": ach / pk["hbm_gbs"], "traffic": traffic.get(dom_name), "peak_source": pk["source"],
                 "avg_launch_ms": dom_avg_ms, "share_of_step": dom_ms / total_prof_ms if total_prof_ms else None}
     out = {
         "metric": METRIC, "value": value, "unit": "GVoxel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

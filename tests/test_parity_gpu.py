@@ -299,3 +299,44 @@ def test_forward_host_pipeline_matches_device_forward(dl, oracle, math):
         got = m.forward_host(xh, B, C, H, W, D)
         got2 = m.forward_host(xh, B, C, H, W, D, y_host=torch.empty_like(xh))  # pageable output buffer
     assert got.device.type == "cpu" and torch.equal(got, ref) and torch.equal(got2, ref)
+
+
+@pytest.mark.parametrize("math_mode", ["bf16x3"])
+def test_headline_shape_properties(dl, math_mode, monkeypatch):
+    """BASELINE.json headline size (2,96,64,128,128): the oracle cannot run here in seconds, so check the
+    size-independent properties on the GPU: (a) zero-initialised conv_offset block == the same block composed from
+    torch's own CUDA convolutions in fp32 (K3 identity, exercises 64-bit addressing: 201M elements per tensor,
+    row index x 96 > 2^31 bytes); (b) batch-shard exactness (sample 1 alone == sample 1 inside the batch);
+    (c) with random offsets: permuting the batch permutes the output (no cross-sample coupling)."""
+    monkeypatch.setenv("DLKA_MATH", math_mode)
+    torch.manual_seed(14)
+    B, C, H, W, D = 2, 96, 64, 128, 128
+    m = dl.LKA_Attention3d_deform(C).to(DEV)
+    x = torch.randn(B, H * W * D, C, device=DEV)
+    with torch.no_grad():
+        y = m(x, B, C, H, W, D)
+        assert torch.isfinite(y).all()
+        # (a) K3 at full size, one sample (keeps torch's workspace small)
+        sg = m.spatial_gating_unit
+        prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            xx = x[1:].permute(0, 2, 1).reshape(1, C, H, W, D)
+            t = F.gelu(m.proj_1(xx))
+            a = F.conv3d(sg.conv_spatial(sg.conv0(t)), sg.deform_conv.weight, sg.deform_conv.bias, 1, 1)
+            ref = (m.proj_2(t * sg.conv1(a)) + xx).reshape(1, C, -1).permute(0, 2, 1)
+            del t, a
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+        err = ((y[1:] - ref).abs().max() / ref.abs().max()).item()
+        assert err < TOL, err
+        del ref
+        # (b) + (c) with non-trivial offsets
+        co = sg.deform_conv.conv_offset
+        co.weight.normal_(0, 0.05); co.bias.uniform_(-1, 1)
+        y2 = m(x, B, C, H, W, D)
+        y1 = m(x[1:].contiguous(), 1, C, H, W, D)
+        assert torch.equal(y2[1:], y1)
+        yp = m(x.flip(0).contiguous(), B, C, H, W, D)
+        assert torch.equal(yp.flip(0), y2)
+        assert (y2 - y).abs().max() > 1e-3
