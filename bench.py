@@ -222,15 +222,22 @@ def main():
         if not args.no_e2e:
             xh = torch.randn(B, N, C).pin_memory()
             yh = torch.empty(B, N, C).pin_memory()
-            ksteps = max(2, min(args.steps, 5))
-            for _ in range(2):
-                m.forward_host(xh, B, C, D1, D2, D3, y_host=yh)
+            # streaming serving loop through the public module API: every step copies its input from pinned host memory
+            # and its result back to pinned host memory; the pipeline keeps 2 steps in flight (H2D of step k+1 and D2H of
+            # step k-1 overlap the compute of step k).
+            pipe = m.host_pipe(depth=2)
+            ksteps = max(4, args.steps)
+            for _ in range(3):
+                m.submit_host(pipe, xh, yh, B, C, D1, D2, D3)
+            pipe.wait()
             barrier()
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             f0.record()
             for _ in range(ksteps):
-                m.forward_host(xh, B, C, D1, D2, D3, y_host=yh)   # H2D of the step input + compute + D2H of the result
+                m.submit_host(pipe, xh, yh, B, C, D1, D2, D3)
+            pipe.join()          # current stream now waits for the last D2H copy
             f1.record()
+            pipe.wait()
             barrier()
             e2e_ms = max_over_ranks(f0.elapsed_time(f1), dev)
             e2e = {"value": world * vox * ksteps / (e2e_ms * 1e-3) / 1e9, "unit": "GVoxel/s",

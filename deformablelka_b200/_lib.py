@@ -81,6 +81,16 @@ def _load() -> ctypes.CDLL:
     lib.dlka_lka_attention3d_deform_forward_host.restype = c_int
     lib.dlka_lka_attention3d_deform_forward_host.argtypes = (
         [POINTER(Block3dParams), V, V] + [I] * 6 + [V, c_size_t, V, c_size_t, V])
+    lib.dlka_host_pipe_create.restype = c_int
+    lib.dlka_host_pipe_create.argtypes = [POINTER(c_void_p), c_int]
+    for name in ("dlka_host_pipe_destroy", "dlka_host_pipe_wait"):
+        getattr(lib, name).restype = c_int
+        getattr(lib, name).argtypes = [c_void_p]
+    lib.dlka_host_pipe_join.restype = c_int
+    lib.dlka_host_pipe_join.argtypes = [c_void_p, c_void_p]
+    lib.dlka_lka_attention3d_deform_forward_host_async.restype = c_int
+    lib.dlka_lka_attention3d_deform_forward_host_async.argtypes = (
+        [c_void_p, POINTER(Block3dParams), V, V] + [I] * 6 + [V, c_size_t, V, c_size_t, V])
     for name in ("dlka_deformable_lka2d", "dlka_deformable_lka_attention2d"):
         getattr(lib, name + "_workspace_bytes").restype = c_size_t
         getattr(lib, name + "_workspace_bytes").argtypes = [I] * 4

@@ -47,6 +47,14 @@ class LKA_Attention3d_deform(nn.Module):
     def forward(self, x, B, C, H, W, D):
         return ops.lka_attention3d_deform_forward(_block3d_params(self.spatial_gating_unit, self), x, B, C, H, W, D)
 
+    def host_pipe(self, depth: int = 2):
+        """A streaming pipeline for `submit_host` (keeps `depth` steps in flight; see ops.HostPipe)."""
+        return ops.HostPipe(self.proj_1.weight.device, depth)
+
+    def submit_host(self, pipe, x_host, y_host, B, C, H, W, D):
+        """Enqueue one forward on host tokens without waiting; call pipe.wait() (or pipe.join()) to collect."""
+        pipe.submit(_block3d_params(self.spatial_gating_unit, self), x_host, y_host, B, C, H, W, D)
+
     def forward_host(self, x_host, B, C, H, W, D, y_host=None):
         """Same forward for HOST tokens (ideally pinned): the library pipelines per-sample H2D copies, compute and D2H
         copies over three streams.  Parameters stay on the module's CUDA device; returns a host tensor."""

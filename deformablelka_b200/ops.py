@@ -275,6 +275,53 @@ def lka_attention3d_deform_forward_host(params: dict, x_host: torch.Tensor, y_ho
     return y_host
 
 
+class HostPipe:
+    """Streaming host-buffer pipeline (dlka_host_pipe_*): keeps `depth` steps in flight so that the H2D copy of the next
+    step and the D2H copy of the previous one overlap the compute of the current step."""
+
+    def __init__(self, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.depth = depth
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.dlka_host_pipe_create(ctypes.byref(self._h), depth), "dlka_host_pipe_create")
+        self._scratch = None
+        self._keep = []
+
+    def submit(self, params: dict, x_host: torch.Tensor, y_host: torch.Tensor, B, C, H, W, D, math=None) -> None:
+        assert x_host.device.type == "cpu" and y_host.device.type == "cpu" and x_host.is_contiguous() and y_host.is_contiguous()
+        n = B * H * W * D * C
+        need = self.depth * 2 * n * 4
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        s, keep = _params_struct(Block3dParams, params)
+        self._keep = [keep, x_host, y_host]
+        ws = Workspace.get(self.device, lib.dlka_lka_attention3d_deform_workspace_bytes(1, C, H, W, D))
+        with torch.cuda.device(self.device):
+            st = lib.dlka_lka_attention3d_deform_forward_host_async(
+                self._h, ctypes.byref(s), x_host.data_ptr(), y_host.data_ptr(), B, C, H, W, D, _math(math),
+                self._scratch.data_ptr(), self._scratch.numel(), ws.data_ptr(), ws.numel(), stream_ptr(self.device))
+        check(st, "dlka_lka_attention3d_deform_forward_host_async")
+
+    def join(self) -> None:
+        """Order the current CUDA stream after every result copy enqueued so far (no host sync)."""
+        with torch.cuda.device(self.device):
+            check(lib.dlka_host_pipe_join(self._h, stream_ptr(self.device)), "dlka_host_pipe_join")
+
+    def wait(self) -> None:
+        with torch.cuda.device(self.device):
+            check(lib.dlka_host_pipe_wait(self._h), "dlka_host_pipe_wait")
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib.dlka_host_pipe_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
 class _HostScratch:
     _bufs = {}
 

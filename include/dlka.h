@@ -185,6 +185,20 @@ DLKA_API int dlka_lka_attention3d_deform_forward_host(const dlkaBlock3dParams *p
                                              void *dev_scratch, size_t dev_scratch_bytes,
                                              void *workspace, size_t workspace_bytes, void *stream);
 
+/* Streaming variant: a pipeline context keeps `depth` steps in flight, so the H2D copy of step k+1 and the
+ * D2H copy of step k-1 overlap the compute of step k.  `dev_scratch` must hold depth * 2 * B*N*C floats.
+ * The async call returns without host synchronisation; x_host / y_host must stay valid until
+ * dlka_host_pipe_wait().  dlka_host_pipe_join() orders `stream` after every D2H copy enqueued so far.   */
+typedef struct dlkaHostPipe dlkaHostPipe;
+DLKA_API int dlka_host_pipe_create(dlkaHostPipe **pipe, int depth);
+DLKA_API int dlka_host_pipe_destroy(dlkaHostPipe *pipe);
+DLKA_API int dlka_host_pipe_wait(dlkaHostPipe *pipe);
+DLKA_API int dlka_host_pipe_join(dlkaHostPipe *pipe, void *stream);
+DLKA_API int dlka_lka_attention3d_deform_forward_host_async(dlkaHostPipe *pipe, const dlkaBlock3dParams *params,
+                                                   const float *x_host, float *y_host, int B, int C, int D1, int D2,
+                                                   int D3, int math, void *dev_scratch, size_t dev_scratch_bytes,
+                                                   void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Block: 2D D-LKA.
  * Replaces  deformable_LKA.forward            (2D/deformable_LKA/deformable_LKA.py:98-104)

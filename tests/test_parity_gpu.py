@@ -340,3 +340,21 @@ def test_headline_shape_properties(dl, math_mode, monkeypatch):
         yp = m(x.flip(0).contiguous(), B, C, H, W, D)
         assert torch.equal(yp.flip(0), y2)
         assert (y2 - y).abs().max() > 1e-3
+
+
+def test_host_pipe_streaming_matches_device_forward(dl, oracle):
+    """Streaming host pipeline (depth 2, 5 steps in flight order) returns the same bits for every step."""
+    torch.manual_seed(15)
+    C, H, W, D, B = 32, 8, 10, 6, 2
+    m = dl.LKA_Attention3d_deform(C)
+    oracle.randomize_offsets_(m)
+    m = m.to(DEV)
+    xs = [torch.randn(B, H * W * D, C).pin_memory() for _ in range(5)]
+    ys = [torch.empty(B, H * W * D, C).pin_memory() for _ in range(5)]
+    pipe = m.host_pipe(depth=2)
+    with torch.no_grad():
+        for x, y in zip(xs, ys):
+            m.submit_host(pipe, x, y, B, C, H, W, D)
+        pipe.wait()
+        for x, y in zip(xs, ys):
+            assert torch.equal(y, m(x.to(DEV), B, C, H, W, D).cpu())
