@@ -9,9 +9,10 @@ from ._lib import LIB_PATH, launch_count  # noqa: F401
 from .deform_conv3d import DeformConv as DeformConv3d, DeformConvFunction, DeformConvPack  # noqa: F401
 from .deformable_LKA import DeformConv, DeformConv2d, deformable_LKA, deformable_LKA_Attention  # noqa: F401
 from .lka3d import LKA3d_deform, LKA_Attention3d_deform  # noqa: F401
+from .blocks import DWConvLKA, Mlp, TransformerBlock_3D_single_deform_LKA, deformableLKABlock  # noqa: F401
 
 __all__ = [
     "ops", "DeformConv", "DeformConv2d", "deformable_LKA", "deformable_LKA_Attention",
     "DeformConv3d", "DeformConvFunction", "DeformConvPack", "LKA3d_deform", "LKA_Attention3d_deform",
-    "launch_count", "LIB_PATH",
+    "deformableLKABlock", "Mlp", "DWConvLKA", "TransformerBlock_3D_single_deform_LKA", "launch_count", "LIB_PATH",
 ]

@@ -36,6 +36,13 @@ class Block2dParams(Structure):
         "conv1_weight", "conv1_bias", "proj_2_weight", "proj_2_bias")]
 
 
+class LkaBlock2dParams(Structure):
+    _fields_ = ([("norm1_weight", c_void_p), ("norm1_bias", c_void_p), ("attn", Block2dParams), ("layer_scale_1", c_void_p),
+                 ("norm2_weight", c_void_p), ("norm2_bias", c_void_p), ("fc1_weight", c_void_p), ("fc1_bias", c_void_p),
+                 ("dw_weight", c_void_p), ("dw_bias", c_void_p), ("fc2_weight", c_void_p), ("fc2_bias", c_void_p),
+                 ("layer_scale_2", c_void_p), ("eps1", ctypes.c_float), ("eps2", ctypes.c_float), ("hidden", c_int)])
+
+
 def _load() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -81,6 +88,15 @@ def _load() -> ctypes.CDLL:
     lib.dlka_lka_attention3d_deform_forward_host.restype = c_int
     lib.dlka_lka_attention3d_deform_forward_host.argtypes = (
         [POINTER(Block3dParams), V, V] + [I] * 6 + [V, c_size_t, V, c_size_t, V])
+    lib.dlka_deformable_lka_block2d_workspace_bytes.restype = c_size_t
+    lib.dlka_deformable_lka_block2d_workspace_bytes.argtypes = [I] * 5
+    lib.dlka_deformable_lka_block2d_forward.restype = c_int
+    lib.dlka_deformable_lka_block2d_forward.argtypes = [POINTER(LkaBlock2dParams), V, V] + [I] * 5 + [V, c_size_t, V]
+    lib.dlka_lka_transformer3d_prenorm_workspace_bytes.restype = c_size_t
+    lib.dlka_lka_transformer3d_prenorm_workspace_bytes.argtypes = [I] * 5
+    lib.dlka_lka_transformer3d_prenorm_forward.restype = c_int
+    lib.dlka_lka_transformer3d_prenorm_forward.argtypes = (
+        [POINTER(Block3dParams), V, V, ctypes.c_float, V, V, V, V] + [I] * 6 + [V, c_size_t, V])
     lib.dlka_host_pipe_create.restype = c_int
     lib.dlka_host_pipe_create.argtypes = [POINTER(c_void_p), c_int]
     for name in ("dlka_host_pipe_destroy", "dlka_host_pipe_wait"):

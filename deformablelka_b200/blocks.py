@@ -1,0 +1,135 @@
+"""Enclosing transformer blocks with the reference's class names, constructor arguments and
+state_dict keys.
+
+2D  ``DWConvLKA``, ``Mlp``, ``deformableLKABlock``      2D/networks/MaxViT_deform_LKA.py:18-52,142-189
+3D  ``TransformerBlock_3D_single_deform_LKA``           3D/d_lka_former/network_architecture/synapse/transformerblock.py:570-630
+
+The 2D block runs entirely inside libdlka_b200 (one call).  The 3D block's attention half (pos-embed, LayerNorm,
+D-LKA attention, gamma residual) is one library call; its UnetResBlock / conv8 tail is row N3 of SURVEY.md 8f and is
+kept here as stock PyTorch layers (same parameter names as monai's UnetResBlock) so that checkpoints load.
+Inference only: dropout / drop-path must be 0 (the reference's eval behaviour).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .deformable_LKA import _block2d_params, deformable_LKA_Attention
+from .lka3d import LKA_Attention3d_deform, _block3d_params
+
+
+class DWConvLKA(nn.Module):
+    def __init__(self, dim=768):
+        super().__init__()
+        self.dwconv = nn.Conv2d(dim, dim, 3, 1, 1, bias=True, groups=dim)
+
+
+class Mlp(nn.Module):
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0., linear=False):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        if linear:
+            raise NotImplementedError("Mlp(linear=True) (extra ReLU) is not on the D-LKA Net path")
+        if act_layer is not nn.GELU:
+            raise NotImplementedError("only act_layer=nn.GELU (the reference default) is implemented")
+        if out_features != in_features:
+            raise NotImplementedError("out_features != in_features is not used by deformableLKABlock")
+        self.fc1 = nn.Conv2d(in_features, hidden_features, 1)
+        self.dwconv = DWConvLKA(hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Conv2d(hidden_features, out_features, 1)
+        self.drop = nn.Dropout(drop)
+        self.linear = linear
+        self.hidden_features = hidden_features
+
+
+class deformableLKABlock(nn.Module):
+    def __init__(self, dim, mlp_ratio=4., drop=0., drop_path=0., act_layer=nn.GELU, linear=False):
+        super().__init__()
+        if drop != 0. or drop_path != 0.:
+            raise NotImplementedError("forward-only build: drop / drop_path must be 0 (eval behaviour)")
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = deformable_LKA_Attention(dim)
+        self.drop_path = nn.Identity()
+        self.norm2 = nn.LayerNorm(dim)
+        mlp_hidden_dim = int(dim * mlp_ratio)
+        self.mlp = Mlp(in_features=dim, hidden_features=mlp_hidden_dim, act_layer=act_layer, drop=drop, linear=linear)
+        layer_scale_init_value = 1e-2
+        self.layer_scale_1 = nn.Parameter(layer_scale_init_value * torch.ones((dim)), requires_grad=True)
+        self.layer_scale_2 = nn.Parameter(layer_scale_init_value * torch.ones((dim)), requires_grad=True)
+
+    def forward(self, x, H, W):
+        blk = {
+            "norm1_weight": self.norm1.weight, "norm1_bias": self.norm1.bias, "layer_scale_1": self.layer_scale_1,
+            "norm2_weight": self.norm2.weight, "norm2_bias": self.norm2.bias, "layer_scale_2": self.layer_scale_2,
+            "fc1_weight": self.mlp.fc1.weight, "fc1_bias": self.mlp.fc1.bias,
+            "dw_weight": self.mlp.dwconv.dwconv.weight, "dw_bias": self.mlp.dwconv.dwconv.bias,
+            "fc2_weight": self.mlp.fc2.weight, "fc2_bias": self.mlp.fc2.bias,
+        }
+        return ops.deformable_lka_block2d_forward(_block2d_params(self.attn.spatial_gating_unit, self.attn), blk, x, H, W,
+                                                  self.mlp.hidden_features, self.norm1.eps, self.norm2.eps)
+
+
+class _ConvNoBias3d(nn.Module):
+    """monai ``Convolution`` keeps its conv under ``.conv`` -> parameter key ``<name>.conv.weight``."""
+
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.conv = nn.Conv3d(cin, cout, k, stride=1, padding=k // 2, bias=False)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class UnetResBlock(nn.Module):
+    """Stock-PyTorch stand-in for monai's UnetResBlock(3, C, C, kernel_size=3, stride=1, norm_name="batch")
+    (3D/d_lka_former/network_architecture/dynunet_block.py:12-80): same parameter names.  Row N3: not native yet."""
+
+    def __init__(self, spatial_dims, in_channels, out_channels, kernel_size=3, stride=1, norm_name="batch"):
+        super().__init__()
+        assert spatial_dims == 3 and stride == 1 and norm_name == "batch" and in_channels == out_channels
+        self.conv1 = _ConvNoBias3d(in_channels, out_channels, kernel_size)
+        self.conv2 = _ConvNoBias3d(out_channels, out_channels, kernel_size)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.01, inplace=True)
+        self.norm1 = nn.BatchNorm3d(out_channels)
+        self.norm2 = nn.BatchNorm3d(out_channels)
+
+    def forward(self, inp):
+        out = self.lrelu(self.norm1(self.conv1(inp)))
+        out = self.norm2(self.conv2(out))
+        return self.lrelu(out + inp)
+
+
+class TransformerBlock_3D_single_deform_LKA(nn.Module):
+    def __init__(self, input_size: int, hidden_size: int, proj_size: int, num_heads: int, dropout_rate: float = 0.0,
+                 pos_embed=False) -> None:
+        super().__init__()
+        if not (0 <= dropout_rate <= 1):
+            raise ValueError("dropout_rate should be between 0 and 1.")
+        if hidden_size % num_heads != 0:
+            raise ValueError("hidden_size should be divisible by num_heads.")
+        self.norm = nn.LayerNorm(hidden_size)
+        self.gamma = nn.Parameter(1e-6 * torch.ones(hidden_size), requires_grad=True)
+        self.epa_block = LKA_Attention3d_deform(d_model=hidden_size)
+        self.conv51 = UnetResBlock(3, hidden_size, hidden_size, kernel_size=3, stride=1, norm_name="batch")
+        self.conv8 = nn.Sequential(nn.Dropout3d(0.1, False), nn.Conv3d(hidden_size, hidden_size, 1))
+        self.pos_embed = None
+        if pos_embed:
+            self.pos_embed = nn.Parameter(torch.zeros(1, input_size, hidden_size))
+
+    def attention_half(self, x_tokens, B, C, H, W, D):
+        """x' = x + pos_embed; x' + gamma * epa_block(norm(x'))  -- one library call (transformerblock.py:620-624)."""
+        ep = self.epa_block
+        return ops.lka_transformer3d_prenorm_forward(_block3d_params(ep.spatial_gating_unit, ep), self.norm.weight,
+                                                     self.norm.bias, self.norm.eps, self.gamma, self.pos_embed, x_tokens,
+                                                     B, C, H, W, D)
+
+    def forward(self, x):
+        B, C, H, W, D = x.shape
+        tokens = x.reshape(B, C, H * W * D).permute(0, 2, 1).contiguous()
+        attn = self.attention_half(tokens, B, C, H, W, D)
+        attn_skip = attn.reshape(B, H, W, D, C).permute(0, 4, 1, 2, 3)  # (B, C, H, W, D)
+        attn = self.conv51(attn_skip)      # row N3 (stock PyTorch for now)
+        return attn_skip + self.conv8(attn)

@@ -303,7 +303,45 @@ bool null_params2d(const dlkaBlock2dParams *P, bool attention)
     return false;
 }
 
+// attention block on channels-last data with an existing plan: y_cl = proj_2(gate(GELU(proj_1 x))) + x   (y_cl != x_cl)
+int attention2d_cl_planned(const dlkaBlock2dParams &P, const float *x_cl, float *y_cl, Block2dPlan &p, int B, int C, int H, int W,
+                           int math, cudaStream_t st)
+{
+    const i64 M = (i64)B * H * W;
+    IgemmArgs a1 = dense_args(x_cl, C, M, C, C, nullptr, 0, P.proj_1_bias, EPI_GELU, nullptr, 0, p.t1, C);
+    DLKA_TRY(contraction(a1, P.proj_1_weight, math, p.wp_proj1, st));
+    DLKA_TRY(run_lka2d_core(P, p.t1, p, B, C, H, W, math, st));  // gate -> t2
+    IgemmArgs a2 = dense_args(p.t2, C, M, C, C, nullptr, 0, P.proj_2_bias, EPI_ADD, x_cl, C, y_cl, C);
+    DLKA_TRY(contraction(a2, P.proj_2_weight, math, p.wp_proj2, st));
+    return DLKA_OK;
+}
+
 }  // namespace
+
+// ---- internal entry points used by blocks_api.cu (channels-last tokens in, tokens out) ----
+int attention2d_cl(const dlkaBlock2dParams *params, const float *x_cl, float *y_cl, int B, int C, int H, int W, int math,
+                   void *workspace, size_t workspace_bytes, cudaStream_t st)
+{
+    if (null_params2d(params, true) || !x_cl || !y_cl || x_cl == y_cl) return DLKA_ERR_INVALID_ARGUMENT;
+    if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    DLKA_TRY(check_device());
+    Arena ar(workspace, workspace_bytes);
+    Block2dPlan p;
+    if (!plan_block2d(ar, B, C, H, W, p)) return DLKA_ERR_WORKSPACE;
+    return attention2d_cl_planned(*params, x_cl, y_cl, p, B, C, H, W, math, st);
+}
+
+int dense_cl(const float *x, int ldX, i64 M, int Ci, int Co, const float *w, const float *bias, int epi, const float *E, int ldE,
+             float *y, int ldY, int math, float *wscratch, cudaStream_t st)
+{
+    IgemmArgs a = dense_args(x, ldX, M, Ci, Co, nullptr, 0, bias, epi, E, ldE, y, ldY);
+    return contraction(a, w, math, wscratch, st);
+}
+
+size_t dense_scratch_floats(int Co, int Ci) { return contraction_scratch_floats(Co, Ci, 1, 1); }
+
+int device_ok() { return check_device(); }
+
 }  // namespace dlka
 
 using namespace dlka;
@@ -694,13 +732,8 @@ int dlka_deformable_lka_attention2d_forward(const dlkaBlock2dParams *params, con
     Arena ar(workspace, workspace_bytes);
     Block2dPlan p;
     if (!plan_block2d(ar, B, C, H, W, p)) return DLKA_ERR_WORKSPACE;
-    const i64 M = (i64)B * H * W;
     DLKA_TRY(transpose_cs_to_sc(x, p.x_cl, B, C, (i64)H * W, st));
-    IgemmArgs a1 = dense_args(p.x_cl, C, M, C, C, nullptr, 0, params->proj_1_bias, EPI_GELU, nullptr, 0, p.t1, C);
-    DLKA_TRY(contraction(a1, params->proj_1_weight, math, p.wp_proj1, st));
-    DLKA_TRY(run_lka2d_core(*params, p.t1, p, B, C, H, W, math, st));  // gate -> t2
-    IgemmArgs a2 = dense_args(p.t2, C, M, C, C, nullptr, 0, params->proj_2_bias, EPI_ADD, p.x_cl, C, p.t3, C);
-    DLKA_TRY(contraction(a2, params->proj_2_weight, math, p.wp_proj2, st));
+    DLKA_TRY(attention2d_cl_planned(*params, p.x_cl, p.t3, p, B, C, H, W, math, st));
     DLKA_TRY(transpose_sc_to_cs(p.t3, y, B, C, (i64)H * W, st));
     return DLKA_OK;
 }

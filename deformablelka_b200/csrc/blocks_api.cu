@@ -1,0 +1,107 @@
+// blocks_api.cu -- C-ABI entry points for the enclosing transformer blocks, tokens in / tokens out.
+//   2D  deformableLKABlock.forward                       2D/networks/MaxViT_deform_LKA.py:165-189
+//   3D  TransformerBlock_3D_single_deform_LKA.forward    transformerblock.py:617-624 (pos-embed, LayerNorm, gamma residual;
+//       the UnetResBlock / conv8 tail at :626-628 is row N3 and not part of this entry)
+// Tokens [B, N, C] are channels-last data, so neither block needs a layout change.
+#include "kernels.cuh"
+
+using namespace dlka;
+
+namespace {
+
+struct Lka2dBlockPlan {
+    float *ln, *attn, *x1, *h1, *h2, *f2, *wp_fc1, *wp_fc2, *wp_dw;
+    void *attn_ws;
+    size_t attn_ws_bytes;
+};
+
+bool plan_block(Arena &ar, int B, int C, int H, int W, int hidden, Lka2dBlockPlan &p)
+{
+    const size_t M = (size_t)B * H * W;
+    p.ln = ar.take<float>(M * C);
+    p.attn = ar.take<float>(M * C);
+    p.x1 = ar.take<float>(M * C);
+    p.h1 = ar.take<float>(M * hidden);
+    p.h2 = ar.take<float>(M * hidden);
+    p.f2 = ar.take<float>(M * C);
+    p.wp_fc1 = ar.take<float>(dense_scratch_floats(hidden, C));
+    p.wp_fc2 = ar.take<float>(dense_scratch_floats(C, hidden));
+    p.wp_dw = ar.take<float>((size_t)9 * hidden);
+    p.attn_ws_bytes = dlka_deformable_lka_attention2d_workspace_bytes(B, C, H, W);
+    p.attn_ws = ar.take<char>(p.attn_ws_bytes);
+    return ar.ok();
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t dlka_deformable_lka_block2d_workspace_bytes(int B, int C, int H, int W, int hidden)
+{
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || hidden <= 0) return 0;
+    Arena ar(nullptr, 0);
+    Lka2dBlockPlan p;
+    plan_block(ar, B, C, H, W, hidden, p);
+    return ar.off + 256;
+}
+
+int dlka_deformable_lka_block2d_forward(const dlkaLkaBlock2dParams *P, const float *x, float *y, int B, int C, int H, int W,
+                                        int math, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!P || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
+    if (!P->norm1_weight || !P->norm1_bias || !P->norm2_weight || !P->norm2_bias || !P->layer_scale_1 || !P->layer_scale_2 ||
+        !P->fc1_weight || !P->fc1_bias || !P->dw_weight || !P->dw_bias || !P->fc2_weight || !P->fc2_bias)
+        return DLKA_ERR_INVALID_ARGUMENT;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || P->hidden <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    if (C % 4 != 0 || P->hidden % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    DLKA_TRY(device_ok());
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ar(workspace, workspace_bytes);
+    Lka2dBlockPlan p;
+    if (!plan_block(ar, B, C, H, W, P->hidden, p)) return DLKA_ERR_WORKSPACE;
+    const i64 M = (i64)B * H * W;
+    const int hid = P->hidden;
+    // x1 = x + layer_scale_1 * attn(norm1(x))                                  (MaxViT_deform_LKA.py:168-175)
+    DLKA_TRY(layernorm_cl(x, nullptr, 0, P->norm1_weight, P->norm1_bias, p.ln, M, C, P->eps1, st));
+    DLKA_TRY(attention2d_cl(&P->attn, p.ln, p.attn, B, C, H, W, math, p.attn_ws, p.attn_ws_bytes, st));
+    DLKA_TRY(scale_residual_cl(x, nullptr, 0, P->layer_scale_1, p.attn, p.x1, M, C, st));
+    // y = x1 + layer_scale_2 * fc2(GELU(dwconv3x3(fc1(norm2(x1)))))             (:179-185, Mlp :44-52)
+    DLKA_TRY(layernorm_cl(p.x1, nullptr, 0, P->norm2_weight, P->norm2_bias, p.ln, M, C, P->eps2, st));
+    DLKA_TRY(dense_cl(p.ln, C, M, C, hid, P->fc1_weight, P->fc1_bias, EPI_NONE, nullptr, 0, p.h1, hid, math, p.wp_fc1, st));
+    DLKA_TRY(dwconv2d3_cl(p.h1, P->dw_weight, P->dw_bias, p.h2, B, hid, H, W, 1, p.wp_dw, st));
+    DLKA_TRY(dense_cl(p.h2, hid, M, hid, C, P->fc2_weight, P->fc2_bias, EPI_NONE, nullptr, 0, p.f2, C, math, p.wp_fc2, st));
+    DLKA_TRY(scale_residual_cl(p.x1, nullptr, 0, P->layer_scale_2, p.f2, y, M, C, st));
+    return DLKA_OK;
+}
+
+size_t dlka_lka_transformer3d_prenorm_workspace_bytes(int B, int C, int D1, int D2, int D3)
+{
+    if (B <= 0 || C <= 0 || D1 <= 0 || D2 <= 0 || D3 <= 0) return 0;
+    const size_t M = (size_t)B * D1 * D2 * D3;
+    return dlka_lka_attention3d_deform_workspace_bytes(B, C, D1, D2, D3) + 2 * (M * C * sizeof(float) + 256) + 256;
+}
+
+// y = (x + pos) + gamma * LKA_Attention3d_deform(LayerNorm(x + pos))   (transformerblock.py:620-624)
+int dlka_lka_transformer3d_prenorm_forward(const dlkaBlock3dParams *attn, const float *norm_weight, const float *norm_bias, float eps,
+                                           const float *gamma, const float *pos_embed, const float *x, float *y, int B, int C,
+                                           int D1, int D2, int D3, int math, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!attn || !norm_weight || !norm_bias || !gamma || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
+    if (B <= 0 || C <= 0 || D1 <= 0 || D2 <= 0 || D3 <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    DLKA_TRY(device_ok());
+    cudaStream_t st = (cudaStream_t)stream;
+    const i64 N = (i64)D1 * D2 * D3, M = (i64)B * N;
+    Arena ar(workspace, workspace_bytes);
+    float *ln = ar.take<float>((size_t)M * C);
+    float *a = ar.take<float>((size_t)M * C);
+    const size_t aws_bytes = dlka_lka_attention3d_deform_workspace_bytes(B, C, D1, D2, D3);
+    void *aws = ar.take<char>(aws_bytes);
+    if (!ar.ok()) return DLKA_ERR_WORKSPACE;
+    DLKA_TRY(layernorm_cl(x, pos_embed, N, norm_weight, norm_bias, ln, M, C, eps, st));
+    DLKA_TRY(dlka_lka_attention3d_deform_forward(attn, ln, a, B, C, D1, D2, D3, math, aws, aws_bytes, stream));
+    DLKA_TRY(scale_residual_cl(x, pos_embed, N, gamma, a, y, M, C, st));
+    return DLKA_OK;
+}
+
+}  // extern "C"

@@ -77,6 +77,22 @@ int dwconv_smem(const float *x, const float *w_packed, const float *bias, float 
 int deform_dwconv_cl(const float *x, const float *off, const float *mask, const float *w, const float *bias, float *y,
                      const ConvGeo &g, float *w_packed /*[K][C]*/, cudaStream_t st);
 
+// ---------------- layers around the attention block (row N1) -- norm_mlp.cu ----------------
+int layernorm_cl(const float *x, const float *pos, i64 pos_rows, const float *gamma, const float *beta, float *y, i64 M, int C,
+                 float eps, cudaStream_t st);
+int scale_residual_cl(const float *x, const float *pos, i64 pos_rows, const float *scale, const float *y, float *out, i64 M, int C,
+                      cudaStream_t st);
+int dwconv2d3_cl(const float *x, const float *w, const float *bias, float *y, int B, int C, int H, int W, int gelu, float *w_packed,
+                 cudaStream_t st);
+
+// ---------------- internal block-level helpers exported by api.cu for blocks_api.cu ----------------
+int attention2d_cl(const dlkaBlock2dParams *params, const float *x_cl, float *y_cl, int B, int C, int H, int W, int math,
+                   void *workspace, size_t workspace_bytes, cudaStream_t st);
+int dense_cl(const float *x, int ldX, i64 M, int Ci, int Co, const float *w, const float *bias, int epi, const float *E, int ldE,
+             float *y, int ldY, int math, float *wscratch, cudaStream_t st);
+size_t dense_scratch_floats(int Co, int Ci);
+int device_ok();
+
 // ---------------- sampler integer planes (parity K4) ----------------
 int sample_indices(const float *off_cf, int32_t *low, int32_t *mask, const ConvGeo &g, cudaStream_t st);
 

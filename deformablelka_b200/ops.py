@@ -275,6 +275,55 @@ def lka_attention3d_deform_forward_host(params: dict, x_host: torch.Tensor, y_ho
     return y_host
 
 
+def deformable_lka_block2d_forward(attn_params: dict, block: dict, x: torch.Tensor, H: int, W: int, hidden: int,
+                                   eps1: float, eps2: float, math=None) -> torch.Tensor:
+    """deformableLKABlock.forward on tokens [B, N, C], N = H*W (MaxViT_deform_LKA.py:165-189)."""
+    if x.dim() != 3 or x.shape[1] != H * W:
+        raise RuntimeError(f"expected tokens of shape [B, {H * W}, C], got {tuple(x.shape)}")
+    x = x.contiguous()
+    B, N, C = x.shape
+    y = torch.empty_like(x)
+    keep = []
+    s = _lib.LkaBlock2dParams()
+    a, k = _params_struct(Block2dParams, attn_params)
+    keep.append(k)
+    s.attn = a
+    for name in ("norm1_weight", "norm1_bias", "layer_scale_1", "norm2_weight", "norm2_bias", "fc1_weight", "fc1_bias",
+                 "dw_weight", "dw_bias", "fc2_weight", "fc2_bias", "layer_scale_2"):
+        t = block[name].detach().contiguous()
+        keep.append(t)
+        setattr(s, name, dptr(t, name))
+    s.eps1, s.eps2, s.hidden = float(eps1), float(eps2), int(hidden)
+    ws = Workspace.get(x.device, lib.dlka_deformable_lka_block2d_workspace_bytes(B, C, H, W, hidden))
+    with torch.cuda.device(x.device):
+        st = lib.dlka_deformable_lka_block2d_forward(ctypes.byref(s), dptr(x, "x"), dptr(y), B, C, H, W, _math(math),
+                                                     ws.data_ptr(), ws.numel(), stream_ptr(x.device))
+    check(st, "dlka_deformable_lka_block2d_forward")
+    return y
+
+
+def lka_transformer3d_prenorm_forward(attn_params: dict, norm_weight, norm_bias, eps, gamma, pos_embed, x, B, C, H, W, D,
+                                      math=None) -> torch.Tensor:
+    """x' = x + pos_embed; y = x' + gamma * LKA_Attention3d_deform(LayerNorm(x'))  (transformerblock.py:620-624)."""
+    if x.dim() != 3 or tuple(x.shape) != (B, H * W * D, C):
+        raise RuntimeError(f"expected tokens of shape {(B, H * W * D, C)}, got {tuple(x.shape)}")
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    s, keep = _params_struct(Block3dParams, attn_params)
+    nw, nb, gm = norm_weight.detach().contiguous(), norm_bias.detach().contiguous(), gamma.detach().contiguous()
+    pe = None if pos_embed is None else pos_embed.detach().reshape(-1, C).contiguous()
+    if pe is not None and pe.shape[0] != H * W * D:
+        raise RuntimeError(f"pos_embed must have {H * W * D} rows, got {pe.shape[0]}")
+    ws = Workspace.get(x.device, lib.dlka_lka_transformer3d_prenorm_workspace_bytes(B, C, H, W, D))
+    with torch.cuda.device(x.device):
+        st = lib.dlka_lka_transformer3d_prenorm_forward(ctypes.byref(s), dptr(nw, "norm.weight"), dptr(nb, "norm.bias"),
+                                                        ctypes.c_float(float(eps)), dptr(gm, "gamma"), dptr(pe, "pos_embed"),
+                                                        dptr(x, "x"), dptr(y), B, C, H, W, D, _math(math), ws.data_ptr(),
+                                                        ws.numel(), stream_ptr(x.device))
+    check(st, "dlka_lka_transformer3d_prenorm_forward")
+    return y
+
+
 class HostPipe:
     """Streaming host-buffer pipeline (dlka_host_pipe_*): keeps `depth` steps in flight so that the H2D copy of the next
     step and the D2H copy of the previous one overlap the compute of the current step."""

@@ -223,6 +223,42 @@ DLKA_API int dlka_deformable_lka_attention2d_forward(const dlkaBlock2dParams *pa
                                             int B, int C, int H, int W, int math,
                                             void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Enclosing transformer blocks.  Tokens [B, N, C] in, tokens out (channels-last data).
+ *
+ * 2D: replaces  deformableLKABlock.forward  (2D/networks/MaxViT_deform_LKA.py:165-189), eval mode
+ *     (drop = drop_path = 0, linear = False):
+ *       x1 = x  + layer_scale_1 * Attn(LayerNorm1(x))
+ *       y  = x1 + layer_scale_2 * fc2(GELU(dwconv3x3(fc1(LayerNorm2(x1)))))
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dlkaLkaBlock2dParams {
+    const float *norm1_weight, *norm1_bias;   /* [C]                 MaxViT_deform_LKA.py:151 */
+    dlkaBlock2dParams attn;                   /* deformable_LKA_Attention(dim)           :152 */
+    const float *layer_scale_1;               /* [C]                                     :160 */
+    const float *norm2_weight, *norm2_bias;   /* [C]                                     :156 */
+    const float *fc1_weight, *fc1_bias;       /* [hidden,C,1,1], [hidden]   Mlp.fc1      :34  */
+    const float *dw_weight, *dw_bias;         /* [hidden,1,3,3], [hidden]   DWConvLKA    :21  */
+    const float *fc2_weight, *fc2_bias;       /* [C,hidden,1,1], [C]        Mlp.fc2      :37  */
+    const float *layer_scale_2;               /* [C]                                     :161 */
+    float eps1, eps2;                         /* LayerNorm eps (1e-5)                          */
+    int hidden;                               /* int(dim * mlp_ratio)                          */
+} dlkaLkaBlock2dParams;
+
+DLKA_API size_t dlka_deformable_lka_block2d_workspace_bytes(int B, int C, int H, int W, int hidden);
+DLKA_API int dlka_deformable_lka_block2d_forward(const dlkaLkaBlock2dParams *params, const float *x, float *y,
+                                        int B, int C, int H, int W, int math,
+                                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* 3D: replaces the attention half of  TransformerBlock_3D_single_deform_LKA.forward
+ *     (3D/d_lka_former/network_architecture/synapse/transformerblock.py:620-624):
+ *       x' = x + pos_embed (pos_embed [N, C] or NULL);  y = x' + gamma * LKA_Attention3d_deform(LayerNorm(x'))
+ *     The UnetResBlock / conv8 tail (:626-628) is row N3 and is not part of this entry.        */
+DLKA_API size_t dlka_lka_transformer3d_prenorm_workspace_bytes(int B, int C, int D1, int D2, int D3);
+DLKA_API int dlka_lka_transformer3d_prenorm_forward(const dlkaBlock3dParams *attn, const float *norm_weight,
+                                           const float *norm_bias, float eps, const float *gamma, const float *pos_embed,
+                                           const float *x, float *y, int B, int C, int D1, int D2, int D3, int math,
+                                           void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -366,3 +366,68 @@ def randomize_offsets_(module: nn.Module, std: float = 0.05, bias_range: float =
             with torch.no_grad():
                 m.conv_offset.weight.copy_(torch.randn(m.conv_offset.weight.shape, generator=g) * std)
                 m.conv_offset.bias.copy_((torch.rand(m.conv_offset.bias.shape, generator=g) * 2 - 1) * bias_range)
+
+
+# --------------------------------------------------------------------------------------
+# Row N1: the enclosing transformer blocks, restated from stock PyTorch layers
+# --------------------------------------------------------------------------------------
+class DWConvLKA(nn.Module):
+    """Restates DWConvLKA (2D/networks/MaxViT_deform_LKA.py:18-27)."""
+
+    def __init__(self, dim=768):
+        super().__init__()
+        self.dwconv = nn.Conv2d(dim, dim, 3, 1, 1, bias=True, groups=dim)
+
+    def forward(self, x):
+        return self.dwconv(x)
+
+
+class Mlp(nn.Module):
+    """Restates Mlp (MaxViT_deform_LKA.py:29-52), linear=False, drop=0."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Conv2d(in_features, hidden_features, 1)
+        self.dwconv = DWConvLKA(hidden_features)
+        self.act = nn.GELU()
+        self.fc2 = nn.Conv2d(hidden_features, out_features, 1)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.dwconv(self.fc1(x))))
+
+
+class deformableLKABlock(nn.Module):
+    """Restates deformableLKABlock (MaxViT_deform_LKA.py:142-189), eval mode (drop_path = Identity)."""
+
+    def __init__(self, dim, mlp_ratio=4., impl="torchvision"):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = deformable_LKA_Attention(dim, impl=impl)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio))
+        self.layer_scale_1 = nn.Parameter(1e-2 * torch.ones((dim)), requires_grad=True)
+        self.layer_scale_2 = nn.Parameter(1e-2 * torch.ones((dim)), requires_grad=True)
+
+    def forward(self, x, H, W):
+        B, N, C = x.shape
+        x = x.permute(0, 2, 1).view(B, C, H, W)
+        y = self.norm1(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        y = self.attn(y)
+        x = x + self.layer_scale_1.unsqueeze(-1).unsqueeze(-1) * y
+        y = self.norm2(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        y = self.mlp(y)
+        x = x + self.layer_scale_2.unsqueeze(-1).unsqueeze(-1) * y
+        return x.view(B, C, N).permute(0, 2, 1)
+
+
+def transformer3d_attention_half(norm: nn.LayerNorm, gamma: torch.Tensor, epa_block: LKA_Attention3d_deform,
+                                 pos_embed: Optional[torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """Restates TransformerBlock_3D_single_deform_LKA.forward up to the gamma residual (transformerblock.py:617-624):
+    x [B,C,H,W,D] -> tokens; (+pos_embed); attn = x + gamma * epa_block(norm(x), B, C, H, W, D).  Returns tokens."""
+    B, C, H, W, D = x.shape
+    t = x.reshape(B, C, H * W * D).permute(0, 2, 1)
+    if pos_embed is not None:
+        t = t + pos_embed
+    return t + gamma * epa_block(norm(t), B, C, H, W, D)

@@ -358,3 +358,47 @@ def test_host_pipe_streaming_matches_device_forward(dl, oracle):
         pipe.wait()
         for x, y in zip(xs, ys):
             assert torch.equal(y, m(x.to(DEV), B, C, H, W, D).cpu())
+
+
+# ----------------------------------------------------------------------------- row N1: enclosing blocks
+@pytest.mark.parametrize("C,H,W,scale", [(16, 10, 12, 1.0), (96, 14, 14, 1.0), (64, 9, 20, 6.0)])
+def test_lka_block2d_vs_oracle(dl, oracle, C, H, W, scale, math):
+    torch.manual_seed(16)
+    ref_m = oracle.deformableLKABlock(C).eval()
+    _scale_offset_nets(ref_m, scale)
+    with torch.no_grad():
+        ref_m.layer_scale_1.uniform_(0.2, 1.0); ref_m.layer_scale_2.uniform_(0.2, 1.0)  # make both branches count
+        ref_m.norm1.weight.uniform_(0.5, 1.5); ref_m.norm1.bias.normal_(0, 0.1)
+    m = dl.deformableLKABlock(C)
+    assert sorted(m.state_dict().keys()) == sorted(ref_m.state_dict().keys())
+    m.load_state_dict(ref_m.state_dict())
+    x = torch.randn(2, H * W, C)
+    with torch.no_grad():
+        ref = ref_m(x, H, W)
+        got = m.to(DEV)(x.to(DEV), H, W)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < TOL
+
+
+@pytest.mark.parametrize("C,dims,pos", [(32, (6, 5, 8), True), (96, (4, 6, 5), False)])
+def test_transformer3d_attention_half_vs_oracle(dl, oracle, C, dims, pos, math):
+    torch.manual_seed(17)
+    H, W, D = dims
+    N = H * W * D
+    m = dl.TransformerBlock_3D_single_deform_LKA(N, C, C, 4, pos_embed=pos)
+    oracle.randomize_offsets_(m)
+    with torch.no_grad():
+        m.gamma.uniform_(0.2, 1.0)          # reference initialises 1e-6: make the branch visible
+        if pos:
+            m.pos_embed.normal_(0, 0.5)
+    ref_attn = oracle.LKA_Attention3d_deform(C).eval()
+    ref_attn.load_state_dict(m.epa_block.state_dict())
+    x = torch.randn(2, C, H, W, D)
+    with torch.no_grad():
+        ref = oracle.transformer3d_attention_half(m.norm, m.gamma, ref_attn, m.pos_embed, x)
+        md = m.to(DEV).eval()
+        tok = x.to(DEV).reshape(2, C, N).permute(0, 2, 1).contiguous()
+        got = md.attention_half(tok, 2, C, H, W, D)
+        full = md(x.to(DEV))                 # whole block incl. the stock-PyTorch UnetResBlock tail (row N3)
+    assert rel_err(got, ref) < TOL
+    assert full.shape == x.shape and torch.isfinite(full).all()
