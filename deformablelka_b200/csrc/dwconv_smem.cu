@@ -18,6 +18,11 @@ namespace {
 #define DLKA_DS_TW 16
 #define DLKA_DS_R 8
 #endif
+#ifndef DLKA_DS_NBUF
+#define DLKA_DS_NBUF 2   // plane buffers: 2 = cp.async double buffer (1 CTA/SM); 1 = single buffer, 2 CTAs/SM overlap each other
+#define DLKA_DS_MINB 1
+#endif
+constexpr int DS_NBUF = DLKA_DS_NBUF;
 constexpr int DS_TD = DLKA_DS_TD, DS_TH = DLKA_DS_TH, DS_TW = DLKA_DS_TW, DS_R = DLKA_DS_R;
 constexpr int DS_CCH = 32;                                     // channels per CTA
 constexpr int DS_THREADS = (DS_CCH / 4) * (DS_TW / DS_R) * DS_TH;  // 8 * 4 * 8 = 256
@@ -33,7 +38,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int K, int L>
-__global__ void __launch_bounds__(DS_THREADS, 1) dwconv_smem_kernel(const float *__restrict__ x, const float *__restrict__ wp,
+__global__ void __launch_bounds__(DS_THREADS, DLKA_DS_MINB) dwconv_smem_kernel(const float *__restrict__ x, const float *__restrict__ wp,
                                                                     const float *__restrict__ bias, float *__restrict__ y,
                                                                     int C, int D, int H, int W, int tiles_d, int tiles_h, int tiles_w)
 {
@@ -43,7 +48,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dwconv_smem_kernel(const float 
     constexpr int NPLANES = DS_TD + K - 1;
     extern __shared__ __align__(128) float4 smem4[];
     float4 *sW = smem4;                                      // [K^3][8] float4 : weights of this channel chunk
-    float4 *sP = sW + K * K * K * (DS_CCH / 4);              // [2][PH][PW][8] float4
+    float4 *sP = sW + K * K * K * (DS_CCH / 4);              // [NBUF][PH][PW][8] float4
+    int *sOff = reinterpret_cast<int *>(sP + DS_NBUF * PLANE_F4);  // [PLANE_F4] in-plane source offsets (elements) or -1
 
     const int tid = threadIdx.x;
     constexpr int WRUNS = DS_TW / DS_R;
@@ -63,10 +69,22 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dwconv_smem_kernel(const float 
     const float *xb = x + (i64)b * D * H * W * C + c0;
 
     // weights of the chunk -> smem ([tap][C] packed layout in global)
+    // asynchronous: lands together with the first plane (same cp.async group)
     for (int i = tid; i < K * K * K * (DS_CCH / 4); i += DS_THREADS) {
         const int tap = i >> 3, qq = i & 7;
-        sW[i] = ldg4(wp + (i64)tap * C + c0 + qq * 4);
+        cp_async16(sW + i, wp + (i64)tap * C + c0 + qq * 4, true);
     }
+
+    // in-plane source offsets are the same for every plane of the tile: computed once (the plane loop only adds d)
+    for (int i = tid; i < PLANE_F4; i += DS_THREADS) {
+        const int qq = i & 7, v = i >> 3;
+        const int ww = v % PW, hh = v / PW;
+        const int zh = zh0 - P + hh, zw = zw0 - P + ww;
+        const int hr = ph_ + L * zh, wrr = pw_ + L * zw;
+        const bool ok = zh >= 0 && zw >= 0 && hr < H && wrr < W;
+        sOff[i] = ok ? (hr * W + wrr) * C + qq * 4 : -1;
+    }
+    __syncthreads();
 
     auto load_plane = [&](int s, int buf) {
         // lattice d index of plane s, real coordinate
@@ -74,14 +92,12 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dwconv_smem_kernel(const float 
         const int dr = pd_ + L * zd;
         const bool dok = zd >= 0 && dr < D;
         float4 *dst = sP + buf * PLANE_F4;
+        const float *pb = xb + (i64)(dok ? dr : 0) * H * W * C;
+#pragma unroll 4
         for (int i = tid; i < PLANE_F4; i += DS_THREADS) {
-            const int qq = i & 7, v = i >> 3;
-            const int ww = v % PW, hh = v / PW;
-            const int zh = zh0 - P + hh, zw = zw0 - P + ww;
-            const int hr = ph_ + L * zh, wrr = pw_ + L * zw;
-            const bool ok = dok && zh >= 0 && zw >= 0 && hr < H && wrr < W;
-            const float *src = ok ? xb + (((i64)dr * H + hr) * W + wrr) * C + qq * 4 : xb;
-            cp_async16(dst + i, src, ok);
+            const int o = sOff[i];
+            const bool ok = dok && o >= 0;
+            cp_async16(dst + i, pb + (ok ? o : 0), ok);
         }
         cp_async_commit();
     };
@@ -95,17 +111,22 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dwconv_smem_kernel(const float 
             for (int r = 0; r < DS_R; ++r) acc[t][r] = bv;
     }
 
-    load_plane(0, 0);
+    if (DS_NBUF == 2) load_plane(0, 0);
 #pragma unroll 1
     for (int s = 0; s < NPLANES; ++s) {
-        if (s + 1 < NPLANES) {
-            load_plane(s + 1, (s + 1) & 1);
-            cp_async_wait<1>();
+        if (DS_NBUF == 2) {
+            if (s + 1 < NPLANES) {
+                load_plane(s + 1, (s + 1) & 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
         } else {
+            load_plane(s, 0);
             cp_async_wait<0>();
         }
         __syncthreads();
-        const float4 *pl = sP + (s & 1) * PLANE_F4;
+        const float4 *pl = sP + (DS_NBUF == 2 ? (s & 1) : 0) * PLANE_F4;
         // plane s contributes to output t with depth tap i = s - t
 #pragma unroll
         for (int j = 0; j < K; ++j) {
@@ -150,7 +171,7 @@ template <int K, int L>
 int launch_ds(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, cudaStream_t st)
 {
     constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;
-    const size_t smem = ((size_t)K * K * K * 8 + 2 * (size_t)PH * PW * 8) * sizeof(float4);
+    const size_t smem = ((size_t)K * K * K * 8 + DS_NBUF * (size_t)PH * PW * 8) * sizeof(float4) + (size_t)PH * PW * 8 * sizeof(int);
     auto kern = dwconv_smem_kernel<K, L>;
     static thread_local bool configured = false;
     if (!configured) {
