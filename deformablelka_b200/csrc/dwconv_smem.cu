@@ -8,6 +8,7 @@
 // thread owns 4 channels (float4) x R outputs along w x TD outputs along d in registers, so each input row loaded
 // from shared memory feeds up to TD*K*R FMAs and each weight vector (broadcast across the warp) R FMAs.
 #include "kernels.cuh"
+#include "tc_ptx.cuh"
 
 namespace dlka {
 namespace {
@@ -23,6 +24,10 @@ namespace {
 #define DLKA_DS_MINB 1
 #endif
 constexpr int DS_NBUF = DLKA_DS_NBUF;
+#ifndef DLKA_DS_BULK
+#define DLKA_DS_BULK 0   // 1: planes + weights by cp.async.bulk (one 128-byte TMA copy per voxel): correct but measured slower (5.9 vs 5.0 ms)
+#endif
+constexpr bool DS_BULK = DLKA_DS_BULK != 0 && DS_NBUF == 2;
 constexpr int DS_TD = DLKA_DS_TD, DS_TH = DLKA_DS_TH, DS_TW = DLKA_DS_TW, DS_R = DLKA_DS_R;
 constexpr int DS_CCH = 32;                                     // channels per CTA
 constexpr int DS_THREADS = (DS_CCH / 4) * (DS_TW / DS_R) * DS_TH;  // 8 * 4 * 8 = 256
@@ -68,23 +73,45 @@ __global__ void __launch_bounds__(DS_THREADS, DLKA_DS_MINB) dwconv_smem_kernel(c
     const int zd0 = td * DS_TD, zh0 = th * DS_TH, zw0 = tw * DS_TW;
     const float *xb = x + (i64)b * D * H * W * C + c0;
 
-    // weights of the chunk -> smem ([tap][C] packed layout in global)
-    // asynchronous: lands together with the first plane (same cp.async group)
-    for (int i = tid; i < K * K * K * (DS_CCH / 4); i += DS_THREADS) {
-        const int tap = i >> 3, qq = i & 7;
-        cp_async16(sW + i, wp + (i64)tap * C + c0 + qq * 4, true);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sOff + PH * PW * 8);   // [0..1] plane buffers, [2] weights
+    const uint32_t bar0 = ptx::smem_u32(bars);
+    if (DS_BULK && tid == 0) {
+        for (int i = 0; i < 3; ++i) ptx::mbar_init(bar0 + 8u * i, DS_THREADS);
+        ptx::fence_barrier_init();
     }
-
-    // in-plane source offsets are the same for every plane of the tile: computed once (the plane loop only adds d)
-    for (int i = tid; i < PLANE_F4; i += DS_THREADS) {
-        const int qq = i & 7, v = i >> 3;
-        const int ww = v % PW, hh = v / PW;
-        const int zh = zh0 - P + hh, zw = zw0 - P + ww;
-        const int hr = ph_ + L * zh, wrr = pw_ + L * zw;
-        const bool ok = zh >= 0 && zw >= 0 && hr < H && wrr < W;
-        sOff[i] = ok ? (hr * W + wrr) * C + qq * 4 : -1;
+    // in-plane source offsets are the same for every plane of the tile: computed once (the plane loop only adds d).
+    // bulk mode: one entry per voxel (element offset of its 32-channel / 128-byte chunk); cp.async mode: one per float4.
+    if (DS_BULK) {
+        for (int v = tid; v < PH * PW; v += DS_THREADS) {
+            const int ww = v % PW, hh = v / PW;
+            const int zh = zh0 - P + hh, zw = zw0 - P + ww;
+            const int hr = ph_ + L * zh, wrr = pw_ + L * zw;
+            sOff[v] = (zh >= 0 && zw >= 0 && hr < H && wrr < W) ? (hr * W + wrr) * C : -1;
+        }
+    } else {
+        for (int i = tid; i < PLANE_F4; i += DS_THREADS) {
+            const int qq = i & 7, v = i >> 3;
+            const int ww = v % PW, hh = v / PW;
+            const int zh = zh0 - P + hh, zw = zw0 - P + ww;
+            const int hr = ph_ + L * zh, wrr = pw_ + L * zw;
+            sOff[i] = (zh >= 0 && zw >= 0 && hr < H && wrr < W) ? (hr * W + wrr) * C + qq * 4 : -1;
+        }
     }
     __syncthreads();
+
+    // weights of the chunk -> smem ([tap][C] packed layout in global: 128 contiguous bytes per tap)
+    if (DS_BULK) {
+        int nb = 0;
+        for (int tap = tid; tap < K * K * K; tap += DS_THREADS) ++nb;
+        ptx::mbar_arrive_expect_tx(bar0 + 16u, (uint32_t)nb * 128u);
+        for (int tap = tid; tap < K * K * K; tap += DS_THREADS)
+            ptx::bulk_g2s(ptx::smem_u32(sW + tap * 8), wp + (i64)tap * C + c0, 128u, bar0 + 16u);
+    } else {
+        for (int i = tid; i < K * K * K * (DS_CCH / 4); i += DS_THREADS) {
+            const int tap = i >> 3, qq = i & 7;
+            cp_async16(sW + i, wp + (i64)tap * C + c0 + qq * 4, true);   // lands with the first plane (same group)
+        }
+    }
 
     auto load_plane = [&](int s, int buf) {
         // lattice d index of plane s, real coordinate
@@ -93,6 +120,26 @@ __global__ void __launch_bounds__(DS_THREADS, DLKA_DS_MINB) dwconv_smem_kernel(c
         const bool dok = zd >= 0 && dr < D;
         float4 *dst = sP + buf * PLANE_F4;
         const float *pb = xb + (i64)(dok ? dr : 0) * H * W * C;
+        if (DS_BULK) {
+            // zero-fill the out-of-volume voxels (generic stores, released by the arrive below), then one 128-byte
+            // bulk copy per in-volume voxel; every thread arrives once with the bytes it is about to request
+            uint32_t bytes = 0;
+            for (int v = tid; v < PH * PW; v += DS_THREADS) {
+                if (dok && sOff[v] >= 0) {
+                    bytes += 128u;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) dst[v * 8 + e] = f4zero();
+                }
+            }
+            ptx::fence_proxy_async();   // earlier generic reads of this buffer are ordered before the async writes
+            ptx::mbar_arrive_expect_tx(bar0 + 8u * buf, bytes);
+            for (int v = tid; v < PH * PW; v += DS_THREADS) {
+                const int o = sOff[v];
+                if (dok && o >= 0) ptx::bulk_g2s(ptx::smem_u32(dst + v * 8), pb + o, 128u, bar0 + 8u * buf);
+            }
+            return;
+        }
 #pragma unroll 4
         for (int i = tid; i < PLANE_F4; i += DS_THREADS) {
             const int o = sOff[i];
@@ -114,7 +161,11 @@ __global__ void __launch_bounds__(DS_THREADS, DLKA_DS_MINB) dwconv_smem_kernel(c
     if (DS_NBUF == 2) load_plane(0, 0);
 #pragma unroll 1
     for (int s = 0; s < NPLANES; ++s) {
-        if (DS_NBUF == 2) {
+        if (DS_BULK) {
+            if (s + 1 < NPLANES) load_plane(s + 1, (s + 1) & 1);
+            if (s == 0) ptx::mbar_wait(bar0 + 16u, 0);
+            ptx::mbar_wait(bar0 + 8u * (s & 1), (s >> 1) & 1);
+        } else if (DS_NBUF == 2) {
             if (s + 1 < NPLANES) {
                 load_plane(s + 1, (s + 1) & 1);
                 cp_async_wait<1>();
@@ -125,7 +176,7 @@ __global__ void __launch_bounds__(DS_THREADS, DLKA_DS_MINB) dwconv_smem_kernel(c
             load_plane(s, 0);
             cp_async_wait<0>();
         }
-        __syncthreads();
+        if (!DS_BULK) __syncthreads();
         const float4 *pl = sP + (DS_NBUF == 2 ? (s & 1) : 0) * PLANE_F4;
         // plane s contributes to output t with depth tap i = s - t
 #pragma unroll
@@ -171,7 +222,7 @@ template <int K, int L>
 int launch_ds(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, cudaStream_t st)
 {
     constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;
-    const size_t smem = ((size_t)K * K * K * 8 + DS_NBUF * (size_t)PH * PW * 8) * sizeof(float4) + (size_t)PH * PW * 8 * sizeof(int);
+    const size_t smem = ((size_t)K * K * K * 8 + DS_NBUF * (size_t)PH * PW * 8) * sizeof(float4) + (size_t)PH * PW * 8 * sizeof(int) + 64;
     auto kern = dwconv_smem_kernel<K, L>;
     static thread_local bool configured = false;
     if (!configured) {
