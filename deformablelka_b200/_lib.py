@@ -43,6 +43,12 @@ class LkaBlock2dParams(Structure):
                  ("layer_scale_2", c_void_p), ("eps1", ctypes.c_float), ("eps2", ctypes.c_float), ("hidden", c_int)])
 
 
+class Transformer3dParams(Structure):
+    _fields_ = ([("attn", Block3dParams)] + [(n, c_void_p) for n in (
+        "norm_weight", "norm_bias", "gamma", "pos_embed", "conv1_weight", "bn1_scale", "bn1_shift", "conv2_weight",
+        "bn2_scale", "bn2_shift", "conv8_weight", "conv8_bias")] + [("eps", ctypes.c_float), ("lrelu_slope", ctypes.c_float)])
+
+
 def _load() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -97,6 +103,10 @@ def _load() -> ctypes.CDLL:
     lib.dlka_lka_transformer3d_prenorm_forward.restype = c_int
     lib.dlka_lka_transformer3d_prenorm_forward.argtypes = (
         [POINTER(Block3dParams), V, V, ctypes.c_float, V, V, V, V] + [I] * 6 + [V, c_size_t, V])
+    lib.dlka_lka_transformer3d_block_workspace_bytes.restype = c_size_t
+    lib.dlka_lka_transformer3d_block_workspace_bytes.argtypes = [I] * 5
+    lib.dlka_lka_transformer3d_block_forward.restype = c_int
+    lib.dlka_lka_transformer3d_block_forward.argtypes = [POINTER(Transformer3dParams), V, V] + [I] * 6 + [V, c_size_t, V]
     lib.dlka_host_pipe_create.restype = c_int
     lib.dlka_host_pipe_create.argtypes = [POINTER(c_void_p), c_int]
     for name in ("dlka_host_pipe_destroy", "dlka_host_pipe_wait"):
@@ -128,7 +138,7 @@ def math_mode(name_or_int) -> int:
 
 
 def default_math() -> int:
-    return math_mode(os.environ.get("DLKA_MATH", "fp32"))
+    return math_mode(os.environ.get("DLKA_MATH", "bf16x3"))  # product default: tcgen05 path; "fp32" = exact SIMT validation path
 
 
 def check(status: int, what: str) -> None:

@@ -4,9 +4,9 @@ state_dict keys.
 2D  ``DWConvLKA``, ``Mlp``, ``deformableLKABlock``      2D/networks/MaxViT_deform_LKA.py:18-52,142-189
 3D  ``TransformerBlock_3D_single_deform_LKA``           3D/d_lka_former/network_architecture/synapse/transformerblock.py:570-630
 
-The 2D block runs entirely inside libdlka_b200 (one call).  The 3D block's attention half (pos-embed, LayerNorm,
-D-LKA attention, gamma residual) is one library call; its UnetResBlock / conv8 tail is row N3 of SURVEY.md 8f and is
-kept here as stock PyTorch layers (same parameter names as monai's UnetResBlock) so that checkpoints load.
+Both blocks run entirely inside libdlka_b200 (one call each).  The 3D block's UnetResBlock / conv8 tail (row N3 of
+SURVEY.md 8f) runs on the zero-copy tcgen05 conv kernel with the inference-mode BatchNorm folded into the weights;
+the sub-modules keep monai's parameter names so that checkpoints load.
 Inference only: dropout / drop-path must be 0 (the reference's eval behaviour).
 """
 from __future__ import annotations
@@ -126,10 +126,37 @@ class TransformerBlock_3D_single_deform_LKA(nn.Module):
                                                      self.norm.bias, self.norm.eps, self.gamma, self.pos_embed, x_tokens,
                                                      B, C, H, W, D)
 
+    @staticmethod
+    def _fold_bn(bn: nn.BatchNorm3d):
+        """Inference-mode BatchNorm as per-channel (scale, shift) -- a few [C]-sized host-side tensor ops."""
+        scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+        return scale.contiguous(), (bn.bias.detach() - bn.running_mean * scale).contiguous()
+
+    def forward_tokens(self, tokens, B, C, H, W, D):
+        """The whole block on tokens [B, N, C] in ONE library call (rows N1 + N3): attention half, UnetResBlock
+        (two 3x3x3 convs on tcgen05 with folded BatchNorm + LeakyReLU + residual) and conv8 + residual."""
+        if self.training:
+            raise RuntimeError("deformablelka_b200 is a forward/inference build: call .eval() (BatchNorm / Dropout3d)")
+        ep = self.epa_block
+        s1, t1 = self._fold_bn(self.conv51.norm1)
+        s2, t2 = self._fold_bn(self.conv51.norm2)
+        tail = {"norm_weight": self.norm.weight, "norm_bias": self.norm.bias, "gamma": self.gamma, "pos_embed": self.pos_embed,
+                "conv1_weight": self.conv51.conv1.conv.weight, "bn1_scale": s1, "bn1_shift": t1,
+                "conv2_weight": self.conv51.conv2.conv.weight, "bn2_scale": s2, "bn2_shift": t2,
+                "conv8_weight": self.conv8[1].weight, "conv8_bias": self.conv8[1].bias}
+        return ops.lka_transformer3d_block_forward(_block3d_params(ep.spatial_gating_unit, ep), tail, self.norm.eps,
+                                                   self.conv51.lrelu.negative_slope, tokens, B, C, H, W, D)
+
     def forward(self, x):
+        B, C, H, W, D = x.shape
+        tokens = x.reshape(B, C, H * W * D).permute(0, 2, 1).contiguous()          # (B, N, C): layout plumbing only
+        out = self.forward_tokens(tokens, B, C, H, W, D)
+        return out.reshape(B, H, W, D, C).permute(0, 4, 1, 2, 3)                    # (B, C, H, W, D) view, as the reference
+
+    def forward_reference_tail(self, x):
+        """Attention half native, UnetResBlock / conv8 through stock PyTorch layers (cross-check of row N3)."""
         B, C, H, W, D = x.shape
         tokens = x.reshape(B, C, H * W * D).permute(0, 2, 1).contiguous()
         attn = self.attention_half(tokens, B, C, H, W, D)
-        attn_skip = attn.reshape(B, H, W, D, C).permute(0, 4, 1, 2, 3)  # (B, C, H, W, D)
-        attn = self.conv51(attn_skip)      # row N3 (stock PyTorch for now)
-        return attn_skip + self.conv8(attn)
+        attn_skip = attn.reshape(B, H, W, D, C).permute(0, 4, 1, 2, 3)
+        return attn_skip + self.conv8(self.conv51(attn_skip))

@@ -340,6 +340,20 @@ int dense_cl(const float *x, int ldX, i64 M, int Ci, int Co, const float *w, con
 
 size_t dense_scratch_floats(int Co, int Ci) { return contraction_scratch_floats(Co, Ci, 1, 1); }
 
+size_t conv3_scratch_floats(int C) { return contraction_scratch_floats(C, C, 27, 1); }
+
+int conv3_bn_act_cl(const float *x, const float *w, const float *scale, const float *shift, int act, float slope, const float *E,
+                    float *y, int B, int C, int D1, int D2, int D3, int math, float *wscratch, cudaStream_t st)
+{
+    const ConvGeo g = make_geo(B, C, D1, D2, D3, C, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3);
+    IgemmArgs a = conv_args(IGEMM_CONV, g, x, nullptr, nullptr, nullptr, 0, shift, EPI_NONE, nullptr, 0, y, C);
+    if (math == DLKA_MATH_BF16X3 && conv_tiled_supported(a))
+        return conv_tiled_ex(a, w, scale, act, slope, E, C, wscratch, st);   // scale folded into the weights, shift = bias
+    a.bias = nullptr;
+    DLKA_TRY(contraction(a, w, math, wscratch, st));
+    return affine_act_cl(y, scale, shift, E, a.M, C, act, slope, st);
+}
+
 int device_ok() { return check_device(); }
 
 }  // namespace dlka

@@ -105,3 +105,52 @@ int dlka_lka_transformer3d_prenorm_forward(const dlkaBlock3dParams *attn, const 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Whole 3D transformer block on tokens (rows N1 + N3): TransformerBlock_3D_single_deform_LKA.forward
+// (transformerblock.py:617-630), inference mode:
+//   a  = x' + gamma * Attn(LayerNorm(x')),  x' = x + pos_embed
+//   r  = LeakyReLU(BN1(conv1(a)));  r = LeakyReLU(BN2(conv2(r)) + a)        UnetResBlock (dynunet_block.py:65-80)
+//   y  = a + conv8(r)                                                        Dropout3d is the identity in eval mode
+// BatchNorm is passed already folded to per-channel (scale, shift) = (w/sqrt(var+eps), b - mean*scale).
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+size_t dlka_lka_transformer3d_block_workspace_bytes(int B, int C, int D1, int D2, int D3)
+{
+    if (B <= 0 || C <= 0 || D1 <= 0 || D2 <= 0 || D3 <= 0) return 0;
+    const size_t M = (size_t)B * D1 * D2 * D3;
+    return dlka_lka_transformer3d_prenorm_workspace_bytes(B, C, D1, D2, D3) + 3 * (M * C * sizeof(float) + 256) +
+           (2 * conv3_scratch_floats(C) + dense_scratch_floats(C, C)) * sizeof(float) + 4 * 256;
+}
+
+int dlka_lka_transformer3d_block_forward(const dlkaTransformer3dParams *P, const float *x, float *y, int B, int C, int D1, int D2,
+                                         int D3, int math, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!P || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
+    if (!P->norm_weight || !P->norm_bias || !P->gamma || !P->conv1_weight || !P->bn1_scale || !P->bn1_shift || !P->conv2_weight ||
+        !P->bn2_scale || !P->bn2_shift || !P->conv8_weight || !P->conv8_bias)
+        return DLKA_ERR_INVALID_ARGUMENT;
+    if (B <= 0 || C <= 0 || D1 <= 0 || D2 <= 0 || D3 <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    DLKA_TRY(device_ok());
+    cudaStream_t st = (cudaStream_t)stream;
+    const i64 M = (i64)B * D1 * D2 * D3;
+    Arena ar(workspace, workspace_bytes);
+    float *a = ar.take<float>((size_t)M * C), *r1 = ar.take<float>((size_t)M * C), *r2 = ar.take<float>((size_t)M * C);
+    float *wp1 = ar.take<float>(conv3_scratch_floats(C)), *wp2 = ar.take<float>(conv3_scratch_floats(C));
+    float *wp8 = ar.take<float>(dense_scratch_floats(C, C));
+    const size_t pws_bytes = dlka_lka_transformer3d_prenorm_workspace_bytes(B, C, D1, D2, D3);
+    void *pws = ar.take<char>(pws_bytes);
+    if (!ar.ok()) return DLKA_ERR_WORKSPACE;
+    DLKA_TRY(dlka_lka_transformer3d_prenorm_forward(&P->attn, P->norm_weight, P->norm_bias, P->eps, P->gamma, P->pos_embed, x, a, B, C,
+                                                    D1, D2, D3, math, pws, pws_bytes, stream));
+    DLKA_TRY(conv3_bn_act_cl(a, P->conv1_weight, P->bn1_scale, P->bn1_shift, 1, P->lrelu_slope, nullptr, r1, B, C, D1, D2, D3, math,
+                             wp1, st));
+    DLKA_TRY(conv3_bn_act_cl(r1, P->conv2_weight, P->bn2_scale, P->bn2_shift, 2, P->lrelu_slope, a, r2, B, C, D1, D2, D3, math, wp2,
+                             st));
+    DLKA_TRY(dense_cl(r2, C, M, C, C, P->conv8_weight, P->conv8_bias, EPI_ADD, a, C, y, C, math, wp8, st));
+    return DLKA_OK;
+}
+
+}  // extern "C"

@@ -41,6 +41,10 @@ struct ConvTileArgs {
     const float *X;      // [B][D][H][W][C]
     const uint8_t *Bp;   // packed weights [n_tiles][chunk][tap][hi|lo][plane 2][NT][8 bf16]
     const float *bias;   // [Co] or null
+    int act;             // 0 none, 1 LeakyReLU(slope), 2 (+E) then LeakyReLU(slope)   (UnetResBlock, row N3)
+    float slope;
+    const float *E;      // residual operand [M][ldE] for act == 2
+    int ldE;
     float *Y;            // [M][ldY]
     int ldY;
     int NT;              // N tile
@@ -216,6 +220,15 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
                         const int ne = n + e < g.Co ? n + e : g.Co - 1;
                         o[e] = v[j4 * 4 + e] + (a.bias ? __ldg(a.bias + ne) : 0.f);
                     }
+                    if (a.act) {
+                        if (a.act == 2) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (n + e < g.Co) o[e] += __ldg(a.E + m * (i64)a.ldE + n + e);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] = o[e] > 0.f ? o[e] : a.slope * o[e];
+                    }
                     float *yp = a.Y + m * (i64)a.ldY + n;
                     if (vec_y && n + 3 < a.ldY) {
                         *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);  // pad columns hold junk-free bias values
@@ -238,8 +251,8 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
 }
 
 // weight [Co][C][taps] -> Bp[n_tile][chunk][tap][hi|lo][plane 2][NT][8]
-__global__ void pack_weight_ct_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ bp, int Co, int C, int taps, int NT,
-                                      int n_tiles)
+__global__ void pack_weight_ct_kernel(const float *__restrict__ w, const float *__restrict__ wscale, __nv_bfloat16 *__restrict__ bp,
+                                      int Co, int C, int taps, int NT, int n_tiles)
 {
     const int nch = C / CT_KCH;
     const i64 total = (i64)n_tiles * nch * taps * 16 * NT;
@@ -251,7 +264,8 @@ __global__ void pack_weight_ct_kernel(const float *__restrict__ w, __nv_bfloat16
         const int ch = (int)((i / ((i64)16 * NT * taps)) % nch);
         const int nt = (int)(i / ((i64)16 * NT * taps * nch));
         const int c = ch * CT_KCH + p * 8 + e, co = nt * NT + n;
-        const float v = co < Co ? w[((i64)co * C + c) * taps + tap] : 0.f;
+        float v = co < Co ? w[((i64)co * C + c) * taps + tap] : 0.f;
+        if (wscale && co < Co) v *= wscale[co];   // folded eval-mode BatchNorm scale (per output channel)
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
         const i64 slot = ((i64)(nt * nch + ch) * taps + tap) * (32 * NT);  // elements per slot: hi+lo = 2*16*NT
@@ -273,6 +287,7 @@ bool ct_plan(const IgemmArgs &g, ConvTileArgs &a)
     if (geo.sd != 1 || geo.sh != 1 || geo.sw != 1) return false;
     if (g.epi != EPI_NONE) return false;
     a.g = geo; a.X = g.X; a.bias = g.bias; a.Y = g.Y; a.ldY = g.ldY;
+    a.act = 0; a.slope = 0.f; a.E = nullptr; a.ldE = 0;
     a.NT = tc_nt(geo.Co);
     const bool is3d = geo.ndim == 3;
     for (int mt = DLKA_CT_MTMAX; mt >= 1; mt >>= 1) {
@@ -327,15 +342,23 @@ size_t conv_tiled_packed_bytes(int Co, int C, int taps)
 
 int conv_tiled(const IgemmArgs &g, const float *w, void *bp, cudaStream_t st)
 {
+    return conv_tiled_ex(g, w, nullptr, 0, 0.f, nullptr, 0, bp, st);
+}
+
+// wscale: per-output-channel factor folded into the packed weights; act / slope / E: see ConvTileArgs
+int conv_tiled_ex(const IgemmArgs &g, const float *w, const float *wscale, int act, float slope, const float *E, int ldE, void *bp,
+                  cudaStream_t st)
+{
     ConvTileArgs a;
     if (!ct_plan(g, a)) return DLKA_ERR_UNSUPPORTED;
+    a.act = act; a.slope = slope; a.E = E; a.ldE = ldE;
     const ConvGeo &geo = g.geo;
     const int n_tiles = (int)cdiv(geo.Co, a.NT);
     {
         const i64 total = (i64)n_tiles * (geo.C / CT_KCH) * geo.K * 16 * a.NT;
         const int blocks = (int)(cdiv(total, 256) < 148 * 8 ? cdiv(total, 256) : 148 * 8);
         DLKA_LAUNCH("pack_weight_ct", st,
-                    pack_weight_ct_kernel<<<blocks, 256, 0, st>>>(w, (__nv_bfloat16 *)bp, geo.Co, geo.C, geo.K, a.NT, n_tiles));
+                    pack_weight_ct_kernel<<<blocks, 256, 0, st>>>(w, wscale, (__nv_bfloat16 *)bp, geo.Co, geo.C, geo.K, a.NT, n_tiles));
     }
     a.Bp = (const uint8_t *)bp;
     switch (a.MT) {

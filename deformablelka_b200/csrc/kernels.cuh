@@ -56,6 +56,8 @@ int deform3d_tc(const IgemmArgs &a, const float *w, void *bp, const DeformChain 
 bool conv_tiled_supported(const IgemmArgs &a);
 size_t conv_tiled_packed_bytes(int Co, int C, int taps);
 int conv_tiled(const IgemmArgs &a, const float *w, void *bp, cudaStream_t st);
+int conv_tiled_ex(const IgemmArgs &a, const float *w, const float *wscale, int act, float slope, const float *E, int ldE, void *bp,
+                  cudaStream_t st);
 
 // ---------------- layout ----------------
 // [B][C][S] -> [B][S][C]  and back (S = spatial size)
@@ -84,6 +86,8 @@ int scale_residual_cl(const float *x, const float *pos, i64 pos_rows, const floa
                       cudaStream_t st);
 int dwconv2d3_cl(const float *x, const float *w, const float *bias, float *y, int B, int C, int H, int W, int gelu, float *w_packed,
                  cudaStream_t st);
+int affine_act_cl(float *y, const float *scale, const float *shift, const float *e, i64 M, int C, int act, float slope,
+                  cudaStream_t st);
 
 // ---------------- internal block-level helpers exported by api.cu for blocks_api.cu ----------------
 int attention2d_cl(const dlkaBlock2dParams *params, const float *x_cl, float *y_cl, int B, int C, int H, int W, int math,
@@ -91,6 +95,11 @@ int attention2d_cl(const dlkaBlock2dParams *params, const float *x_cl, float *y_
 int dense_cl(const float *x, int ldX, i64 M, int Ci, int Co, const float *w, const float *bias, int epi, const float *E, int ldE,
              float *y, int ldY, int math, float *wscratch, cudaStream_t st);
 size_t dense_scratch_floats(int Co, int Ci);
+// dense 3x3x3 conv C->C (stride 1, pad 1) on channels-last tokens with folded per-channel scale/shift and
+// LeakyReLU (+ residual): the two convolutions of UnetResBlock (row N3).  SIMT fp32 fallback when math != bf16x3.
+int conv3_bn_act_cl(const float *x, const float *w, const float *scale, const float *shift, int act, float slope, const float *E,
+                    float *y, int B, int C, int D1, int D2, int D3, int math, float *wscratch, cudaStream_t st);
+size_t conv3_scratch_floats(int C);
 int device_ok();
 
 // ---------------- sampler integer planes (parity K4) ----------------

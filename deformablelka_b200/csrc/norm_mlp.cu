@@ -111,6 +111,28 @@ __global__ void __launch_bounds__(256) dwconv2d3_cl_kernel(const float *__restri
     }
 }
 
+// y = act(scale[c] * y + shift[c] (+ e)); act: 1 LeakyReLU, 2 (+e) then LeakyReLU   (fallback path of conv3_bn_act_cl)
+__global__ void __launch_bounds__(256) affine_act_kernel(float *__restrict__ y, const float *__restrict__ scale,
+                                                         const float *__restrict__ shift, const float *__restrict__ e, i64 M, int C,
+                                                         int act, float slope)
+{
+    const int C4 = C / 4;
+    const i64 total = M * C4;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        const i64 row = i / C4;
+        float4 v = *reinterpret_cast<float4 *>(y + row * C + c);
+        const float4 s = scale ? ldg4(scale + c) : make_float4(1.f, 1.f, 1.f, 1.f), t = shift ? ldg4(shift + c) : f4zero();
+        v.x = fmaf(s.x, v.x, t.x); v.y = fmaf(s.y, v.y, t.y); v.z = fmaf(s.z, v.z, t.z); v.w = fmaf(s.w, v.w, t.w);
+        if (act == 2) { const float4 r = ldg4(e + row * C + c); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        if (act) {
+            v.x = v.x > 0.f ? v.x : slope * v.x; v.y = v.y > 0.f ? v.y : slope * v.y;
+            v.z = v.z > 0.f ? v.z : slope * v.z; v.w = v.w > 0.f ? v.w : slope * v.w;
+        }
+        *reinterpret_cast<float4 *>(y + row * C + c) = v;
+    }
+}
+
 __global__ void pack_dw9_kernel(const float *__restrict__ w, float *__restrict__ wp, int C)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 9 * C; i += gridDim.x * blockDim.x) wp[i] = w[(i % C) * 9 + i / C];
@@ -139,6 +161,16 @@ int scale_residual_cl(const float *x, const float *pos, i64 pos_rows, const floa
     const int blocks = (int)(cdiv(total, 256) < 148 * 16 ? cdiv(total, 256) : 148 * 16);
     DLKA_LAUNCH("scale_residual", st,
                 scale_residual_kernel<<<blocks, 256, 0, st>>>(x, pos, scale, y, out, M, C, pos_rows > 0 ? pos_rows : 1));
+    return DLKA_OK;
+}
+
+int affine_act_cl(float *y, const float *scale, const float *shift, const float *e, i64 M, int C, int act, float slope, cudaStream_t st)
+{
+    if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    if (M <= 0) return DLKA_OK;
+    const i64 total = M * (C / 4);
+    const int blocks = (int)(cdiv(total, 256) < 148 * 16 ? cdiv(total, 256) : 148 * 16);
+    DLKA_LAUNCH("affine_act", st, affine_act_kernel<<<blocks, 256, 0, st>>>(y, scale, shift, e, M, C, act, slope));
     return DLKA_OK;
 }
 

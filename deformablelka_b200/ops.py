@@ -324,6 +324,39 @@ def lka_transformer3d_prenorm_forward(attn_params: dict, norm_weight, norm_bias,
     return y
 
 
+def lka_transformer3d_block_forward(attn_params: dict, tail: dict, eps: float, slope: float, x: torch.Tensor, B, C, H, W, D,
+                                    math=None) -> torch.Tensor:
+    """Whole TransformerBlock_3D_single_deform_LKA on tokens (transformerblock.py:617-630, inference mode).
+    `tail` holds norm_weight, norm_bias, gamma, pos_embed (or None), conv1_weight, bn1_scale, bn1_shift, conv2_weight,
+    bn2_scale, bn2_shift, conv8_weight, conv8_bias."""
+    if x.dim() != 3 or tuple(x.shape) != (B, H * W * D, C):
+        raise RuntimeError(f"expected tokens of shape {(B, H * W * D, C)}, got {tuple(x.shape)}")
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    keep = []
+    s = _lib.Transformer3dParams()
+    a, k = _params_struct(Block3dParams, attn_params)
+    keep.append(k)
+    s.attn = a
+    for name, _ in _lib.Transformer3dParams._fields_:
+        if name in ("attn", "eps", "lrelu_slope"):
+            continue
+        t = tail.get(name)
+        if t is None:
+            setattr(s, name, None)
+            continue
+        t = t.detach().reshape(-1, C).contiguous() if name == "pos_embed" else t.detach().contiguous()
+        keep.append(t)
+        setattr(s, name, dptr(t, name))
+    s.eps, s.lrelu_slope = float(eps), float(slope)
+    ws = Workspace.get(x.device, lib.dlka_lka_transformer3d_block_workspace_bytes(B, C, H, W, D))
+    with torch.cuda.device(x.device):
+        st = lib.dlka_lka_transformer3d_block_forward(ctypes.byref(s), dptr(x, "x"), dptr(y), B, C, H, W, D, _math(math),
+                                                      ws.data_ptr(), ws.numel(), stream_ptr(x.device))
+    check(st, "dlka_lka_transformer3d_block_forward")
+    return y
+
+
 class HostPipe:
     """Streaming host-buffer pipeline (dlka_host_pipe_*): keeps `depth` steps in flight so that the H2D copy of the next
     step and the D2H copy of the previous one overlap the compute of the current step."""

@@ -259,6 +259,30 @@ DLKA_API int dlka_lka_transformer3d_prenorm_forward(const dlkaBlock3dParams *att
                                            const float *x, float *y, int B, int C, int D1, int D2, int D3, int math,
                                            void *workspace, size_t workspace_bytes, void *stream);
 
+/* Whole 3D transformer block on tokens (rows N1 + N3), inference mode: replaces
+ * TransformerBlock_3D_single_deform_LKA.forward (transformerblock.py:617-630) between its two layout reshapes:
+ *   a = x' + gamma * Attn(LayerNorm(x'));  r = LeakyReLU(BN1(conv1 a));  r = LeakyReLU(BN2(conv2 r) + a);  y = a + conv8(r)
+ * conv1/conv2: UnetResBlock 3x3x3 convs without bias (dynunet_block.py:44-53, 65-80); BatchNorm3d (running statistics)
+ * is passed folded: scale = weight / sqrt(running_var + eps), shift = bias - running_mean * scale.                  */
+typedef struct dlkaTransformer3dParams {
+    dlkaBlock3dParams attn;                    /* epa_block                                transformerblock.py:609 */
+    const float *norm_weight, *norm_bias;      /* LayerNorm(hidden_size)                                      :607 */
+    const float *gamma;                        /* [C]                                                         :608 */
+    const float *pos_embed;                    /* [N, C] or NULL                                              :613-615 */
+    const float *conv1_weight;                 /* conv51.conv1.conv.weight [C,C,3,3,3]                        :610 */
+    const float *bn1_scale, *bn1_shift;        /* folded conv51.norm1                                              */
+    const float *conv2_weight;                 /* conv51.conv2.conv.weight [C,C,3,3,3]                             */
+    const float *bn2_scale, *bn2_shift;        /* folded conv51.norm2                                              */
+    const float *conv8_weight, *conv8_bias;    /* conv8[1]: Conv3d(C, C, 1)                                   :611 */
+    float eps;                                 /* LayerNorm eps                                                    */
+    float lrelu_slope;                         /* 0.01 (dynunet_block.py:39)                                       */
+} dlkaTransformer3dParams;
+
+DLKA_API size_t dlka_lka_transformer3d_block_workspace_bytes(int B, int C, int D1, int D2, int D3);
+DLKA_API int dlka_lka_transformer3d_block_forward(const dlkaTransformer3dParams *params, const float *x, float *y,
+                                         int B, int C, int D1, int D2, int D3, int math,
+                                         void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -431,3 +431,39 @@ def transformer3d_attention_half(norm: nn.LayerNorm, gamma: torch.Tensor, epa_bl
     if pos_embed is not None:
         t = t + pos_embed
     return t + gamma * epa_block(norm(t), B, C, H, W, D)
+
+
+class UnetResBlock3D(nn.Module):
+    """Restates monai/dynunet UnetResBlock(3, C, C, kernel_size=3, stride=1, norm_name="batch")
+    (3D/d_lka_former/network_architecture/dynunet_block.py:12-80) from stock layers; conv layers keep monai's
+    ``.conv`` nesting so state_dict keys match (conv1.conv.weight, norm1.*, ...)."""
+
+    class _Conv(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.conv = nn.Conv3d(c, c, 3, stride=1, padding=1, bias=False)
+
+        def forward(self, x):
+            return self.conv(x)
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = UnetResBlock3D._Conv(c)
+        self.conv2 = UnetResBlock3D._Conv(c)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.01, inplace=False)
+        self.norm1 = nn.BatchNorm3d(c)
+        self.norm2 = nn.BatchNorm3d(c)
+
+    def forward(self, inp):
+        out = self.lrelu(self.norm1(self.conv1(inp)))
+        out = self.norm2(self.conv2(out))
+        return self.lrelu(out + inp)
+
+
+def transformer3d_block(norm, gamma, epa_block, pos_embed, conv51: UnetResBlock3D, conv8_conv: nn.Conv3d, x: torch.Tensor):
+    """Restates TransformerBlock_3D_single_deform_LKA.forward (transformerblock.py:617-630), eval mode
+    (Dropout3d(0.1) in conv8 is the identity).  x [B,C,H,W,D] -> [B,C,H,W,D]."""
+    B, C, H, W, D = x.shape
+    attn = transformer3d_attention_half(norm, gamma, epa_block, pos_embed, x)
+    attn_skip = attn.reshape(B, H, W, D, C).permute(0, 4, 1, 2, 3)
+    return attn_skip + conv8_conv(conv51(attn_skip))

@@ -402,3 +402,35 @@ def test_transformer3d_attention_half_vs_oracle(dl, oracle, C, dims, pos, math):
         full = md(x.to(DEV))                 # whole block incl. the stock-PyTorch UnetResBlock tail (row N3)
     assert rel_err(got, ref) < TOL
     assert full.shape == x.shape and torch.isfinite(full).all()
+
+
+@pytest.mark.parametrize("C,dims,pos", [(32, (6, 5, 8), True), (96, (4, 6, 5), False), (256, (4, 4, 4), True)])
+def test_transformer3d_whole_block_vs_oracle(dl, oracle, C, dims, pos, math):
+    """Rows N1 + N3: the whole TransformerBlock_3D_single_deform_LKA (attention half + UnetResBlock + conv8)."""
+    torch.manual_seed(18)
+    H, W, D = dims
+    N = H * W * D
+    m = dl.TransformerBlock_3D_single_deform_LKA(N, C, C, 4, pos_embed=pos)
+    oracle.randomize_offsets_(m)
+    with torch.no_grad():
+        m.gamma.uniform_(0.2, 1.0)
+        if pos:
+            m.pos_embed.normal_(0, 0.5)
+        for bn in (m.conv51.norm1, m.conv51.norm2):   # non-trivial running statistics
+            bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.5, 2.0); bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.2)
+    m.eval()
+    ref_attn = oracle.LKA_Attention3d_deform(C).eval()
+    ref_attn.load_state_dict(m.epa_block.state_dict())
+    ref_res = oracle.UnetResBlock3D(C).eval()
+    ref_res.load_state_dict(m.conv51.state_dict())
+    x = torch.randn(2, C, H, W, D)
+    with torch.no_grad():
+        ref = oracle.transformer3d_block(m.norm, m.gamma, ref_attn, m.pos_embed, ref_res, m.conv8[1], x)
+        md = m.to(DEV)
+        got = md(x.to(DEV))
+        got_tail_torch = md.forward_reference_tail(x.to(DEV))
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < TOL
+    assert rel_err(got_tail_torch, ref) < TOL
+    with pytest.raises(RuntimeError, match="eval"):
+        md.train()(x.to(DEV))
