@@ -380,6 +380,13 @@ const char *dlka_status_string(int status)
 const char *dlka_last_cuda_error(void) { return g_last_cuda_error; }
 uint64_t dlka_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+/* debug: clock64 timeline of one CTA of the deformable-conv kernel; buf = [6][1024][2] int64 on the device, or NULL */
+DLKA_API int dlka_debug_deform_trace(void *buf, int cta)
+{
+    deform3d_set_trace((long long *)buf, cta);
+    return DLKA_OK;
+}
+
 int dlka_profile_enable(int on)
 {
     g_profiling.store(on ? 1 : 0);

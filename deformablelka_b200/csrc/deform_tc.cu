@@ -44,6 +44,14 @@ constexpr int DF_APLANE = (DF_KC / 8) * DF_LBO;
 constexpr int DF_ASLOT = 2 * DF_APLANE;
 constexpr int DF_PARAM_WARPS = 4, DF_GATHER_WARPS = 16;
 constexpr int DF_THREADS = (4 + DF_PARAM_WARPS + DF_GATHER_WARPS) * 32;
+#ifndef DLKA_DF_GROUPS
+#define DLKA_DF_GROUPS 2   // gather warp groups taking alternate K steps (1: all 16 warps on every K step)
+#endif
+constexpr int DF_GROUPS = DLKA_DF_GROUPS;
+constexpr int DF_GW = DF_GATHER_WARPS / DF_GROUPS;   // warps per group
+constexpr int DF_GT = DF_GW * 32;                     // threads per group
+constexpr int DF_UNITS = 128 * 8 / DF_GT;             // (row, float4) units per thread and K step
+static_assert(DF_GROUPS == 1 || DF_GROUPS == 2, "gather groups");
 constexpr int DF_BD = 4, DF_BH = 4, DF_BW = 8;  // brick
 // staged region = brick + halo: covers every corner of samples with |offset| <~ 1 (tap reach 1 + offset + 1);
 // samples that leave it take the guarded global path, so any offset stays correct.
@@ -75,7 +83,16 @@ struct DeformTcArgs {
     const float *b2;
     const float *R;
     int ldR;
+    long long *trace;     // optional debug timeline (clock64 stamps of CTA `trace_cta`), see tools/df_trace.py
+    int trace_cta;
 };
+
+// trace layout: [role 0..5][ks][2] : 0 MMA (wait done, issued) 1 loader (slot free, issued) 2 param warp 4 (start, done)
+//               3 gather warp 8 (waits done, arrive) 4 gather warp 23 (waits done, arrive) 5 gather warp 8 (loads consumed, -)
+#define DF_TRACE(role, ks, ev)                                                                      \
+    do {                                                                                            \
+        if (a.trace && (int)blockIdx.x == a.trace_cta) a.trace[((role) * 1024 + (ks)) * 2 + (ev)] = clock64(); \
+    } while (0)
 
 struct DfRow {
     int b, d, h, w;
@@ -169,9 +186,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     const uint32_t chainB_lo = (uint32_t)CP * NT * 16;     // byte offset of the lo half in sB (chain layout)
 
     if (tid == 0) {
-        for (int s = 0; s < DF_SA; ++s) { mbar_init(fullA(s), DF_GATHER_WARPS); mbar_init(emptyA(s), 1); }
+        for (int s = 0; s < DF_SA; ++s) { mbar_init(fullA(s), DF_GW); mbar_init(emptyA(s), 1); }
         for (int s = 0; s < DF_SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
-        for (int s = 0; s < DF_SP; ++s) { mbar_init(fullP(s), DF_PARAM_WARPS); mbar_init(emptyP(s), DF_GATHER_WARPS); }
+        for (int s = 0; s < DF_SP; ++s) { mbar_init(fullP(s), DF_PARAM_WARPS); mbar_init(emptyP(s), DF_GW); }
         mbar_init(accFull, 1);
         mbar_init(barW1, 1); mbar_init(barE1, DF_PARAM_WARPS + DF_GATHER_WARPS); mbar_init(barC1, 1);
         mbar_init(barW2, 1); mbar_init(barE2, DF_PARAM_WARPS + DF_GATHER_WARPS); mbar_init(barC2, 1);
@@ -202,7 +219,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             for (int ks = 0; ks < KS; ++ks) {
                 const int bs = ks % DF_SB, as = ks % DF_SA;
                 mbar_wait(fullB(bs), (ks / DF_SB) & 1);
+                DF_TRACE(0, ks, 0);
                 mbar_wait(fullA(as), (ks / DF_SA) & 1);
+                DF_TRACE(0, ks, 1);
                 tc_fence_after();
                 const uint32_t ahi = smem_u32(sA + as * DF_ASLOT), alo = ahi + DF_APLANE;
                 const uint32_t bhi = smem_u32(sB + bs * B_SLOT), blo = bhi + B_PLANE;
@@ -245,6 +264,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             for (int ks = 0; ks < KS; ++ks) {
                 const int bs = ks % DF_SB;
                 mbar_wait(emptyB(bs), ((ks / DF_SB) & 1) ^ 1);
+                DF_TRACE(1, ks, 0);
                 mbar_arrive_expect_tx(fullB(bs), (uint32_t)B_SLOT);
                 bulk_g2s(smem_u32(sB + bs * B_SLOT), src + (i64)ks * B_SLOT, (uint32_t)B_SLOT, fullB(bs));
             }
@@ -273,10 +293,12 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             const int ntap = tap + 1 == K ? 0 : tap + 1;
             const float nod = __ldg(offrow + ntap * 3), noh = __ldg(offrow + ntap * 3 + 1), now = __ldg(offrow + ntap * 3 + 2);
             mbar_wait(emptyP(ps), ph);
+            if (warp == 4 && lane == 0) DF_TRACE(2, ks, 0);
             df_make_params(a, ri, ii, jj, kk, od, oh, ow, sPrm + (ps * 128 + r) * DF_PSTRIDE, td * DF_BD - DF_HALO,
                            th * DF_BH - DF_HALO, tw * DF_BW - DF_HALO);
             __syncwarp();
             if (lane == 0) mbar_arrive(fullP(ps));
+            if (warp == 4 && lane == 0) DF_TRACE(2, ks, 1);
             od = nod; oh = noh; ow = now;
             tap = ntap;
             if (++kk == g.kw) { kk = 0; if (++jj == g.kh) { jj = 0; if (++ii == g.kd) ii = 0; } }
@@ -284,15 +306,22 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
         }
     } else if (warp >= 8) {
         // ===================== gather / blend / convert producers =====================
+        // DF_GROUPS == 2: the 16 warps form two groups that take alternate K steps, so one group's shared/L1 load phase
+        // overlaps the other's blend/convert/store phase instead of all 16 warps moving in lock step.
         const int gt = tid - 256;                      // 0..511
+        const int grp = (warp - 8) / DF_GW;
+        const int ggt = gt - grp * DF_GT;              // thread within its group
         const int cg = gt & 7;                         // float4 of the 32-channel chunk
         const float *Xb = a.X + (i64)b * a.vol_c + cg * 4;
         const uint8_t *rbase = sReg + cg * 16;
         const int rd0 = td * DF_BD - DF_HALO, rh0 = th * DF_BH - DF_HALO, rw0 = tw * DF_BW - DF_HALO;
-        int as = 0, ps = 0, tap = 0, chunk = 0;
-        uint32_t phA = 1, phP = 0;                      // parities: emptyA starts "free", fullP starts "not ready"
-        for (int ks = 0; ks < KS; ++ks) {
-            if (DF_REGION && tap == 0) {
+        int cur_chunk = -1;
+        for (int ks = grp; ks < KS; ks += DF_GROUPS) {
+            const int chunk = ks / K;
+            const int as = ks % DF_SA, ps = ks % DF_SP;
+            const uint32_t phA = ((ks / DF_SA) & 1) ^ 1, phP = (ks / DF_SP) & 1;   // emptyA starts "free", fullP "not ready"
+            if (DF_REGION && chunk != cur_chunk) {
+                cur_chunk = chunk;
                 // (re)stage the brick + halo region for this 32-channel chunk: 768 voxels x 128 B, zero outside the volume
                 asm volatile("bar.sync 2, %0;" ::"r"(DF_GATHER_WARPS * 32) : "memory");   // everyone done with the old chunk
                 for (int i = gt; i < DF_RV * 8; i += DF_GATHER_WARPS * 32) {
@@ -310,49 +339,55 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                 asm volatile("bar.sync 2, %0;" ::"r"(DF_GATHER_WARPS * 32) : "memory");
             }
             mbar_wait(fullP(ps), phP);
+            if (warp == 8 && lane == 0) DF_TRACE(5, ks, 1);
             mbar_wait(emptyA(as), phA);
+            if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 0);
             uint8_t *slot = sA + as * DF_ASLOT;
             const float *base = Xb + chunk * DF_KC;
-            float4 acc[2];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int row = (gt >> 3) + s * 64;
-                const int4 *prm = sPrm + (ps * 128 + row) * DF_PSTRIDE;
-                const int4 o0 = prm[0], o1 = prm[1];
-                const float4 w0 = *reinterpret_cast<const float4 *>(prm + 2), w1 = *reinterpret_cast<const float4 *>(prm + 3);
-                float4 v0, v1, v2, v3, v4, v5, v6, v7;
-                if (DF_REGION && o0.x >= 0) {
-                    v0 = *reinterpret_cast<const float4 *>(rbase + o0.x); v1 = *reinterpret_cast<const float4 *>(rbase + o0.y);
-                    v2 = *reinterpret_cast<const float4 *>(rbase + o0.z); v3 = *reinterpret_cast<const float4 *>(rbase + o0.w);
-                    v4 = *reinterpret_cast<const float4 *>(rbase + o1.x); v5 = *reinterpret_cast<const float4 *>(rbase + o1.y);
-                    v6 = *reinterpret_cast<const float4 *>(rbase + o1.z); v7 = *reinterpret_cast<const float4 *>(rbase + o1.w);
-                } else {
-                    const int ox = o0.x & 0x7fffffff;
-                    v0 = ldg4(base + ox); v1 = ldg4(base + o0.y); v2 = ldg4(base + o0.z); v3 = ldg4(base + o0.w);
-                    v4 = ldg4(base + o1.x); v5 = ldg4(base + o1.y); v6 = ldg4(base + o1.z); v7 = ldg4(base + o1.w);
+            for (int u0 = 0; u0 < DF_UNITS; u0 += 2) {
+                float4 acc[2];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int row = (ggt >> 3) + (u0 + s) * (DF_GT / 8);
+                    const int4 *prm = sPrm + (ps * 128 + row) * DF_PSTRIDE;
+                    const int4 o0 = prm[0], o1 = prm[1];
+                    const float4 w0 = *reinterpret_cast<const float4 *>(prm + 2), w1 = *reinterpret_cast<const float4 *>(prm + 3);
+                    float4 v0, v1, v2, v3, v4, v5, v6, v7;
+                    if (DF_REGION && o0.x >= 0) {
+                        v0 = *reinterpret_cast<const float4 *>(rbase + o0.x); v1 = *reinterpret_cast<const float4 *>(rbase + o0.y);
+                        v2 = *reinterpret_cast<const float4 *>(rbase + o0.z); v3 = *reinterpret_cast<const float4 *>(rbase + o0.w);
+                        v4 = *reinterpret_cast<const float4 *>(rbase + o1.x); v5 = *reinterpret_cast<const float4 *>(rbase + o1.y);
+                        v6 = *reinterpret_cast<const float4 *>(rbase + o1.z); v7 = *reinterpret_cast<const float4 *>(rbase + o1.w);
+                    } else {
+                        const int ox = o0.x & 0x7fffffff;
+                        v0 = ldg4(base + ox); v1 = ldg4(base + o0.y); v2 = ldg4(base + o0.z); v3 = ldg4(base + o0.w);
+                        v4 = ldg4(base + o1.x); v5 = ldg4(base + o1.y); v6 = ldg4(base + o1.z); v7 = ldg4(base + o1.w);
+                    }
+                    float4 r = f4zero();
+                    fma4(r, w0.x, v0); fma4(r, w0.y, v1); fma4(r, w0.z, v2); fma4(r, w0.w, v3);
+                    fma4(r, w1.x, v4); fma4(r, w1.y, v5); fma4(r, w1.z, v6); fma4(r, w1.w, v7);
+                    acc[s] = r;
                 }
-                float4 r = f4zero();
-                fma4(r, w0.x, v0); fma4(r, w0.y, v1); fma4(r, w0.z, v2); fma4(r, w0.w, v3);
-                fma4(r, w1.x, v4); fma4(r, w1.y, v5); fma4(r, w1.z, v6); fma4(r, w1.w, v7);
-                acc[s] = r;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(emptyP(ps));    // parameters consumed
+                if (u0 + 2 == DF_UNITS) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(emptyP(ps));    // parameters consumed
+                    if (warp == 8 && lane == 0) DF_TRACE(5, ks, 0);
+                }
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int row = (gt >> 3) + s * 64;
-                uint2 hi, lo;
-                split_bf16x4(acc[s], hi, lo);
-                const int boff = (cg >> 1) * DF_LBO + row * 16 + (cg & 1) * 8;
-                *reinterpret_cast<uint2 *>(slot + boff) = hi;
-                *reinterpret_cast<uint2 *>(slot + DF_APLANE + boff) = lo;
+                for (int s = 0; s < 2; ++s) {
+                    const int row = (ggt >> 3) + (u0 + s) * (DF_GT / 8);
+                    uint2 hi, lo;
+                    split_bf16x4(acc[s], hi, lo);
+                    const int boff = (cg >> 1) * DF_LBO + row * 16 + (cg & 1) * 8;
+                    *reinterpret_cast<uint2 *>(slot + boff) = hi;
+                    *reinterpret_cast<uint2 *>(slot + DF_APLANE + boff) = lo;
+                }
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(fullA(as));
-            if (++as == DF_SA) { as = 0; phA ^= 1; }
-            if (++ps == DF_SP) { ps = 0; phP ^= 1; }
-            if (++tap == K) { tap = 0; ++chunk; }
+            if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 1);
         }
     }
     if (warp >= 4) {
@@ -463,6 +498,10 @@ size_t df_smem_bytes(int NT)
 
 }  // namespace
 
+static long long *g_df_trace = nullptr;
+static int g_df_trace_cta = 0;
+void deform3d_set_trace(long long *buf, int cta) { g_df_trace = buf; g_df_trace_cta = cta; }
+
 bool deform3d_tc_supported(const IgemmArgs &a)
 {
     const ConvGeo &g = a.geo;
@@ -491,6 +530,7 @@ int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, const DeformChain
     const int n_tiles = (int)cdiv(g.Co, a.NT);
     a.tiles_d = (int)cdiv(g.Do, DF_BD); a.tiles_h = (int)cdiv(g.Ho, DF_BH); a.tiles_w = (int)cdiv(g.Wo, DF_BW);
     a.vol_c = (i64)g.D * g.H * g.W * g.C;
+    a.trace = g_df_trace; a.trace_cta = g_df_trace_cta;
     a.chain = 0; a.W1p = a.W2p = nullptr; a.b1 = a.b2 = a.U = a.R = nullptr; a.ldU = a.ldR = 0;
     if (chain && chain->stages) {
         a.chain = chain->stages;

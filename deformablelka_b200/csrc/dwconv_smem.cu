@@ -13,11 +13,20 @@
 namespace dlka {
 namespace {
 
-#ifndef DLKA_DS_TD
-#define DLKA_DS_TD 2
-#define DLKA_DS_TH 16
-#define DLKA_DS_TW 16
-#define DLKA_DS_R 8
+// tile shapes per stencil (lattice voxels): TD x TH x TW outputs per CTA, R outputs along w per thread.
+// 5^3:    D,H,W = 64,128,128 divide evenly.  7^3 dil 3: the sub-lattices of the headline volume are 22 x 43 x 43, so
+// 15 x 22 tiles (3 x 2 per plane) waste 7 % of the lanes where 16 x 16 wasted 20 %.
+#ifndef DLKA_DS5_TD
+#define DLKA_DS5_TD 4
+#define DLKA_DS5_TH 16
+#define DLKA_DS5_TW 16
+#define DLKA_DS5_R 8
+#endif
+#ifndef DLKA_DS7_TD
+#define DLKA_DS7_TD 2
+#define DLKA_DS7_TH 15
+#define DLKA_DS7_TW 22
+#define DLKA_DS7_R 11
 #endif
 #ifndef DLKA_DS_NBUF
 #define DLKA_DS_NBUF 2   // plane buffers: 2 = cp.async double buffer (1 CTA/SM); 1 = single buffer, 2 CTAs/SM overlap each other
@@ -28,9 +37,7 @@ constexpr int DS_NBUF = DLKA_DS_NBUF;
 #define DLKA_DS_BULK 0   // 1: planes + weights by cp.async.bulk (one 128-byte TMA copy per voxel): correct but measured slower (5.9 vs 5.0 ms)
 #endif
 constexpr bool DS_BULK = DLKA_DS_BULK != 0 && DS_NBUF == 2;
-constexpr int DS_TD = DLKA_DS_TD, DS_TH = DLKA_DS_TH, DS_TW = DLKA_DS_TW, DS_R = DLKA_DS_R;
 constexpr int DS_CCH = 32;                                     // channels per CTA
-constexpr int DS_THREADS = (DS_CCH / 4) * (DS_TW / DS_R) * DS_TH;  // 8 * 4 * 8 = 256
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid)
 {
@@ -42,11 +49,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int K, int L>
-__global__ void __launch_bounds__(DS_THREADS, DLKA_DS_MINB) dwconv_smem_kernel(const float *__restrict__ x, const float *__restrict__ wp,
+template <int K, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R>
+__global__ void __launch_bounds__((DS_CCH / 4) * (DS_TW / DS_R) * DS_TH, DLKA_DS_MINB) dwconv_smem_kernel(const float *__restrict__ x, const float *__restrict__ wp,
                                                                     const float *__restrict__ bias, float *__restrict__ y,
                                                                     int C, int D, int H, int W, int tiles_d, int tiles_h, int tiles_w)
 {
+    constexpr int DS_THREADS = (DS_CCH / 4) * (DS_TW / DS_R) * DS_TH;
+    static_assert(DS_TW % DS_R == 0 && DS_THREADS <= 1024, "tile shape");
     constexpr int P = (K - 1) / 2;
     constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;   // plane extent (lattice voxels)
     constexpr int PLANE_F4 = PH * PW * (DS_CCH / 4);         // float4 elements per plane
@@ -218,12 +227,13 @@ __global__ void __launch_bounds__(DS_THREADS, DLKA_DS_MINB) dwconv_smem_kernel(c
     }
 }
 
-template <int K, int L>
+template <int K, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R>
 int launch_ds(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, cudaStream_t st)
 {
     constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;
     const size_t smem = ((size_t)K * K * K * 8 + DS_NBUF * (size_t)PH * PW * 8) * sizeof(float4) + (size_t)PH * PW * 8 * sizeof(int) + 64;
-    auto kern = dwconv_smem_kernel<K, L>;
+    constexpr int DS_THREADS = (DS_CCH / 4) * (DS_TW / DS_R) * DS_TH;
+    auto kern = dwconv_smem_kernel<K, L, DS_TD, DS_TH, DS_TW, DS_R>;
     static thread_local bool configured = false;
     if (!configured) {
         DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -251,8 +261,8 @@ bool dwconv_smem_supported(int C, int kd, int kh, int kw, int dil)
 int dwconv_smem(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, int k, int dil,
                 cudaStream_t st)
 {
-    if (k == 5 && dil == 1) return launch_ds<5, 1>(x, wp, bias, y, B, C, D, H, W, st);
-    if (k == 7 && dil == 3) return launch_ds<7, 3>(x, wp, bias, y, B, C, D, H, W, st);
+    if (k == 5 && dil == 1) return launch_ds<5, 1, DLKA_DS5_TD, DLKA_DS5_TH, DLKA_DS5_TW, DLKA_DS5_R>(x, wp, bias, y, B, C, D, H, W, st);
+    if (k == 7 && dil == 3) return launch_ds<7, 3, DLKA_DS7_TD, DLKA_DS7_TH, DLKA_DS7_TW, DLKA_DS7_R>(x, wp, bias, y, B, C, D, H, W, st);
     return DLKA_ERR_UNSUPPORTED;
 }
 
