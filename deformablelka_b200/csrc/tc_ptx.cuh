@@ -68,6 +68,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem
                  : "memory");
 }
 
+// TMA tile copy global -> shared of a rank-5 tensor map box at signed coordinates (c0 innermost); out-of-bounds
+// elements are zero-filled and still counted in the transaction bytes
+__device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const void *tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            dst_smem),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
 // ---- tcgen05: tensor memory ----
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols)
 {
