@@ -14,8 +14,11 @@
 // warps 8-23 gather/blend/convert producers that fill the UMMA A slots.
 #include <cuda_bf16.h>
 
+#include <cstring>
+
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
+#include "tma_host.cuh"
 
 namespace dlka {
 namespace {
@@ -28,9 +31,9 @@ constexpr int DF_KC = 32;                 // channels per K step (one 128-byte l
 #endif
 #ifndef DLKA_DF_SA
 #if DLKA_DF_REGION
-#define DLKA_DF_SA 2
+#define DLKA_DF_SA 3
 #define DLKA_DF_SB 2
-#define DLKA_DF_SP 3
+#define DLKA_DF_SP 4
 #else
 #define DLKA_DF_SA 3
 #define DLKA_DF_SB 3
@@ -145,7 +148,7 @@ __device__ __forceinline__ void df_make_params(const DeformTcArgs &a, const DfRo
     *reinterpret_cast<float4 *>(prm + 3) = w1;
 }
 
-__global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const DeformTcArgs a)
+__global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const DeformTcArgs a, const __grid_constant__ CUtensorMap tmapX)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const ConvGeo &g = a.g;
@@ -156,9 +159,10 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     int4 *sPrm = reinterpret_cast<int4 *>(sB + DF_SB * B_SLOT);                 // [SP][128][PSTRIDE]
     DfRow *sRow = reinterpret_cast<DfRow *>(sPrm + DF_SP * 128 * DF_PSTRIDE);   // [128]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sRow + 128);
-    constexpr int NBARS = 2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6;
+    constexpr int NBARS = 2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6 + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
-    uint8_t *sReg = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~(uintptr_t)127);  // region
+    float *sBias = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);                 // [3][128]: conv bias, conv1 bias, proj_2 bias (0 beyond Co)
+    uint8_t *sReg = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sBias + 3 * 128) + 127) & ~(uintptr_t)127);  // region
     uint8_t *sChainW = DF_REGION ? sReg : sB;   // chain weights: the region is free once the main loop is done
     const uint32_t bar0 = smem_u32(bars);
     auto fullA = [&](int s) { return bar0 + 8u * s; };
@@ -167,11 +171,12 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     auto emptyB = [&](int s) { return bar0 + 8u * (2 * DF_SA + DF_SB + s); };
     auto fullP = [&](int s) { return bar0 + 8u * (2 * DF_SA + 2 * DF_SB + s); };
     auto emptyP = [&](int s) { return bar0 + 8u * (2 * DF_SA + 2 * DF_SB + DF_SP + s); };
-    const uint32_t accFull = bar0 + 8u * (NBARS - 7);
+    const uint32_t accFull = bar0 + 8u * (NBARS - 9);
     const uint32_t barW1 = accFull + 8, barE1 = accFull + 16, barC1 = accFull + 24, barW2 = accFull + 32, barE2 = accFull + 40,
-                   barC2 = accFull + 48;
+                   barC2 = accFull + 48, regFull = accFull + 56, regEmpty = accFull + 64;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 128) DF_TRACE(1, 0, 1);   // misc stamps (role 1, event 1): 0 entry, 1 setup done, 2 accFull, 3+2*stage waited, 4+2*stage done, 10 exit
     const int n_tile = blockIdx.y;
     int bid = blockIdx.x;
     const int tw = bid % a.tiles_w; bid /= a.tiles_w;
@@ -192,11 +197,17 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
         mbar_init(accFull, 1);
         mbar_init(barW1, 1); mbar_init(barE1, DF_PARAM_WARPS + DF_GATHER_WARPS); mbar_init(barC1, 1);
         mbar_init(barW2, 1); mbar_init(barE2, DF_PARAM_WARPS + DF_GATHER_WARPS); mbar_init(barC2, 1);
+        mbar_init(regFull, 1); mbar_init(regEmpty, DF_GATHER_WARPS);
         fence_barrier_init();
     }
     if (warp == 0) {
         tmem_alloc(smem_u32(tmem_slot), tmem_cols);
         tmem_relinquish();
+    }
+    if (warp >= 8 && tid - 256 < 3 * 128) {  // bias vectors of the three GEMM stages (one element per gather thread)
+        const int i = tid - 256, st = i >> 7, n = n_tile * NT + (i & 127);
+        const float *src = st == 0 ? a.bias : st == 1 ? a.b1 : a.b2;
+        sBias[i] = (src && (i & 127) < NT && n < g.Co && (st == 0 || st <= a.chain)) ? __ldg(src + n) : 0.f;
     }
     if (warp >= 4 && warp < 8) {  // brick row decode
         const int r = tid - 128;
@@ -211,6 +222,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tid == 128) DF_TRACE(1, 1, 1);
 
     if (warp == 0) {
         // ===================== MMA issuer =====================
@@ -242,7 +254,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             // ---- fused 1x1 chain: A = epilogue-written rows in sA, B = whole weight matrix in sB ----
             for (int stage = 1; stage <= a.chain; ++stage) {
                 mbar_wait(stage == 1 ? barW1 : barW2, 0);
+                DF_TRACE(1, 20 + 3 * stage, 1);
                 mbar_wait(stage == 1 ? barE1 : barE2, 0);
+                DF_TRACE(1, 21 + 3 * stage, 1);
                 tc_fence_after();
                 const uint32_t ahi = smem_u32(sA), alo = ahi + chainA_lo, bhi = smem_u32(sChainW), blo = bhi + chainB_lo;
                 const uint32_t d_tmem = tmem_base + (stage == 1 ? (uint32_t)NT : 0u);
@@ -255,6 +269,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                     }
                 }
                 umma_commit(stage == 1 ? barC1 : barC2);
+                DF_TRACE(1, 22 + 3 * stage, 1);
             }
         }
     } else if (warp == 1) {
@@ -280,6 +295,15 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                 }
             }
         }
+    } else if (DF_REGION && warp == 2) {
+        // ===================== region loader: brick + halo of one 32-channel chunk, ONE TMA tile copy =====================
+        if (elect_one()) {
+            for (int c = 0; c < nchunks; ++c) {
+                if (c > 0) mbar_wait(regEmpty, (c - 1) & 1);   // all 16 gather warps are done with the previous chunk
+                mbar_arrive_expect_tx(regFull, (uint32_t)DF_REGION_BYTES);
+                tma_load_5d(smem_u32(sReg), &tmapX, regFull, c * DF_KC, tw * DF_BW - DF_HALO, th * DF_BH - DF_HALO, td * DF_BD - DF_HALO, b);
+            }
+        }
     } else if (warp >= 4 && warp < 8) {
         // ===================== sample-parameter producers (one thread per brick row) =====================
         const int r = tid - 128;
@@ -289,9 +313,17 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
         float od = __ldg(offrow), oh = __ldg(offrow + 1), ow = __ldg(offrow + 2);
         int ps = 0, tap = 0, ii = 0, jj = 0, kk = 0;
         uint32_t ph = 1;
+        const int pf_ks = KS > 12 ? KS - 12 : 0;
         for (int ks = 0; ks < KS; ++ks) {
             const int ntap = tap + 1 == K ? 0 : tap + 1;
             const float nod = __ldg(offrow + ntap * 3), noh = __ldg(offrow + ntap * 3 + 1), now = __ldg(offrow + ntap * 3 + 2);
+            if (ks == pf_ks && a.chain && ri.m >= 0) {
+                // pull this row's gate / residual operand of the fused epilogue into L2 while the main loop still runs
+                for (int c = 0; c < g.Co; c += 32) {
+                    prefetch_l2(a.U + (i64)ri.m * a.ldU + c);
+                    if (a.chain == 2) prefetch_l2(a.R + (i64)ri.m * a.ldR + c);
+                }
+            }
             mbar_wait(emptyP(ps), ph);
             if (warp == 4 && lane == 0) DF_TRACE(2, ks, 0);
             df_make_params(a, ri, ii, jj, kk, od, oh, ow, sPrm + (ps * 128 + r) * DF_PSTRIDE, td * DF_BD - DF_HALO,
@@ -306,125 +338,189 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
         }
     } else if (warp >= 8) {
         // ===================== gather / blend / convert producers =====================
-        // DF_GROUPS == 2: the 16 warps form two groups that take alternate K steps, so one group's shared/L1 load phase
-        // overlaps the other's blend/convert/store phase instead of all 16 warps moving in lock step.
+        // DF_GROUPS == 2: the 16 warps form two groups that take alternate K steps, so one group's load phase overlaps
+        // the other's blend/convert/store phase instead of all 16 warps moving in lock step.
         const int gt = tid - 256;                      // 0..511
         const int grp = (warp - 8) / DF_GW;
         const int ggt = gt - grp * DF_GT;              // thread within its group
-        const int cg = gt & 7;                         // float4 of the 32-channel chunk
-        const float *Xb = a.X + (i64)b * a.vol_c + cg * 4;
-        const uint8_t *rbase = sReg + cg * 16;
-        const int rd0 = td * DF_BD - DF_HALO, rh0 = th * DF_BH - DF_HALO, rw0 = tw * DF_BW - DF_HALO;
-        int cur_chunk = -1;
-        for (int ks = grp; ks < KS; ks += DF_GROUPS) {
-            const int chunk = ks / K;
-            const int as = ks % DF_SA, ps = ks % DF_SP;
-            const uint32_t phA = ((ks / DF_SA) & 1) ^ 1, phP = (ks / DF_SP) & 1;   // emptyA starts "free", fullP "not ready"
-            if (DF_REGION && chunk != cur_chunk) {
-                cur_chunk = chunk;
-                // (re)stage the brick + halo region for this 32-channel chunk: 768 voxels x 128 B, zero outside the volume
-                asm volatile("bar.sync 2, %0;" ::"r"(DF_GATHER_WARPS * 32) : "memory");   // everyone done with the old chunk
-                for (int i = gt; i < DF_RV * 8; i += DF_GATHER_WARPS * 32) {
-                    const int qq = i & 7, v = i >> 3;
-                    const int rx = v % DF_RW, ry = (v / DF_RW) % DF_RH, rz = v / (DF_RW * DF_RH);
-                    const int d = rd0 + rz, h = rh0 + ry, w = rw0 + rx;
-                    const bool ok = (unsigned)d < (unsigned)g.D && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W;
-                    const float *src = ok ? a.X + (i64)b * a.vol_c + (((i64)d * g.H + h) * g.W + w) * g.C + chunk * DF_KC + qq * 4 : a.X;
-                    const unsigned dst = smem_u32(sReg + i * 16);
-                    const int sz = ok ? 16 : 0;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+        if (!DF_REGION) {
+            // ---- L1 path: thread = (row, float4 cg of the 32-channel chunk); a warp instruction touches 4 lines ----
+            const int cg = gt & 7;
+            const float *Xb = a.X + (i64)b * a.vol_c + cg * 4;
+            for (int ks = grp; ks < KS; ks += DF_GROUPS) {
+                const int chunk = ks / K;
+                const int as = ks % DF_SA, ps = ks % DF_SP;
+                const uint32_t phA = ((ks / DF_SA) & 1) ^ 1, phP = (ks / DF_SP) & 1;   // emptyA starts "free", fullP "not ready"
+                mbar_wait(fullP(ps), phP);
+                if (warp == 8 && lane == 0) DF_TRACE(5, ks, 1);
+                mbar_wait(emptyA(as), phA);
+                if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 0);
+                uint8_t *slot = sA + as * DF_ASLOT;
+                const float *base = Xb + chunk * DF_KC;
+#pragma unroll
+                for (int u0 = 0; u0 < DF_UNITS; u0 += 2) {
+                    float4 acc[2];
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const int row = (ggt >> 3) + (u0 + s) * (DF_GT / 8);
+                        const int4 *prm = sPrm + (ps * 128 + row) * DF_PSTRIDE;
+                        const int4 o0 = prm[0], o1 = prm[1];
+                        const float4 w0 = *reinterpret_cast<const float4 *>(prm + 2), w1 = *reinterpret_cast<const float4 *>(prm + 3);
+                        const float4 v0 = ldg4(base + o0.x), v1 = ldg4(base + o0.y), v2 = ldg4(base + o0.z), v3 = ldg4(base + o0.w);
+                        const float4 v4 = ldg4(base + o1.x), v5 = ldg4(base + o1.y), v6 = ldg4(base + o1.z), v7 = ldg4(base + o1.w);
+                        float4 r = f4zero();
+                        fma4(r, w0.x, v0); fma4(r, w0.y, v1); fma4(r, w0.z, v2); fma4(r, w0.w, v3);
+                        fma4(r, w1.x, v4); fma4(r, w1.y, v5); fma4(r, w1.z, v6); fma4(r, w1.w, v7);
+                        acc[s] = r;
+                    }
+                    if (u0 + 2 == DF_UNITS) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(emptyP(ps));    // parameters consumed
+                        if (warp == 8 && lane == 0) DF_TRACE(5, ks, 0);
+                    }
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const int row = (ggt >> 3) + (u0 + s) * (DF_GT / 8);
+                        uint2 hi, lo;
+                        split_bf16x4(acc[s], hi, lo);
+                        const int boff = (cg >> 1) * DF_LBO + row * 16 + (cg & 1) * 8;
+                        *reinterpret_cast<uint2 *>(slot + boff) = hi;
+                        *reinterpret_cast<uint2 *>(slot + DF_APLANE + boff) = lo;
+                    }
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                asm volatile("bar.sync 2, %0;" ::"r"(DF_GATHER_WARPS * 32) : "memory");
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(fullA(as));
+                if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 1);
             }
-            mbar_wait(fullP(ps), phP);
-            if (warp == 8 && lane == 0) DF_TRACE(5, ks, 1);
-            mbar_wait(emptyA(as), phA);
-            if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 0);
-            uint8_t *slot = sA + as * DF_ASLOT;
-            const float *base = Xb + chunk * DF_KC;
+        } else {
+            // ---- shared-memory path: the chunk's brick + halo region is staged by TMA; thread = (row, float4 pair) ----
+            // 4 lanes per row, each owning float4 f and f ^ 4 of the 32-channel line, so the 64-byte parameter record is read
+            // once per 8 channels.  Odd rows start with the upper 64 bytes: a quarter-warp (2 rows x 4 lanes) then covers
+            // all 32 banks exactly once per LDS.128.
+            const int j4 = ggt & 3;
+            constexpr int ROWS_PER_ROUND = DF_GT / 4, ROUNDS = 128 / ROWS_PER_ROUND;
+            int cur_chunk = -1;
+            for (int ks = grp; ks < KS; ks += DF_GROUPS) {
+                const int chunk = ks / K;
+                const int as = ks % DF_SA, ps = ks % DF_SP;
+                const uint32_t phA = ((ks / DF_SA) & 1) ^ 1, phP = (ks / DF_SP) & 1;
+                if (chunk != cur_chunk) {
+                    if (cur_chunk >= 0) {   // this warp has consumed every load of the previous chunk: release the region
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(regEmpty);
+                    }
+                    cur_chunk = chunk;
+                    mbar_wait(regFull, chunk & 1);
+                }
+                mbar_wait(fullP(ps), phP);
+                if (warp == 8 && lane == 0) DF_TRACE(5, ks, 1);
+                mbar_wait(emptyA(as), phA);
+                if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 0);
+                uint8_t *slot = sA + as * DF_ASLOT;
 #pragma unroll
-            for (int u0 = 0; u0 < DF_UNITS; u0 += 2) {
-                float4 acc[2];
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int row = (ggt >> 3) + (u0 + s) * (DF_GT / 8);
+                for (int rd = 0; rd < ROUNDS; ++rd) {
+                    const int row = (ggt >> 2) + rd * ROWS_PER_ROUND;
+                    const int f0 = j4 + ((row & 1) << 2), f1 = f0 ^ 4;
                     const int4 *prm = sPrm + (ps * 128 + row) * DF_PSTRIDE;
                     const int4 o0 = prm[0], o1 = prm[1];
                     const float4 w0 = *reinterpret_cast<const float4 *>(prm + 2), w1 = *reinterpret_cast<const float4 *>(prm + 3);
-                    float4 v0, v1, v2, v3, v4, v5, v6, v7;
-                    if (DF_REGION && o0.x >= 0) {
-                        v0 = *reinterpret_cast<const float4 *>(rbase + o0.x); v1 = *reinterpret_cast<const float4 *>(rbase + o0.y);
-                        v2 = *reinterpret_cast<const float4 *>(rbase + o0.z); v3 = *reinterpret_cast<const float4 *>(rbase + o0.w);
-                        v4 = *reinterpret_cast<const float4 *>(rbase + o1.x); v5 = *reinterpret_cast<const float4 *>(rbase + o1.y);
-                        v6 = *reinterpret_cast<const float4 *>(rbase + o1.z); v7 = *reinterpret_cast<const float4 *>(rbase + o1.w);
-                    } else {
+                    float4 v0, v1, v2, v3, v4, v5, v6, v7, u0, u1, u2, u3, u4, u5, u6, u7;
+                    if (o0.x >= 0) {
+                        const uint8_t *ra = sReg + f0 * 16, *rb = sReg + f1 * 16;
+                        v0 = *reinterpret_cast<const float4 *>(ra + o0.x); u0 = *reinterpret_cast<const float4 *>(rb + o0.x);
+                        v1 = *reinterpret_cast<const float4 *>(ra + o0.y); u1 = *reinterpret_cast<const float4 *>(rb + o0.y);
+                        v2 = *reinterpret_cast<const float4 *>(ra + o0.z); u2 = *reinterpret_cast<const float4 *>(rb + o0.z);
+                        v3 = *reinterpret_cast<const float4 *>(ra + o0.w); u3 = *reinterpret_cast<const float4 *>(rb + o0.w);
+                        v4 = *reinterpret_cast<const float4 *>(ra + o1.x); u4 = *reinterpret_cast<const float4 *>(rb + o1.x);
+                        v5 = *reinterpret_cast<const float4 *>(ra + o1.y); u5 = *reinterpret_cast<const float4 *>(rb + o1.y);
+                        v6 = *reinterpret_cast<const float4 *>(ra + o1.z); u6 = *reinterpret_cast<const float4 *>(rb + o1.z);
+                        v7 = *reinterpret_cast<const float4 *>(ra + o1.w); u7 = *reinterpret_cast<const float4 *>(rb + o1.w);
+                    } else {   // a corner left the staged region (large offset): guarded global path, same arithmetic
+                        const float *ga = a.X + (i64)b * a.vol_c + chunk * DF_KC + f0 * 4, *gb = ga + (f1 - f0) * 4;
                         const int ox = o0.x & 0x7fffffff;
-                        v0 = ldg4(base + ox); v1 = ldg4(base + o0.y); v2 = ldg4(base + o0.z); v3 = ldg4(base + o0.w);
-                        v4 = ldg4(base + o1.x); v5 = ldg4(base + o1.y); v6 = ldg4(base + o1.z); v7 = ldg4(base + o1.w);
+                        v0 = ldg4(ga + ox); u0 = ldg4(gb + ox); v1 = ldg4(ga + o0.y); u1 = ldg4(gb + o0.y);
+                        v2 = ldg4(ga + o0.z); u2 = ldg4(gb + o0.z); v3 = ldg4(ga + o0.w); u3 = ldg4(gb + o0.w);
+                        v4 = ldg4(ga + o1.x); u4 = ldg4(gb + o1.x); v5 = ldg4(ga + o1.y); u5 = ldg4(gb + o1.y);
+                        v6 = ldg4(ga + o1.z); u6 = ldg4(gb + o1.z); v7 = ldg4(ga + o1.w); u7 = ldg4(gb + o1.w);
                     }
-                    float4 r = f4zero();
-                    fma4(r, w0.x, v0); fma4(r, w0.y, v1); fma4(r, w0.z, v2); fma4(r, w0.w, v3);
-                    fma4(r, w1.x, v4); fma4(r, w1.y, v5); fma4(r, w1.z, v6); fma4(r, w1.w, v7);
-                    acc[s] = r;
-                }
-                if (u0 + 2 == DF_UNITS) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(emptyP(ps));    // parameters consumed
-                    if (warp == 8 && lane == 0) DF_TRACE(5, ks, 0);
-                }
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int row = (ggt >> 3) + (u0 + s) * (DF_GT / 8);
+                    float4 r0 = f4zero(), r1 = f4zero();
+                    fma4(r0, w0.x, v0); fma4(r0, w0.y, v1); fma4(r0, w0.z, v2); fma4(r0, w0.w, v3);
+                    fma4(r0, w1.x, v4); fma4(r0, w1.y, v5); fma4(r0, w1.z, v6); fma4(r0, w1.w, v7);
+                    fma4(r1, w0.x, u0); fma4(r1, w0.y, u1); fma4(r1, w0.z, u2); fma4(r1, w0.w, u3);
+                    fma4(r1, w1.x, u4); fma4(r1, w1.y, u5); fma4(r1, w1.z, u6); fma4(r1, w1.w, u7);
+                    if (rd + 1 == ROUNDS) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(emptyP(ps));    // parameters consumed
+                        if (warp == 8 && lane == 0) DF_TRACE(5, ks, 0);
+                    }
                     uint2 hi, lo;
-                    split_bf16x4(acc[s], hi, lo);
-                    const int boff = (cg >> 1) * DF_LBO + row * 16 + (cg & 1) * 8;
+                    split_bf16x4(r0, hi, lo);
+                    int boff = (f0 >> 1) * DF_LBO + row * 16 + (f0 & 1) * 8;
+                    *reinterpret_cast<uint2 *>(slot + boff) = hi;
+                    *reinterpret_cast<uint2 *>(slot + DF_APLANE + boff) = lo;
+                    split_bf16x4(r1, hi, lo);
+                    boff = (f1 >> 1) * DF_LBO + row * 16 + (f1 & 1) * 8;
                     *reinterpret_cast<uint2 *>(slot + boff) = hi;
                     *reinterpret_cast<uint2 *>(slot + DF_APLANE + boff) = lo;
                 }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(fullA(as));
+                if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 1);
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(fullA(as));
-            if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 1);
         }
     }
     if (warp >= 4) {
         // ===================== epilogue: all 20 producer warps =====================
-        // TMEM lane quadrant q = warp % 4 (hardware rule); the 5 warps of a quadrant split the columns in chunks
-        // of 8, so each thread keeps only 2 x LDG.128 of the gate / residual operand in flight per chunk.
-        mbar_wait(accFull, 0);
-        tc_fence_after();
+        // TMEM lane quadrant q = warp % 4 (hardware rule); the 5 warps of a quadrant split the columns in chunks of 8
+        // (chunk it of this thread = columns cc*8 + it*40 ...).  The gate (U) / residual (R) rows of the NEXT stage are
+        // fetched before this thread waits for that stage's MMA, so their HBM latency hides behind the 1x1 GEMM, and the
+        // bias vectors sit in shared memory: no dependent global load is left inside the per-chunk loop.
+        constexpr int EP_MAXIT = 4;                     // NT <= 128 -> at most 4 chunks of 8 columns per thread
         const int q = warp & 3, cc = (warp - 4) >> 2;  // cc = 0..4
         const int row = q * 32 + lane;
         const DfRow ro = sRow[row];
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         const bool vec_y = (a.ldY & 3) == 0;
+        float4 e0[EP_MAXIT], e1[EP_MAXIT];
+        auto fetch_operand = [&](const float *src, int ld) {
+#pragma unroll
+            for (int it = 0; it < EP_MAXIT; ++it) {
+                const int c0 = cc * 8 + it * 40, nb = n_tile * NT + c0;
+                e0[it] = e1[it] = f4zero();
+                if (c0 < NT && ro.m >= 0 && nb < g.Co) {
+                    e0[it] = ldg4(src + (i64)ro.m * ld + nb);
+                    e1[it] = ldg4(src + (i64)ro.m * ld + nb + 4);
+                }
+            }
+        };
+        mbar_wait(accFull, 0);
+        if (tid == 128) DF_TRACE(1, 2, 1);
+        tc_fence_after();
         for (int stage = 0; stage <= a.chain; ++stage) {
             if (stage == 1) mbar_wait(barC1, 0);
             if (stage == 2) mbar_wait(barC2, 0);
+            if (tid == 128) DF_TRACE(1, 3 + 2 * stage, 1);
             if (stage) tc_fence_after();
             const bool last = stage == a.chain;
-            const float *bias = stage == 0 ? a.bias : stage == 1 ? a.b1 : a.b2;
+            const float *sb = sBias + stage * 128;
             const uint32_t tcol = trow + (stage == 1 ? (uint32_t)NT : 0u);
-            for (int c0 = cc * 8; c0 < NT; c0 += 5 * 8) {
+#pragma unroll
+            for (int it = 0; it < EP_MAXIT; ++it) {
+                const int c0 = cc * 8 + it * 40;
+                if (c0 >= NT) break;
                 float v[8];
                 tmem_ld8(tcol + c0, v);
                 const int nb = n_tile * NT + c0;
-                float4 e0 = f4zero(), e1 = f4zero();
                 const bool live = ro.m >= 0 && nb < g.Co;
-                if (live && stage == 1) {
-                    e0 = ldg4(a.U + (i64)ro.m * a.ldU + nb); e1 = ldg4(a.U + (i64)ro.m * a.ldU + nb + 4);
-                } else if (live && stage == 2) {
-                    e0 = ldg4(a.R + (i64)ro.m * a.ldR + nb); e1 = ldg4(a.R + (i64)ro.m * a.ldR + nb + 4);
-                }
-                const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                const float4 b0 = *reinterpret_cast<const float4 *>(sb + c0), b1 = *reinterpret_cast<const float4 *>(sb + c0 + 4);
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float ev[8] = {e0[it].x, e0[it].y, e0[it].z, e0[it].w, e1[it].x, e1[it].y, e1[it].z, e1[it].w};
                 float o[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int ne = nb + e < g.Co ? nb + e : g.Co - 1;
-                    float t = live ? v[e] + (bias ? __ldg(bias + ne) : 0.f) : 0.f;
+                    float t = live ? v[e] + bv[e] : 0.f;
                     if (stage == 1) t *= ev[e];
                     else if (stage == 2) t += ev[e];
                     o[e] = t;
@@ -450,16 +546,21 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                     *reinterpret_cast<uint4 *>(sA + chainA_lo + boff) = make_uint4(lo0.x, lo0.y, lo1.x, lo1.y);
                 }
             }
+            if (tid == 128) DF_TRACE(1, 4 + 2 * stage, 1);
             if (!last) {
                 fence_proxy_async();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(stage == 0 ? barE1 : barE2);
+                // operand of the next stage: issued now, consumed after that stage's MMA has been waited for
+                if (stage == 0) fetch_operand(a.U, a.ldU);
+                else fetch_operand(a.R, a.ldR);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 128) DF_TRACE(1, 10, 1);
     if (warp == 0) {
         __syncwarp();
         tc_fence_after();
@@ -493,7 +594,7 @@ __global__ void pack_weight_df_kernel(const float *__restrict__ w, __nv_bfloat16
 size_t df_smem_bytes(int NT)
 {
     return (size_t)DF_SA * DF_ASLOT + (size_t)DF_SB * 2 * (DF_KC / 8) * NT * 16 + (size_t)DF_SP * 128 * DF_PSTRIDE * 16 +
-           128 * sizeof(DfRow) + (2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6) * 8 + 16 + 256 + DF_REGION_BYTES;
+           128 * sizeof(DfRow) + (2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6 + 2) * 8 + 16 + 3 * 128 * sizeof(float) + 256 + DF_REGION_BYTES;
 }
 
 }  // namespace
@@ -551,7 +652,10 @@ int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, const DeformChain
         configured = smem;
     }
     dim3 grid((unsigned)((i64)g.B * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)n_tiles);
-    DLKA_LAUNCH(a.chain ? "tc_deform3d_chain" : "tc_deform3d", st, (deform3d_tc_kernel<<<grid, DF_THREADS, smem, st>>>(a)));
+    CUtensorMap tmapX;
+    memset(&tmapX, 0, sizeof(tmapX));
+    if (DF_REGION && !make_tmap_cl5(&tmapX, a.X, g.B, g.C, g.D, g.H, g.W, DF_KC, DF_RW, DF_RH, DF_RD, 1)) return DLKA_ERR_CUDA;
+    DLKA_LAUNCH(a.chain ? "tc_deform3d_chain" : "tc_deform3d", st, (deform3d_tc_kernel<<<grid, DF_THREADS, smem, st>>>(a, tmapX)));
     return DLKA_OK;
 }
 

@@ -8,10 +8,9 @@
 // (cp.async.bulk.tensor.5d, traversal stride L, hardware zero fill outside the volume) per plane; every
 // thread owns 4 channels (float4) x R outputs along w x TD outputs along d in registers, so each input row loaded
 // from shared memory feeds up to TD*K*R FMAs and each weight vector (broadcast across the warp) R FMAs.
-#include <cuda.h>   // CUtensorMap types only: the encoder is resolved through cudaGetDriverEntryPoint (no libcuda link)
-
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
+#include "tma_host.cuh"
 
 namespace dlka {
 namespace {
@@ -42,25 +41,6 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool va
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// host side: tensor map of the channels-last activation [B][D][H][W][C]; box = one plane of the lattice tile
-// (32 channels x PW x PH voxels), traversal stride L along w and h picks the sub-lattice of this phase
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled_fn()
-{
-    static EncodeTiledFn fn = [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-            qres != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return (EncodeTiledFn)p;
-    }();
-    return fn;
-}
 
 template <int K, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R>
 __global__ void __launch_bounds__((DS_CCH / 4) * (DS_TW / DS_R) * DS_TH, 1)
@@ -187,16 +167,10 @@ int launch_ds(const float *x, const float *wp, const float *bias, float *y, int 
         DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    EncodeTiledFn encode = encode_tiled_fn();
-    if (!encode) return DLKA_ERR_CUDA;
+    // tensor map of the channels-last activation; box = one plane of the lattice tile (32 channels x PW x PH voxels),
+    // traversal stride L along w and h picks the sub-lattice of the CTA's phase
     CUtensorMap tmap;
-    const cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
-    const cuuint64_t gstr[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)D * H * W * C * 4};
-    const cuuint32_t box[5] = {DS_CCH, PW * L, PH * L, 1, 1};
-    const cuuint32_t estr[5] = {1, L, L, 1, 1};
-    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return DLKA_ERR_CUDA;
+    if (!make_tmap_cl5(&tmap, x, B, C, D, H, W, DS_CCH, PW, PH, 1, L)) return DLKA_ERR_CUDA;
     // lattice extents of the largest phase
     const int ld = (int)cdiv(D, L), lh = (int)cdiv(H, L), lw = (int)cdiv(W, L);
     const int tiles_d = (int)cdiv(ld, DS_TD), tiles_h = (int)cdiv(lh, DS_TH), tiles_w = (int)cdiv(lw, DS_TW);

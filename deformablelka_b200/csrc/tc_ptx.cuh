@@ -79,6 +79,8 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const void *tmap,
         : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- tcgen05: tensor memory ----
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols)
 {

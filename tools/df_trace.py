@@ -40,13 +40,36 @@ for ks in list(range(0, 12)) + list(range(40, 46)) + list(range(76, 81)):
 a_ready = t[0, :KS, 1]
 print("per-ks period (mma A-ready deltas): mean", float((a_ready[1:] - a_ready[:-1]).float().mean()),
       " total main loop", int(a_ready[KS - 1] - a_ready[0]))
-g = t[3, :KS]
-print("gather warp 8: mean busy (waits-done -> arrive)", float((g[:, 1] - g[:, 0]).float().mean()),
-      " mean wait (arrive -> next waits-done)", float((g[1:, 0] - g[:-1, 1]).float().mean()))
-p = t[2, :KS]
-print("param warp 4: mean busy", float((p[:, 1] - p[:, 0]).float().mean()), " mean wait", float((p[1:, 0] - p[:-1, 1]).float().mean()))
-mm = t[0, :KS]
-print("mma: mean wait for A after B ready", float((mm[:, 1] - mm[:, 0]).float().mean()))
-lu = t[5, :KS]
-print("g8: waits-done -> loads consumed", float((lu[:, 0] - g[:, 0]).float().mean()), "; loads consumed -> arrive", float((g[:, 1] - lu[:, 0]).float().mean()))
-print("g8: fullP-ok -> emptyA ok", float((g[:, 0] - lu[:, 1]).float().mean()))
+import numpy as np
+
+
+def stats(role, label):
+    """busy = event 0 -> event 1 of the same K step; gap = event 1 -> event 0 of the warp's next K step (gather warps
+    take every DF_GROUPS-th step, so untouched entries are zero and skipped)."""
+    r = t[role, :KS].numpy()
+    ks = np.nonzero(r[:, 0])[0]
+    busy = (r[ks, 1] - r[ks, 0]).mean()
+    gap = (r[ks[1:], 0] - r[ks[:-1], 1]).mean() if len(ks) > 1 else float("nan")
+    print(f"{label}: steps {len(ks)}  mean busy {busy:.1f}  mean wait {gap:.1f}")
+    return r, ks
+
+
+g, gks = stats(3, "gather warp 8  (waits-done -> arrive)")
+stats(4, "gather warp 23 (waits-done -> arrive)")
+stats(2, "param warp 4")
+mm = t[0, :KS].numpy()
+print("mma: mean wait for A after B ready", (mm[:, 1] - mm[:, 0]).mean())
+lu = t[5, :KS].numpy()
+print("g8: waits-done -> loads consumed", (lu[gks, 0] - g[gks, 0]).mean(), "; loads consumed -> arrive", (g[gks, 1] - lu[gks, 0]).mean())
+print("g8: fullP-ok -> emptyA ok", (g[gks, 0] - lu[gks, 1]).mean())
+misc = t[1, :32, 1].numpy()
+lab = {0: "entry", 1: "setup done", 2: "accFull seen", 3: "stage0 start", 4: "stage0 done", 5: "stage1 start (conv1 acc ready)",
+       6: "stage1 done", 7: "stage2 start (proj_2 acc ready)", 8: "stage2 done (stored)", 10: "exit barrier passed"}
+print("CTA timeline (cycles from kernel entry of this CTA; first mma B-ready at", t0 - int(misc[0]), ")")
+for k in sorted(lab):
+    if misc[k]:
+        print(f"  {lab[k]:34s} {int(misc[k] - misc[0]):8d}")
+print("  last main-loop A-ready              ", int(t[0, KS - 1, 1] - misc[0]))
+for st in (1, 2):
+    print(f"  mma stage {st}: weights ready {int(misc[20 + 3 * st] - misc[0])}  A operand ready {int(misc[21 + 3 * st] - misc[0])}  "
+          f"MMAs issued {int(misc[22 + 3 * st] - misc[0])}")
