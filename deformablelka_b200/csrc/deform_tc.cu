@@ -27,7 +27,7 @@ using namespace ptx;
 
 constexpr int DF_KC = 32;                 // channels per K step (one 128-byte line per voxel)
 #ifndef DLKA_DF_REGION
-#define DLKA_DF_REGION 0   // 0: gather through L1 (LDG, measured faster: 12.8 ms); 1: shared-memory staged region (14.0 ms: reload bubbles)
+#define DLKA_DF_REGION 0   // 0: gather through L1 (LDG; 12.3 ms, default); 1: TMA-staged shared-memory region, 8 fat gather warps (13.8 ms)
 #endif
 #ifndef DLKA_DF_SA
 #if DLKA_DF_REGION
@@ -45,15 +45,25 @@ constexpr int DF_SA = DLKA_DF_SA, DF_SB = DLKA_DF_SB, DF_SP = DLKA_DF_SP;
 constexpr int DF_LBO = 2048 + 32;         // A plane stride (bank-spread padding; see profiles/r01 notes)
 constexpr int DF_APLANE = (DF_KC / 8) * DF_LBO;
 constexpr int DF_ASLOT = 2 * DF_APLANE;
-constexpr int DF_PARAM_WARPS = 4, DF_GATHER_WARPS = 16;
-constexpr int DF_THREADS = (4 + DF_PARAM_WARPS + DF_GATHER_WARPS) * 32;
-#ifndef DLKA_DF_GROUPS
-#define DLKA_DF_GROUPS 2   // gather warp groups taking alternate K steps (1: all 16 warps on every K step)
+#ifndef DLKA_DF_SETMAXNREG
+#define DLKA_DF_SETMAXNREG 1
 #endif
-constexpr int DF_GROUPS = DLKA_DF_GROUPS;
+#if DLKA_DF_REGION && DLKA_DF_SETMAXNREG
+#define DF_SETMAXNREG(dir, n) asm volatile("setmaxnreg." dir ".sync.aligned.u32 " n ";")
+#else
+#define DF_SETMAXNREG(dir, n)
+#endif
+constexpr int DF_PARAM_WARPS = 4;
+constexpr int DF_GATHER_WARPS = DF_REGION ? 8 : 16;   // region path: fewer, fatter warps (128 registers) so loads can be software-pipelined
+constexpr int DF_THREADS = (4 + DF_PARAM_WARPS + DF_GATHER_WARPS) * 32;
+constexpr int DF_EPI_WARPS = DF_PARAM_WARPS + DF_GATHER_WARPS, DF_EWQ = DF_EPI_WARPS / 4;   // epilogue warps, per TMEM lane quadrant
+#ifndef DLKA_DF_GROUPS
+#define DLKA_DF_GROUPS 2   // L1 path: gather warp groups taking alternate K steps (1: all 16 warps on every K step)
+#endif
+constexpr int DF_GROUPS = DF_REGION ? 1 : DLKA_DF_GROUPS;
 constexpr int DF_GW = DF_GATHER_WARPS / DF_GROUPS;   // warps per group
 constexpr int DF_GT = DF_GW * 32;                     // threads per group
-constexpr int DF_UNITS = 128 * 8 / DF_GT;             // (row, float4) units per thread and K step
+constexpr int DF_UNITS = 128 * 8 / DF_GT;             // L1 path: (row, float4) units per thread and K step
 static_assert(DF_GROUPS == 1 || DF_GROUPS == 2, "gather groups");
 constexpr int DF_BD = 4, DF_BH = 4, DF_BW = 8;  // brick
 // staged region = brick + halo: covers every corner of samples with |offset| <~ 1 (tap reach 1 + offset + 1);
@@ -123,18 +133,18 @@ __device__ __forceinline__ void df_make_params(const DeformTcArgs &a, const DfRo
             const int x0 = max(s.lo[2], 0), x1 = min(s.lo[2] + 1, g.W - 1);
             const int zd0 = d0 - rd0, zd1 = d1 - rd0, zh0 = h0 - rh0, zh1 = h1 - rh0, zx0 = x0 - rw0, zx1 = x1 - rw0;
             const bool inside = DF_REGION && zd0 >= 0 && zd1 < DF_RD && zh0 >= 0 && zh1 < DF_RH && zx0 >= 0 && zx1 < DF_RW;
-            if (inside) {
-                const int sH = DF_RW * 128, sD = DF_RH * sH;
-                o0.x = zd0 * sD + zh0 * sH + zx0 * 128; o0.y = zd0 * sD + zh0 * sH + zx1 * 128;
-                o0.z = zd0 * sD + zh1 * sH + zx0 * 128; o0.w = zd0 * sD + zh1 * sH + zx1 * 128;
-                o1.x = zd1 * sD + zh0 * sH + zx0 * 128; o1.y = zd1 * sD + zh0 * sH + zx1 * 128;
-                o1.z = zd1 * sD + zh1 * sH + zx0 * 128; o1.w = zd1 * sD + zh1 * sH + zx1 * 128;
-            } else {
-                const int sH = g.W * g.C, sD = g.H * sH;
-                o0.x = d0 * sD + h0 * sH + x0 * g.C; o0.y = d0 * sD + h0 * sH + x1 * g.C;
-                o0.z = d0 * sD + h1 * sH + x0 * g.C; o0.w = d0 * sD + h1 * sH + x1 * g.C;
-                o1.x = d1 * sD + h0 * sH + x0 * g.C; o1.y = d1 * sD + h0 * sH + x1 * g.C;
-                o1.z = d1 * sD + h1 * sH + x0 * g.C; o1.w = d1 * sD + h1 * sH + x1 * g.C;
+            if (inside) {   // region path: offsets in float4 (16-byte) units from the region base
+                const int sX = 8, sH = DF_RW * sX, sD = DF_RH * sH;
+                o0.x = zd0 * sD + zh0 * sH + zx0 * sX; o0.y = zd0 * sD + zh0 * sH + zx1 * sX;
+                o0.z = zd0 * sD + zh1 * sH + zx0 * sX; o0.w = zd0 * sD + zh1 * sH + zx1 * sX;
+                o1.x = zd1 * sD + zh0 * sH + zx0 * sX; o1.y = zd1 * sD + zh0 * sH + zx1 * sX;
+                o1.z = zd1 * sD + zh1 * sH + zx0 * sX; o1.w = zd1 * sD + zh1 * sH + zx1 * sX;
+            } else {        // global element offsets (L1 path), or float4 units with bit 31 of o0.x set (region path, corner outside)
+                const int sX = DF_REGION ? g.C / 4 : g.C, sH = g.W * sX, sD = g.H * sH;
+                o0.x = d0 * sD + h0 * sH + x0 * sX; o0.y = d0 * sD + h0 * sH + x1 * sX;
+                o0.z = d0 * sD + h1 * sH + x0 * sX; o0.w = d0 * sD + h1 * sH + x1 * sX;
+                o1.x = d1 * sD + h0 * sH + x0 * sX; o1.y = d1 * sD + h0 * sH + x1 * sX;
+                o1.z = d1 * sD + h1 * sH + x0 * sX; o1.w = d1 * sD + h1 * sH + x1 * sX;
                 if (DF_REGION) o0.x |= (int)0x80000000;
             }
             w0.x = (s.mask & (1 << 1)) ? hd * hh * hw : 0.f; w0.y = (s.mask & (1 << 2)) ? hd * hh * lw : 0.f;
@@ -146,6 +156,27 @@ __device__ __forceinline__ void df_make_params(const DeformTcArgs &a, const DfRo
     prm[0] = o0; prm[1] = o1;
     *reinterpret_cast<float4 *>(prm + 2) = w0;
     *reinterpret_cast<float4 *>(prm + 3) = w1;
+}
+
+// predicated pair: shared-memory load when `in`, read-only global load otherwise (exactly one of them executes).
+// `off` is in float4 units from either base; the addresses are formed inside the block so they do not stay live.
+__device__ __forceinline__ float4 ld_region_or_global(uint32_t sbase, const float4 *gbase, int off, int in)
+{
+    float4 v;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 sa;\n\t"
+        ".reg .b64 ga;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "mad.lo.u32 sa, %6, 16, %4;\n\t"
+        "mad.wide.s32 ga, %6, 16, %5;\n\t"
+        "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [sa];\n\t"
+        "@!p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [ga];\n\t"
+        "}\n"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "r"(sbase), "l"(gbase), "r"(off), "r"(in));
+    return v;
 }
 
 __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const DeformTcArgs a, const __grid_constant__ CUtensorMap tmapX)
@@ -195,8 +226,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
         for (int s = 0; s < DF_SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
         for (int s = 0; s < DF_SP; ++s) { mbar_init(fullP(s), DF_PARAM_WARPS); mbar_init(emptyP(s), DF_GW); }
         mbar_init(accFull, 1);
-        mbar_init(barW1, 1); mbar_init(barE1, DF_PARAM_WARPS + DF_GATHER_WARPS); mbar_init(barC1, 1);
-        mbar_init(barW2, 1); mbar_init(barE2, DF_PARAM_WARPS + DF_GATHER_WARPS); mbar_init(barC2, 1);
+        mbar_init(barW1, 1); mbar_init(barE1, DF_EPI_WARPS); mbar_init(barC1, 1);
+        mbar_init(barW2, 1); mbar_init(barE2, DF_EPI_WARPS); mbar_init(barC2, 1);
         mbar_init(regFull, 1); mbar_init(regEmpty, DF_GATHER_WARPS);
         fence_barrier_init();
     }
@@ -204,10 +235,12 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
         tmem_alloc(smem_u32(tmem_slot), tmem_cols);
         tmem_relinquish();
     }
-    if (warp >= 8 && tid - 256 < 3 * 128) {  // bias vectors of the three GEMM stages (one element per gather thread)
-        const int i = tid - 256, st = i >> 7, n = n_tile * NT + (i & 127);
-        const float *src = st == 0 ? a.bias : st == 1 ? a.b1 : a.b2;
-        sBias[i] = (src && (i & 127) < NT && n < g.Co && (st == 0 || st <= a.chain)) ? __ldg(src + n) : 0.f;
+    if (warp >= 8) {  // bias vectors of the three GEMM stages (the gather threads are idle during setup)
+        for (int i = tid - 256; i < 3 * 128; i += DF_GATHER_WARPS * 32) {
+            const int st = i >> 7, n = n_tile * NT + (i & 127);
+            const float *src = st == 0 ? a.bias : st == 1 ? a.b1 : a.b2;
+            sBias[i] = (src && (i & 127) < NT && n < g.Co && (st == 0 || st <= a.chain)) ? __ldg(src + n) : 0.f;
+        }
     }
     if (warp >= 4 && warp < 8) {  // brick row decode
         const int r = tid - 128;
@@ -224,6 +257,99 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     const uint32_t tmem_base = *tmem_slot;
     if (tid == 128) DF_TRACE(1, 1, 1);
 
+    auto epilogue = [&]() {
+        // ===================== epilogue: all producer warps (parameter + gather) =====================
+        // TMEM lane quadrant q = warp % 4 (hardware rule); the 5 warps of a quadrant split the columns in chunks of 8
+        // (chunk it of this thread = columns (cc + it*DF_EWQ)*8 ...).  The gate (U) / residual (R) rows of the NEXT stage are
+        // fetched before this thread waits for that stage's MMA, so their HBM latency hides behind the 1x1 GEMM, and the
+        // bias vectors sit in shared memory: no dependent global load is left inside the per-chunk loop.
+        constexpr int EP_MAXIT = (16 + DF_EWQ - 1) / DF_EWQ;   // NT <= 128 -> 16 chunks of 8 columns over DF_EWQ warps per quadrant
+        const int q = warp & 3, cc = (warp - 4) >> 2;  // cc = 0..DF_EWQ-1
+        const int row = q * 32 + lane;
+        const DfRow ro = sRow[row];
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool vec_y = (a.ldY & 3) == 0;
+        float4 e0[EP_MAXIT], e1[EP_MAXIT];
+        auto fetch_operand = [&](const float *src, int ld) {
+#pragma unroll
+            for (int it = 0; it < EP_MAXIT; ++it) {
+                const int c0 = cc * 8 + it * 8 * DF_EWQ, nb = n_tile * NT + c0;
+                e0[it] = e1[it] = f4zero();
+                if (c0 < NT && ro.m >= 0 && nb < g.Co) {
+                    e0[it] = ldg4(src + (i64)ro.m * ld + nb);
+                    e1[it] = ldg4(src + (i64)ro.m * ld + nb + 4);
+                }
+            }
+        };
+        mbar_wait(accFull, 0);
+        if (tid == 128) DF_TRACE(1, 2, 1);
+        tc_fence_after();
+        for (int stage = 0; stage <= a.chain; ++stage) {
+            if (stage == 1) mbar_wait(barC1, 0);
+            if (stage == 2) mbar_wait(barC2, 0);
+            if (tid == 128) DF_TRACE(1, 3 + 2 * stage, 1);
+            if (stage) tc_fence_after();
+            const bool last = stage == a.chain;
+            const float *sb = sBias + stage * 128;
+            const uint32_t tcol = trow + (stage == 1 ? (uint32_t)NT : 0u);
+#pragma unroll
+            for (int it = 0; it < EP_MAXIT; ++it) {
+                const int c0 = cc * 8 + it * 8 * DF_EWQ;
+                if (c0 >= NT) break;
+                float v[8];
+                tmem_ld8(tcol + c0, v);
+                const int nb = n_tile * NT + c0;
+                const bool live = ro.m >= 0 && nb < g.Co;
+                const float4 b0 = *reinterpret_cast<const float4 *>(sb + c0), b1 = *reinterpret_cast<const float4 *>(sb + c0 + 4);
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float ev[8] = {e0[it].x, e0[it].y, e0[it].z, e0[it].w, e1[it].x, e1[it].y, e1[it].z, e1[it].w};
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float t = live ? v[e] + bv[e] : 0.f;
+                    if (stage == 1) t *= ev[e];
+                    else if (stage == 2) t += ev[e];
+                    o[e] = t;
+                }
+                if (last) {
+                    if (live) {
+                        float *yp = a.Y + (i64)ro.m * a.ldY + nb;
+                        if (vec_y && nb + 7 < g.Co) {
+                            *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4 *>(yp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (nb + e < g.Co) yp[e] = o[e];
+                        }
+                    }
+                } else {  // restage as the next GEMM's A operand: this thread's row, 16-byte chunk nb/8
+                    uint2 hi0, lo0, hi1, lo1;
+                    split_bf16x4(make_float4(o[0], o[1], o[2], o[3]), hi0, lo0);
+                    split_bf16x4(make_float4(o[4], o[5], o[6], o[7]), hi1, lo1);
+                    const int boff = (nb >> 3) * DF_LBO + row * 16;
+                    *reinterpret_cast<uint4 *>(sA + boff) = make_uint4(hi0.x, hi0.y, hi1.x, hi1.y);
+                    *reinterpret_cast<uint4 *>(sA + chainA_lo + boff) = make_uint4(lo0.x, lo0.y, lo1.x, lo1.y);
+                }
+            }
+            if (tid == 128) DF_TRACE(1, 4 + 2 * stage, 1);
+            if (!last) {
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(stage == 0 ? barE1 : barE2);
+                // operand of the next stage: issued now, consumed after that stage's MMA has been waited for
+                if (stage == 0) fetch_operand(a.U, a.ldU);
+                else fetch_operand(a.R, a.ldR);
+            }
+        }
+    };
+
+    // Roles by warpgroup.  Region path: register reallocation per warpgroup (56 + 120 + 168 + 168 = 4 x 128, what the CTA was
+    // launched with) -- the control warps and the parameter producers hand registers to the two gather warpgroups, which
+    // keep two 8-load batches in flight.  setmaxnreg must dominate the role code for ptxas to honour the new budget.
+    if (warp < 4) {
+    DF_SETMAXNREG("dec", "56");
     if (warp == 0) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
@@ -304,7 +430,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                 tma_load_5d(smem_u32(sReg), &tmapX, regFull, c * DF_KC, tw * DF_BW - DF_HALO, th * DF_BH - DF_HALO, td * DF_BD - DF_HALO, b);
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    }
+    } else if (warp < 8) {
+        DF_SETMAXNREG("dec", "120");
         // ===================== sample-parameter producers (one thread per brick row) =====================
         const int r = tid - 128;
         const DfRow ri = sRow[r];
@@ -336,7 +464,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             if (++kk == g.kw) { kk = 0; if (++jj == g.kh) { jj = 0; if (++ii == g.kd) ii = 0; } }
             if (++ps == DF_SP) { ps = 0; ph ^= 1; }
         }
-    } else if (warp >= 8) {
+        epilogue();
+    } else {
+        DF_SETMAXNREG("inc", "168");
         // ===================== gather / blend / convert producers =====================
         // DF_GROUPS == 2: the 16 warps form two groups that take alternate K steps, so one group's load phase overlaps
         // the other's blend/convert/store phase instead of all 16 warps moving in lock step.
@@ -394,169 +524,95 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                 if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 1);
             }
         } else {
-            // ---- shared-memory path: the chunk's brick + halo region is staged by TMA; thread = (row, float4 pair) ----
-            // 4 lanes per row, each owning float4 f and f ^ 4 of the 32-channel line, so the 64-byte parameter record is read
-            // once per 8 channels.  Odd rows start with the upper 64 bytes: a quarter-warp (2 rows x 4 lanes) then covers
-            // all 32 banks exactly once per LDS.128.
-            const int j4 = ggt & 3;
-            constexpr int ROWS_PER_ROUND = DF_GT / 4, ROUNDS = 128 / ROWS_PER_ROUND;
-            int cur_chunk = -1;
-            for (int ks = grp; ks < KS; ks += DF_GROUPS) {
-                const int chunk = ks / K;
+            // ---- shared-memory path: the chunk's brick + halo region is staged by ONE TMA tile copy; 8 fat gather warps ----
+            // thread = (row, 8 channels): 4 lanes per row, lane j owns channels [8j, 8j+8) = one 16-byte K chunk of the A
+            // operand, fetched as two float4 halves.  Odd rows take the upper half first, so a quarter-warp (2 rows x 4
+            // lanes) covers all 32 banks exactly once per LDS.128.  Each thread serves rows r0 and r0 + 64 per K step; the
+            // four (row, half) items are software-pipelined: the 8 corner loads of the next item are in flight while the
+            // current one is blended, across K steps too, so the LSU and the FMA pipe overlap inside every warp.
+            const int j4 = lane & 3, r0 = gt >> 2, swp = r0 & 1;
+            // every corner is fetched by a PREDICATED pair (ld.shared from the staged region | ld.global when the sample left
+            // the region): no branch, so the loads stay in flight across the blend of the previous item, and the common case
+            // runs at the shared-memory rate (a generic-address load measured at the L1 rate instead)
+            const uint32_t rs0 = smem_u32(sReg) + (2 * j4 + swp) * 16, rs1 = smem_u32(sReg) + (2 * j4 + (swp ^ 1)) * 16;
+            const float4 *xg = reinterpret_cast<const float4 *>(a.X + (i64)b * a.vol_c);
+            auto ldp = [&](int ps, int row, int4 &o0, int4 &o1, float4 &w0, float4 &w1) {
+                const int4 *prm = sPrm + (ps * 128 + row) * DF_PSTRIDE;
+                o0 = prm[0]; o1 = prm[1];
+                w0 = *reinterpret_cast<const float4 *>(prm + 2); w1 = *reinterpret_cast<const float4 *>(prm + 3);
+            };
+            auto issue = [&](float4(&v)[8], const int4 &o0, const int4 &o1, int half, int chunk) {
+                const int in = o0.x >= 0;
+                const uint32_t sb = half ? rs1 : rs0;
+                const float4 *gb = xg + chunk * (DF_KC / 4) + (2 * j4 + (half ^ swp));
+                const int ox = o0.x & 0x7fffffff;
+                v[0] = ld_region_or_global(sb, gb, ox, in); v[1] = ld_region_or_global(sb, gb, o0.y, in);
+                v[2] = ld_region_or_global(sb, gb, o0.z, in); v[3] = ld_region_or_global(sb, gb, o0.w, in);
+                v[4] = ld_region_or_global(sb, gb, o1.x, in); v[5] = ld_region_or_global(sb, gb, o1.y, in);
+                v[6] = ld_region_or_global(sb, gb, o1.z, in); v[7] = ld_region_or_global(sb, gb, o1.w, in);
+            };
+            auto blend = [&](const float4(&v)[8], const float4 &w0, const float4 &w1) {
+                float4 r = f4zero();
+                fma4(r, w0.x, v[0]); fma4(r, w0.y, v[1]); fma4(r, w0.z, v[2]); fma4(r, w0.w, v[3]);
+                fma4(r, w1.x, v[4]); fma4(r, w1.y, v[5]); fma4(r, w1.z, v[6]); fma4(r, w1.w, v[7]);
+                return r;
+            };
+            auto store_row = [&](uint8_t *slot, int row, const float4 &h0, const float4 &h1) {   // results of half 0 / half 1
+                uint2 hl, ll, hu, lu;
+                split_bf16x4(swp ? h1 : h0, hl, ll);   // channels 8j .. 8j+3
+                split_bf16x4(swp ? h0 : h1, hu, lu);   // channels 8j+4 .. 8j+7
+                const int boff = j4 * DF_LBO + row * 16;
+                *reinterpret_cast<uint4 *>(slot + boff) = make_uint4(hl.x, hl.y, hu.x, hu.y);
+                *reinterpret_cast<uint4 *>(slot + DF_APLANE + boff) = make_uint4(ll.x, ll.y, lu.x, lu.y);
+            };
+            int4 oA0, oA1, oB0, oB1;
+            float4 wA0, wA1, wB0, wB1, va[8], vb[8];
+            int chunk = 0, tap = 0;
+            mbar_wait(regFull, 0);
+            mbar_wait(fullP(0), 0);
+            ldp(0, r0, oA0, oA1, wA0, wA1);
+            issue(va, oA0, oA1, 0, chunk);
+            for (int ks = 0; ks < KS; ++ks) {
                 const int as = ks % DF_SA, ps = ks % DF_SP;
-                const uint32_t phA = ((ks / DF_SA) & 1) ^ 1, phP = (ks / DF_SP) & 1;
-                if (chunk != cur_chunk) {
-                    if (cur_chunk >= 0) {   // this warp has consumed every load of the previous chunk: release the region
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(regEmpty);
-                    }
-                    cur_chunk = chunk;
-                    mbar_wait(regFull, chunk & 1);
-                }
-                mbar_wait(fullP(ps), phP);
-                if (warp == 8 && lane == 0) DF_TRACE(5, ks, 1);
-                mbar_wait(emptyA(as), phA);
-                if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 0);
+                const uint32_t phA = ((ks / DF_SA) & 1) ^ 1;
                 uint8_t *slot = sA + as * DF_ASLOT;
-#pragma unroll
-                for (int rd = 0; rd < ROUNDS; ++rd) {
-                    const int row = (ggt >> 2) + rd * ROWS_PER_ROUND;
-                    const int f0 = j4 + ((row & 1) << 2), f1 = f0 ^ 4;
-                    const int4 *prm = sPrm + (ps * 128 + row) * DF_PSTRIDE;
-                    const int4 o0 = prm[0], o1 = prm[1];
-                    const float4 w0 = *reinterpret_cast<const float4 *>(prm + 2), w1 = *reinterpret_cast<const float4 *>(prm + 3);
-                    float4 v0, v1, v2, v3, v4, v5, v6, v7, u0, u1, u2, u3, u4, u5, u6, u7;
-                    if (o0.x >= 0) {
-                        const uint8_t *ra = sReg + f0 * 16, *rb = sReg + f1 * 16;
-                        v0 = *reinterpret_cast<const float4 *>(ra + o0.x); u0 = *reinterpret_cast<const float4 *>(rb + o0.x);
-                        v1 = *reinterpret_cast<const float4 *>(ra + o0.y); u1 = *reinterpret_cast<const float4 *>(rb + o0.y);
-                        v2 = *reinterpret_cast<const float4 *>(ra + o0.z); u2 = *reinterpret_cast<const float4 *>(rb + o0.z);
-                        v3 = *reinterpret_cast<const float4 *>(ra + o0.w); u3 = *reinterpret_cast<const float4 *>(rb + o0.w);
-                        v4 = *reinterpret_cast<const float4 *>(ra + o1.x); u4 = *reinterpret_cast<const float4 *>(rb + o1.x);
-                        v5 = *reinterpret_cast<const float4 *>(ra + o1.y); u5 = *reinterpret_cast<const float4 *>(rb + o1.y);
-                        v6 = *reinterpret_cast<const float4 *>(ra + o1.z); u6 = *reinterpret_cast<const float4 *>(rb + o1.z);
-                        v7 = *reinterpret_cast<const float4 *>(ra + o1.w); u7 = *reinterpret_cast<const float4 *>(rb + o1.w);
-                    } else {   // a corner left the staged region (large offset): guarded global path, same arithmetic
-                        const float *ga = a.X + (i64)b * a.vol_c + chunk * DF_KC + f0 * 4, *gb = ga + (f1 - f0) * 4;
-                        const int ox = o0.x & 0x7fffffff;
-                        v0 = ldg4(ga + ox); u0 = ldg4(gb + ox); v1 = ldg4(ga + o0.y); u1 = ldg4(gb + o0.y);
-                        v2 = ldg4(ga + o0.z); u2 = ldg4(gb + o0.z); v3 = ldg4(ga + o0.w); u3 = ldg4(gb + o0.w);
-                        v4 = ldg4(ga + o1.x); u4 = ldg4(gb + o1.x); v5 = ldg4(ga + o1.y); u5 = ldg4(gb + o1.y);
-                        v6 = ldg4(ga + o1.z); u6 = ldg4(gb + o1.z); v7 = ldg4(ga + o1.w); u7 = ldg4(gb + o1.w);
-                    }
-                    float4 r0 = f4zero(), r1 = f4zero();
-                    fma4(r0, w0.x, v0); fma4(r0, w0.y, v1); fma4(r0, w0.z, v2); fma4(r0, w0.w, v3);
-                    fma4(r0, w1.x, v4); fma4(r0, w1.y, v5); fma4(r0, w1.z, v6); fma4(r0, w1.w, v7);
-                    fma4(r1, w0.x, u0); fma4(r1, w0.y, u1); fma4(r1, w0.z, u2); fma4(r1, w0.w, u3);
-                    fma4(r1, w1.x, u4); fma4(r1, w1.y, u5); fma4(r1, w1.z, u6); fma4(r1, w1.w, u7);
-                    if (rd + 1 == ROUNDS) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(emptyP(ps));    // parameters consumed
-                        if (warp == 8 && lane == 0) DF_TRACE(5, ks, 0);
-                    }
-                    uint2 hi, lo;
-                    split_bf16x4(r0, hi, lo);
-                    int boff = (f0 >> 1) * DF_LBO + row * 16 + (f0 & 1) * 8;
-                    *reinterpret_cast<uint2 *>(slot + boff) = hi;
-                    *reinterpret_cast<uint2 *>(slot + DF_APLANE + boff) = lo;
-                    split_bf16x4(r1, hi, lo);
-                    boff = (f1 >> 1) * DF_LBO + row * 16 + (f1 & 1) * 8;
-                    *reinterpret_cast<uint2 *>(slot + boff) = hi;
-                    *reinterpret_cast<uint2 *>(slot + DF_APLANE + boff) = lo;
+                if (lane == 0 && warp == 8) DF_TRACE(3, ks, 0);
+                issue(vb, oA0, oA1, 1, chunk);
+                const float4 ra0 = blend(va, wA0, wA1);
+                ldp(ps, r0 + 64, oB0, oB1, wB0, wB1);
+                issue(va, oB0, oB1, 0, chunk);
+                const float4 ra1 = blend(vb, wA0, wA1);
+                mbar_wait(emptyA(as), phA);
+                store_row(slot, r0, ra0, ra1);
+                issue(vb, oB0, oB1, 1, chunk);
+                const float4 rb0 = blend(va, wB0, wB1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(emptyP(ps));    // both rows' parameters are in registers
+                const int nks = ks + 1;
+                const bool more = nks < KS, same = more && tap + 1 < K;
+                if (same) {   // first item of the next K step: in flight while this step's last item is blended and stored
+                    mbar_wait(fullP(nks % DF_SP), (nks / DF_SP) & 1);
+                    ldp(nks % DF_SP, r0, oA0, oA1, wA0, wA1);
+                    issue(va, oA0, oA1, 0, chunk);
                 }
+                const float4 rb1 = blend(vb, wB0, wB1);
+                store_row(slot, r0 + 64, rb0, rb1);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(fullA(as));
-                if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 1);
+                if (lane == 0 && warp == 8) DF_TRACE(3, ks, 1);
+                if (++tap == K) tap = 0;
+                if (more && !same) {   // chunk boundary: every load of the old region has been consumed by this warp
+                    if (lane == 0) mbar_arrive(regEmpty);
+                    ++chunk;
+                    mbar_wait(regFull, chunk & 1);
+                    mbar_wait(fullP(nks % DF_SP), (nks / DF_SP) & 1);
+                    ldp(nks % DF_SP, r0, oA0, oA1, wA0, wA1);
+                    issue(va, oA0, oA1, 0, chunk);
+                }
             }
         }
-    }
-    if (warp >= 4) {
-        // ===================== epilogue: all 20 producer warps =====================
-        // TMEM lane quadrant q = warp % 4 (hardware rule); the 5 warps of a quadrant split the columns in chunks of 8
-        // (chunk it of this thread = columns cc*8 + it*40 ...).  The gate (U) / residual (R) rows of the NEXT stage are
-        // fetched before this thread waits for that stage's MMA, so their HBM latency hides behind the 1x1 GEMM, and the
-        // bias vectors sit in shared memory: no dependent global load is left inside the per-chunk loop.
-        constexpr int EP_MAXIT = 4;                     // NT <= 128 -> at most 4 chunks of 8 columns per thread
-        const int q = warp & 3, cc = (warp - 4) >> 2;  // cc = 0..4
-        const int row = q * 32 + lane;
-        const DfRow ro = sRow[row];
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        const bool vec_y = (a.ldY & 3) == 0;
-        float4 e0[EP_MAXIT], e1[EP_MAXIT];
-        auto fetch_operand = [&](const float *src, int ld) {
-#pragma unroll
-            for (int it = 0; it < EP_MAXIT; ++it) {
-                const int c0 = cc * 8 + it * 40, nb = n_tile * NT + c0;
-                e0[it] = e1[it] = f4zero();
-                if (c0 < NT && ro.m >= 0 && nb < g.Co) {
-                    e0[it] = ldg4(src + (i64)ro.m * ld + nb);
-                    e1[it] = ldg4(src + (i64)ro.m * ld + nb + 4);
-                }
-            }
-        };
-        mbar_wait(accFull, 0);
-        if (tid == 128) DF_TRACE(1, 2, 1);
-        tc_fence_after();
-        for (int stage = 0; stage <= a.chain; ++stage) {
-            if (stage == 1) mbar_wait(barC1, 0);
-            if (stage == 2) mbar_wait(barC2, 0);
-            if (tid == 128) DF_TRACE(1, 3 + 2 * stage, 1);
-            if (stage) tc_fence_after();
-            const bool last = stage == a.chain;
-            const float *sb = sBias + stage * 128;
-            const uint32_t tcol = trow + (stage == 1 ? (uint32_t)NT : 0u);
-#pragma unroll
-            for (int it = 0; it < EP_MAXIT; ++it) {
-                const int c0 = cc * 8 + it * 40;
-                if (c0 >= NT) break;
-                float v[8];
-                tmem_ld8(tcol + c0, v);
-                const int nb = n_tile * NT + c0;
-                const bool live = ro.m >= 0 && nb < g.Co;
-                const float4 b0 = *reinterpret_cast<const float4 *>(sb + c0), b1 = *reinterpret_cast<const float4 *>(sb + c0 + 4);
-                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                const float ev[8] = {e0[it].x, e0[it].y, e0[it].z, e0[it].w, e1[it].x, e1[it].y, e1[it].z, e1[it].w};
-                float o[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float t = live ? v[e] + bv[e] : 0.f;
-                    if (stage == 1) t *= ev[e];
-                    else if (stage == 2) t += ev[e];
-                    o[e] = t;
-                }
-                if (last) {
-                    if (live) {
-                        float *yp = a.Y + (i64)ro.m * a.ldY + nb;
-                        if (vec_y && nb + 7 < g.Co) {
-                            *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);
-                            *reinterpret_cast<float4 *>(yp + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                if (nb + e < g.Co) yp[e] = o[e];
-                        }
-                    }
-                } else {  // restage as the next GEMM's A operand: this thread's row, 16-byte chunk nb/8
-                    uint2 hi0, lo0, hi1, lo1;
-                    split_bf16x4(make_float4(o[0], o[1], o[2], o[3]), hi0, lo0);
-                    split_bf16x4(make_float4(o[4], o[5], o[6], o[7]), hi1, lo1);
-                    const int boff = (nb >> 3) * DF_LBO + row * 16;
-                    *reinterpret_cast<uint4 *>(sA + boff) = make_uint4(hi0.x, hi0.y, hi1.x, hi1.y);
-                    *reinterpret_cast<uint4 *>(sA + chainA_lo + boff) = make_uint4(lo0.x, lo0.y, lo1.x, lo1.y);
-                }
-            }
-            if (tid == 128) DF_TRACE(1, 4 + 2 * stage, 1);
-            if (!last) {
-                fence_proxy_async();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(stage == 0 ? barE1 : barE2);
-                // operand of the next stage: issued now, consumed after that stage's MMA has been waited for
-                if (stage == 0) fetch_operand(a.U, a.ldU);
-                else fetch_operand(a.R, a.ldR);
-            }
-        }
+        epilogue();
     }
     tc_fence_before();
     __syncthreads();

@@ -37,17 +37,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the thread is parked by the hardware until the phase completes (or the hint, in
+// ns, expires) instead of spinning -- a spinning waiter costs issue slots AND shared-memory wavefronts (measured: 39 % of all
+// instructions of the deformable kernel were BRA / TRYWAIT / YIELD of waiting warps before the hint was added).
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P1;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
