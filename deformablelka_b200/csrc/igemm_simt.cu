@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(NTHREADS) igemm_simt_kernel(const IgemmArgs a)
             if (n >= Ng) continue;
             const int nc = group * Ng + n;
             float v = acc[i][j] + (a.bias ? __ldg(a.bias + nc) : 0.f);
-            if (a.epi == EPI_GELU) v = gelu_erf(v);
+            if (a.epi == EPI_GELU) v = gelu_erf_libm(v);
             else if (a.epi == EPI_MUL) v *= __ldg(a.E + m * (i64)a.ldE + nc);
             else if (a.epi == EPI_ADD) v += __ldg(a.E + m * (i64)a.ldE + nc);
             a.Y[m * (i64)a.ldY + nc] = v;

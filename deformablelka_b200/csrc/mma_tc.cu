@@ -26,9 +26,9 @@ namespace {
 using namespace ptx;
 
 #ifndef DLKA_A_PAD
-#define DLKA_A_PAD 0
+#define DLKA_A_PAD 16   // LBO = 2064: the 8 K-chunk planes a half-warp writes land on 8 different 4-bank groups (2048 gave an 8-way conflict)
 #endif
-constexpr int A_PAD = DLKA_A_PAD;       // extra bytes on LBO_A (bank-conflict padding experiment)
+constexpr int A_PAD = DLKA_A_PAD;       // extra bytes on LBO_A (bank spread; descriptors only need 16-byte granularity)
 constexpr int LBO_A = 2048 + A_PAD;     // bytes between 16-byte K chunks of an A slot (128 rows)
 constexpr int CTRL_WARPS = 4;
 
@@ -132,6 +132,7 @@ __global__ void __launch_bounds__((CTRL_WARPS + NPW) * 32, (MODE == IGEMM_DENSE 
     RowInfo *sRow = reinterpret_cast<RowInfo *>(reinterpret_cast<uint8_t *>(sPrm) + (MODE == IGEMM_DEFORM ? SA * 128 * 64 : 0));
     uint64_t *bars = reinterpret_cast<uint64_t *>(sRow + NKC_MAXROWS);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * SA + 2 * SB + 1);
+    float *sBias = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [128], 0 beyond Co
 
     const uint32_t bar0 = smem_u32(bars);
     auto fullA = [&](int s) { return bar0 + 8u * s; };
@@ -157,11 +158,15 @@ __global__ void __launch_bounds__((CTRL_WARPS + NPW) * 32, (MODE == IGEMM_DENSE 
         tmem_alloc(smem_u32(tmem_slot), tmem_cols);
         tmem_relinquish();
     }
-    if (warp >= CTRL_WARPS) {  // row decode, once per CTA
+    if (warp >= CTRL_WARPS) {  // bias vector + row decode, once per CTA
+        for (int i = tid - CTRL_WARPS * 32; i < 128; i += NPT) {
+            const int n = n_tile * a.NT + i;
+            sBias[i] = (a.g.bias && i < a.NT && n < a.g.geo.Co) ? __ldg(a.g.bias + n) : 0.f;
+        }
         for (int r = tid - CTRL_WARPS * 32; r < MT * 128; r += NPT) {
             i64 m = m0 + r;
             RowInfo ri = {0, 0, 0, 0};
-            if (m < a.g.M) {
+            if (MODE != IGEMM_DENSE && m < a.g.M) {   // dense rows need no coordinates
                 const ConvGeo &g = a.g.geo;
                 ri.w = (int)(m % g.Wo);
                 i64 t = m / g.Wo;
@@ -235,8 +240,11 @@ __global__ void __launch_bounds__((CTRL_WARPS + NPW) * 32, (MODE == IGEMM_DENSE 
                     asm volatile("bar.sync 1, %0;" ::"r"(NPT) : "memory");
                 }
                 uint8_t *slot = sA + as * A_SLOT;
-#pragma unroll 4
-                for (int u = ptid; u < UNITS; u += NPT) {
+                // dense / conv rows are plain loads: keep every load of the slot in flight (HBM latency is paid once per slot)
+                static_assert(UNITS % NPT == 0, "units per producer thread");
+#pragma unroll(MODE == IGEMM_DEFORM ? 2 : UNITS / NPT)
+                for (int ui = 0; ui < UNITS / NPT; ++ui) {
+                    const int u = ptid + ui * NPT;
                     const int row = u / CG, cg = u - row * CG;
                     const i64 m = m0 + h * 128 + row;
                     const float4 v = produce4<MODE>(a, sRow[h * 128 + row], m < a.g.M, m, tap, kc * KC + cg * 4,
@@ -252,56 +260,75 @@ __global__ void __launch_bounds__((CTRL_WARPS + NPW) * 32, (MODE == IGEMM_DENSE 
                 if (lane == 0) mbar_arrive(fullA(as));
             }
         }
-        // ===================== epilogue =====================
+        // ===================== epilogue: every producer warp =====================
+        // TMEM lane quadrant q = warp % 4 (hardware rule); the WPP warps that share a (quadrant, 128-row half) interleave
+        // the 16-column chunks.  Bias comes from shared memory and the multiply / add operand rows are fetched BEFORE the
+        // accumulator wait, so no dependent global load sits between tcgen05.ld and the store.
+        constexpr int WPP = NPW / (4 * MT);             // warps per (quadrant, half)
+        constexpr int EP_MAXIT = (8 + WPP - 1) / WPP;    // NT <= 128 -> 8 chunks of 16 columns
         const int pw = warp - CTRL_WARPS;
-        if (pw < 4 * MT) {
-            const int q = warp & 3, h = pw >> 2;  // TMEM lane quadrant of this warp, 128-row half
-            mbar_wait(accFull, 0);
-            tc_fence_after();
-            const i64 m = m0 + h * 128 + q * 32 + lane;
-            const bool mv = m < a.g.M;
-            const int Nvalid = a.g.geo.Co;
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * NT);
-            const bool vec_y = (a.g.ldY & 3) == 0, vec_e = (a.g.ldE & 3) == 0;
-            for (int c0 = 0; c0 < NT; c0 += 16) {
-                float v[16];
-                tmem_ld16(trow + c0, v);
-                if (!mv) continue;
-                const int nb = n_tile * NT + c0;
+        const int q = warp & 3, h = (pw >> 2) % MT, cc = (pw >> 2) / MT;
+        const i64 m = m0 + h * 128 + q * 32 + lane;
+        const bool mv = m < a.g.M;
+        const int Nvalid = a.g.geo.Co;
+        const bool vec_y = (a.g.ldY & 3) == 0, vec_e = (a.g.ldE & 3) == 0;
+        const bool has_e = a.g.epi == EPI_MUL || a.g.epi == EPI_ADD;
+        float4 ev[EP_MAXIT][4];
+        if (has_e) {
+#pragma unroll
+            for (int it = 0; it < EP_MAXIT; ++it) {
+                const int nb = n_tile * NT + (cc + it * WPP) * 16;
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const int n = nb + j4 * 4;
-                    if (n >= Nvalid) break;
-                    float o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int ne = n + e < Nvalid ? n + e : Nvalid - 1;
-                        o[e] = v[j4 * 4 + e] + (a.g.bias ? __ldg(a.g.bias + ne) : 0.f);
-                    }
-                    if (a.g.epi == EPI_GELU) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) o[e] = gelu_erf(o[e]);
-                    } else if (a.g.epi == EPI_MUL || a.g.epi == EPI_ADD) {
-                        float ev[4];
+                    float4 t = f4zero();
+                    if (mv && (cc + it * WPP) * 16 < NT && n < Nvalid) {
                         const float *ep = a.g.E + m * (i64)a.g.ldE + n;
-                        if (vec_e && n + 3 < Nvalid) {
-                            const float4 t = ldg4(ep);
-                            ev[0] = t.x; ev[1] = t.y; ev[2] = t.z; ev[3] = t.w;
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) ev[e] = n + e < Nvalid ? __ldg(ep + e) : 0.f;
+                        if (vec_e && n + 3 < Nvalid) t = ldg4(ep);
+                        else {
+                            t.x = __ldg(ep);
+                            if (n + 1 < Nvalid) t.y = __ldg(ep + 1);
+                            if (n + 2 < Nvalid) t.z = __ldg(ep + 2);
+                            if (n + 3 < Nvalid) t.w = __ldg(ep + 3);
                         }
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) o[e] = a.g.epi == EPI_MUL ? o[e] * ev[e] : o[e] + ev[e];
                     }
-                    float *yp = a.g.Y + m * (i64)a.g.ldY + n;
-                    if (vec_y && n + 3 < Nvalid) {
-                        *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);
-                    } else {
+                    ev[it][j4] = t;
+                }
+            }
+        }
+        mbar_wait(accFull, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * NT);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (n + e < Nvalid) yp[e] = o[e];
-                    }
+        for (int it = 0; it < EP_MAXIT; ++it) {
+            const int c0 = (cc + it * WPP) * 16;
+            if (c0 >= NT) break;
+            float v[16];
+            tmem_ld16(trow + c0, v);
+            if (!mv) continue;
+            const int nb = n_tile * NT + c0;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const int n = nb + j4 * 4;
+                if (n >= Nvalid) break;
+                const float4 bv = *reinterpret_cast<const float4 *>(sBias + c0 + j4 * 4);
+                float o[4] = {v[j4 * 4] + bv.x, v[j4 * 4 + 1] + bv.y, v[j4 * 4 + 2] + bv.z, v[j4 * 4 + 3] + bv.w};
+                if (a.g.epi == EPI_GELU) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = gelu_erf(o[e]);
+                } else if (has_e) {
+                    const float4 t = ev[it][j4];
+                    const float e4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = a.g.epi == EPI_MUL ? o[e] * e4[e] : o[e] + e4[e];
+                }
+                float *yp = a.g.Y + m * (i64)a.g.ldY + n;
+                if (vec_y && n + 3 < Nvalid) {
+                    *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (n + e < Nvalid) yp[e] = o[e];
                 }
             }
         }
@@ -345,7 +372,7 @@ int launch_tc(const TcArgs &a, int n_tiles, cudaStream_t st)
     const int NT = a.NT;
     const size_t smem = (size_t)SA * 2 * a_plane_bytes<KC>() + (size_t)SB * 2 * (KC / 8) * NT * 16 +
                         (MODE == IGEMM_DEFORM ? (size_t)SA * 128 * 64 : 0) + (size_t)MT * 128 * sizeof(RowInfo) +
-                        (2 * SA + 2 * SB + 1) * 8 + 16 + 128;
+                        (2 * SA + 2 * SB + 1) * 8 + 16 + 16 + 128 * sizeof(float) + 128;
     auto kern = tc_igemm_kernel<MODE, KC, MT, NPW, SA, SB>;
     static thread_local size_t configured = 0;
     if (smem > configured) {
