@@ -213,6 +213,15 @@ __device__ __forceinline__ void fma4v(float4 &acc, const float4 &w, const float4
     asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a0));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.z), "=f"(acc.w) : "l"(a1));
 }
+__device__ __forceinline__ void fma2v(float2 &acc, const float2 &w, const float2 &x)
+{
+    unsigned long long a0, w0, x0;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(acc.x), "f"(acc.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(w0) : "f"(w.x), "f"(w.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x0) : "f"(x.x), "f"(x.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(w0), "l"(x0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a0));
+}
 // acc += s * x with a scalar weight (broadcast into both halves)
 __device__ __forceinline__ void fma4s(float4 &acc, float s, const float4 &x)
 {

@@ -24,11 +24,17 @@ namespace {
 #define DLKA_DS5_TW 16
 #define DLKA_DS5_R 8
 #endif
+#ifndef DLKA_DS5_VW
+#define DLKA_DS5_VW 2   // channels per thread (4: float4, 8 lanes per voxel; 2: float2, 16 lanes per voxel)
+#endif
 #ifndef DLKA_DS7_TD
 #define DLKA_DS7_TD 2
 #define DLKA_DS7_TH 15
 #define DLKA_DS7_TW 22
 #define DLKA_DS7_R 11
+#endif
+#ifndef DLKA_DS7_VW
+#define DLKA_DS7_VW 2
 #endif
 constexpr int DS_CCH = 32;                                     // channels per CTA
 
@@ -39,19 +45,38 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool va
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// per-thread channel vector: float4 (8 lanes per voxel) or float2 (16 lanes per voxel: half the registers per thread, twice
+// the warps per scheduler for the same LSU / FMA totals)
+template <int VW> struct DsVec;
+template <> struct DsVec<4> {
+    typedef float4 T;
+    static __device__ __forceinline__ T zero() { return f4zero(); }
+    static __device__ __forceinline__ T ldg(const float *p) { return ldg4(p); }
+    static __device__ __forceinline__ void fma(T &a, const T &w, const T &x) { fma4v(a, w, x); }
+};
+template <> struct DsVec<2> {
+    typedef float2 T;
+    static __device__ __forceinline__ T zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ T ldg(const float *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
+    static __device__ __forceinline__ void fma(T &a, const T &w, const T &x) { fma2v(a, w, x); }
+};
+
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int K, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R>
-__global__ void __launch_bounds__((DS_CCH / 4) * (DS_TW / DS_R) * DS_TH, 1)
+template <int K, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R, int VW>
+__global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
     dwconv_smem_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ wp, const float *__restrict__ bias,
                        float *__restrict__ y, int C, int D, int H, int W, int tiles_d, int tiles_h, int tiles_w)
 {
-    constexpr int DS_THREADS = (DS_CCH / 4) * (DS_TW / DS_R) * DS_TH;
+    typedef DsVec<VW> V;
+    typedef typename V::T vec;
+    constexpr int LPV = DS_CCH / VW;                          // lanes (vectors) per voxel
+    constexpr int DS_THREADS = LPV * (DS_TW / DS_R) * DS_TH;
     static_assert(DS_TW % DS_R == 0 && DS_THREADS <= 1024, "tile shape");
     constexpr int P = (K - 1) / 2;
     constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;   // plane extent (lattice voxels)
-    constexpr int PLANE_F4 = PH * PW * (DS_CCH / 4);         // float4 elements per plane
+    constexpr int PLANE_F4 = PH * PW * (DS_CCH / 4);         // float4 elements per plane (128 B per voxel)
     constexpr int NPLANES = DS_TD + K - 1;
     extern __shared__ __align__(128) float4 smem4[];
     float4 *sP = smem4;                                      // [2][PH][PW][8] float4 (TMA destination, 128-byte aligned)
@@ -60,7 +85,7 @@ __global__ void __launch_bounds__((DS_CCH / 4) * (DS_TW / DS_R) * DS_TH, 1)
 
     const int tid = threadIdx.x;
     constexpr int WRUNS = DS_TW / DS_R;
-    const int q = tid & 7, wr = (tid >> 3) % WRUNS, hl = (tid >> 3) / WRUNS;
+    const int q = tid % LPV, wr = (tid / LPV) % WRUNS, hl = (tid / LPV) / WRUNS;
     // CTA decomposition: x = tile, y = phase * nchunks + chunk, z = batch
     int bid = blockIdx.x;
     const int tw = bid % tiles_w; bid /= tiles_w;
@@ -95,9 +120,9 @@ __global__ void __launch_bounds__((DS_CCH / 4) * (DS_TW / DS_R) * DS_TH, 1)
                          pd_ + L * (zd0 - P + s), b);
     };
 
-    float4 acc[DS_TD][DS_R];
+    vec acc[DS_TD][DS_R];
     {
-        const float4 bv = bias ? ldg4(bias + c0 + q * 4) : f4zero();
+        const vec bv = bias ? V::ldg(bias + c0 + q * VW) : V::zero();
 #pragma unroll
         for (int t = 0; t < DS_TD; ++t)
 #pragma unroll
@@ -111,24 +136,24 @@ __global__ void __launch_bounds__((DS_CCH / 4) * (DS_TW / DS_R) * DS_TH, 1)
     for (int s = 0; s < NPLANES; ++s) {
         if (tid == 0 && s + 1 < NPLANES) load_plane(s + 1, (s + 1) & 1);   // that buffer was released by the barrier below
         ptx::mbar_wait(bar0 + 8u * (s & 1), (s >> 1) & 1);
-        const float4 *pl = sP + (s & 1) * PLANE_F4;
+        const vec *pl = reinterpret_cast<const vec *>(sP + (s & 1) * PLANE_F4);
         // plane s contributes to output t with depth tap i = s - t
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            float4 in[DS_R + K - 1];
-            const float4 *row = pl + ((hl + j) * PW + wr * DS_R) * 8 + q;
+            vec in[DS_R + K - 1];
+            const vec *row = pl + ((hl + j) * PW + wr * DS_R) * LPV + q;
 #pragma unroll
-            for (int e = 0; e < DS_R + K - 1; ++e) in[e] = row[e * 8];
+            for (int e = 0; e < DS_R + K - 1; ++e) in[e] = row[e * LPV];
 #pragma unroll
             for (int t = 0; t < DS_TD; ++t) {
                 const int i = s - t;
                 if (i < 0 || i >= K) continue;  // uniform across the CTA
-                const float4 *wrow = sW + ((i * K + j) * K) * 8 + q;
+                const vec *wrow = reinterpret_cast<const vec *>(sW) + ((i * K + j) * K) * LPV + q;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const float4 wv = wrow[k * 8];
+                    const vec wv = wrow[k * LPV];
 #pragma unroll
-                    for (int r = 0; r < DS_R; ++r) fma4v(acc[t][r], wv, in[r + k]);
+                    for (int r = 0; r < DS_R; ++r) V::fma(acc[t][r], wv, in[r + k]);
                 }
             }
         }
@@ -148,20 +173,20 @@ __global__ void __launch_bounds__((DS_CCH / 4) * (DS_TW / DS_R) * DS_TH, 1)
             for (int r = 0; r < DS_R; ++r) {
                 const int wrr = pw_ + L * (zw0 + wr * DS_R + r);
                 if (wrr < W)
-                    *reinterpret_cast<float4 *>(y + ((((i64)b * D + dr) * H + hr) * W + wrr) * C + c0 + q * 4) = acc[t][r];
+                    *reinterpret_cast<vec *>(y + ((((i64)b * D + dr) * H + hr) * W + wrr) * C + c0 + q * VW) = acc[t][r];
             }
         }
     }
 }
 
-template <int K, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R>
+template <int K, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R, int VW>
 int launch_ds(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, cudaStream_t st)
 {
     constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;
-    constexpr int DS_THREADS = (DS_CCH / 4) * (DS_TW / DS_R) * DS_TH;
+    constexpr int DS_THREADS = (DS_CCH / VW) * (DS_TW / DS_R) * DS_TH;
     static_assert(PW * L <= 256 && PH * L <= 256, "TMA box extent");
     const size_t smem = ((size_t)K * K * K * 8 + 2 * (size_t)PH * PW * 8) * sizeof(float4) + 64;
-    auto kern = dwconv_smem_kernel<K, L, DS_TD, DS_TH, DS_TW, DS_R>;
+    auto kern = dwconv_smem_kernel<K, L, DS_TD, DS_TH, DS_TW, DS_R, VW>;
     static thread_local bool configured = false;
     if (!configured) {
         DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -193,8 +218,8 @@ bool dwconv_smem_supported(int C, int kd, int kh, int kw, int dil)
 int dwconv_smem(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, int k, int dil,
                 cudaStream_t st)
 {
-    if (k == 5 && dil == 1) return launch_ds<5, 1, DLKA_DS5_TD, DLKA_DS5_TH, DLKA_DS5_TW, DLKA_DS5_R>(x, wp, bias, y, B, C, D, H, W, st);
-    if (k == 7 && dil == 3) return launch_ds<7, 3, DLKA_DS7_TD, DLKA_DS7_TH, DLKA_DS7_TW, DLKA_DS7_R>(x, wp, bias, y, B, C, D, H, W, st);
+    if (k == 5 && dil == 1) return launch_ds<5, 1, DLKA_DS5_TD, DLKA_DS5_TH, DLKA_DS5_TW, DLKA_DS5_R, DLKA_DS5_VW>(x, wp, bias, y, B, C, D, H, W, st);
+    if (k == 7 && dil == 3) return launch_ds<7, 3, DLKA_DS7_TD, DLKA_DS7_TH, DLKA_DS7_TW, DLKA_DS7_R, DLKA_DS7_VW>(x, wp, bias, y, B, C, D, H, W, st);
     return DLKA_ERR_UNSUPPORTED;
 }
 
