@@ -272,6 +272,14 @@ def main():
         roof = {"bound": "tensor", "kernel": dom_name, "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops"], "traffic": traffic.get(dom_name), "peak_source": pk["source"] + " bf16 burst",
                 "avg_launch_ms": dom_avg_ms, "share_of_step": dom_ms / total_prof_ms if total_prof_ms else None}
+        if dom_name.startswith("tc_deform3d"):
+            # what actually binds this kernel: the trilinear gather through the SM's L1 data path, 1.84 cycles
+            # per 128-byte line measured by tools/l1_probe.cu; reported beside the contract's tensor roofline
+            lines = vox * 27 * 8 * (C // 32)
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            floor_ms = lines * 1.84 / (148 * sm_mhz * 1e6) * 1e3
+            roof["onchip_gather"] = {"lines_128B": lines, "cycles_per_line_measured": 1.84, "floor_ms": floor_ms,
+                                     "frac_of_floor": floor_ms / dom_avg_ms}
     else:
         ach = HBM_BYTES_PER_VOXEL * vox / (dom_avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
