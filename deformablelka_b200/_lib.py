@@ -22,11 +22,16 @@ MATH_BF16X3 = 1
 _MATH_NAMES = {"fp32": MATH_FP32_SIMT, "fp32_simt": MATH_FP32_SIMT, "bf16x3": MATH_BF16X3}
 
 
+class DwGeom3d(Structure):
+    """dlkaDwGeom3d: depthwise stencil shapes of the 3D block (include/dlka.h)."""
+    _fields_ = [("conv0_k", c_int * 3), ("conv0_dil", c_int * 3), ("conv_spatial_k", c_int * 3), ("conv_spatial_dil", c_int * 3)]
+
+
 class Block3dParams(Structure):
     _fields_ = [(n, c_void_p) for n in (
         "proj_1_weight", "proj_1_bias", "conv0_weight", "conv0_bias", "conv_spatial_weight", "conv_spatial_bias",
         "conv_offset_weight", "conv_offset_bias", "deform_weight", "deform_bias", "conv1_weight", "conv1_bias",
-        "proj_2_weight", "proj_2_bias")]
+        "proj_2_weight", "proj_2_bias")] + [("dw_geom", POINTER(DwGeom3d))]
 
 
 class Block2dParams(Structure):

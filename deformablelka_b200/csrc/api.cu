@@ -189,14 +189,30 @@ bool plan_block3d(Arena &ar, int B, int C, int D1, int D2, int D3, Block3dPlan &
     return ar.ok();
 }
 
+// packed depthwise weights live in fixed workspace slots sized for 5^3 and 7^3 taps
+bool bad_dw_geom(const dlkaDwGeom3d &G)
+{
+    auto bad = [](const int *k, const int *dil, int max_taps) {
+        for (int i = 0; i < 3; ++i)
+            if (k[i] < 1 || !(k[i] & 1) || dil[i] < 1) return true;
+        return k[1] != k[2] || dil[1] != dil[2] || k[0] * k[1] * k[2] > max_taps;
+    };
+    return bad(G.conv0_k, G.conv0_dil, 125) || bad(G.conv_spatial_k, G.conv_spatial_dil, 343);
+}
+
 // u (channels-last, = GELU(proj_1 x) or x itself) -> gate = u * conv1(deform(dw7(dw5(u)))) into p.t3
 // returns DLKA_OK with the gate in p.t3, or 1 when (fuse_proj2) proj_2 + shortcut were fused and y_final is complete
 int run_lka3d_core(const dlkaBlock3dParams &P, const float *u, Block3dPlan &p, int B, int C, int D1, int D2, int D3,
                    int math, cudaStream_t st, bool fuse_proj2 = false, const float *resid = nullptr, float *y_final = nullptr)
 {
     const i64 M = (i64)B * D1 * D2 * D3;
-    DLKA_TRY(dwconv_cl(u, P.conv0_weight, P.conv0_bias, p.t2, B, C, D1, D2, D3, 5, 5, 5, 1, p.wp_dw5, st));
-    DLKA_TRY(dwconv_cl(p.t2, P.conv_spatial_weight, P.conv_spatial_bias, p.t3, B, C, D1, D2, D3, 7, 7, 7, 3, p.wp_dw7, st));
+    static const dlkaDwGeom3d synapse = {{5, 5, 5}, {1, 1, 1}, {7, 7, 7}, {3, 3, 3}};   // transformerblock.py:637-638
+    const dlkaDwGeom3d &G = P.dw_geom ? *P.dw_geom : synapse;
+    if (bad_dw_geom(G)) return DLKA_ERR_UNSUPPORTED;
+    DLKA_TRY(dwconv_cl(u, P.conv0_weight, P.conv0_bias, p.t2, B, C, D1, D2, D3, G.conv0_k[0], G.conv0_k[1], G.conv0_k[2],
+                       G.conv0_dil[0], G.conv0_dil[1], p.wp_dw5, st));
+    DLKA_TRY(dwconv_cl(p.t2, P.conv_spatial_weight, P.conv_spatial_bias, p.t3, B, C, D1, D2, D3, G.conv_spatial_k[0],
+                       G.conv_spatial_k[1], G.conv_spatial_k[2], G.conv_spatial_dil[0], G.conv_spatial_dil[1], p.wp_dw7, st));
     // conv_offset: Conv3d(C -> 81, k3, stride 1, pad 1)  (synapse/deform_conv.py:80-85)
     const ConvGeo go = make_geo(B, C, D1, D2, D3, 81, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3);
     IgemmArgs ao = conv_args(IGEMM_CONV, go, p.t3, nullptr, nullptr, nullptr, 0, P.conv_offset_bias, EPI_NONE, nullptr, 0, p.off,

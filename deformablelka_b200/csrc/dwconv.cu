@@ -75,6 +75,41 @@ __global__ void __launch_bounds__(256) dwconv3d_cl_kernel(const float *__restric
     }
 }
 
+// any odd kernel (kd, kh, kw) with per-axis dilation, "same" extent: thread = (voxel, 4-channel chunk).  Fallback for the
+// stencil shapes / channel counts the shared-memory kernel has no instance for.
+__global__ void __launch_bounds__(256) dwconv3d_generic_kernel(const float *__restrict__ x, const float *__restrict__ wp,
+                                                               const float *__restrict__ bias, float *__restrict__ y, int B, int C,
+                                                               int D, int H, int W, int kd, int kh, int kw, int dd, int dh, int dw)
+{
+    const int C4 = C / 4;
+    const i64 total = (i64)B * D * H * W * C4;
+    const int pd = dd * (kd - 1) / 2, ph = dh * (kh - 1) / 2, pw = dw * (kw - 1) / 2;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        i64 v = i / C4;
+        const int w = (int)(v % W); v /= W;
+        const int h = (int)(v % H); v /= H;
+        const int d = (int)(v % D);
+        const int b = (int)(v / D);
+        float4 acc = bias ? ldg4(bias + c) : f4zero();
+        for (int ii = 0; ii < kd; ++ii) {
+            const int din = d - pd + dd * ii;
+            if ((unsigned)din >= (unsigned)D) continue;
+            for (int jj = 0; jj < kh; ++jj) {
+                const int hin = h - ph + dh * jj;
+                if ((unsigned)hin >= (unsigned)H) continue;
+                for (int kk = 0; kk < kw; ++kk) {
+                    const int win = w - pw + dw * kk;
+                    if ((unsigned)win >= (unsigned)W) continue;
+                    fma4v(acc, ldg4(wp + (i64)((ii * kh + jj) * kw + kk) * C + c),
+                          ldg4(x + ((((i64)b * D + din) * H + hin) * W + win) * C + c));
+                }
+            }
+        }
+        *reinterpret_cast<float4 *>(y + i * 4) = acc;
+    }
+}
+
 // depthwise deformable conv: thread = (row, 4-channel chunk)
 template <int NDIM>
 __global__ void __launch_bounds__(256) deform_dwconv_cl_kernel(const float *__restrict__ x, const float *__restrict__ off,
@@ -149,15 +184,22 @@ int launch_dw(const float *x, const float *wp, const float *bias, float *y, int 
 }  // namespace
 
 int dwconv_cl(const float *x, const float *w, const float *bias, float *y, int B, int C, int D, int H, int W, int kd,
-              int kh, int kw, int dil, float *w_packed, cudaStream_t st)
+              int kh, int kw, int dd, int dil, float *w_packed, cudaStream_t st)
 {
-    if (C % 4 != 0 || C / 4 > 256) return DLKA_ERR_UNSUPPORTED;
-    if (kh != kw || (kd != kh && kd != 1)) return DLKA_ERR_UNSUPPORTED;
+    if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    if (kd < 1 || kh < 1 || kw < 1 || !(kd & 1) || !(kh & 1) || !(kw & 1) || dd < 1 || dil < 1) return DLKA_ERR_UNSUPPORTED;
     DLKA_TRY(pack_dw(w, w_packed, C, kd * kh * kw, st));
-    if (dwconv_smem_supported(C, kd, kh, kw, dil)) return dwconv_smem(x, w_packed, bias, y, B, C, D, H, W, kh, dil, st);
-    if (kh == 5 && dil == 1) return launch_dw<5, 1, 4>(x, w_packed, bias, y, B, C, D, H, W, kd, st);
-    if (kh == 7 && dil == 3) return launch_dw<7, 3, 4>(x, w_packed, bias, y, B, C, D, H, W, kd, st);
-    return DLKA_ERR_UNSUPPORTED;
+    if (dwconv_smem_supported(C, kd, kh, kw, dd, dil, dil)) return dwconv_smem(x, w_packed, bias, y, B, C, D, H, W, kd, kh, dd, dil, st);
+    if (C / 4 <= 256 && kh == kw && dd == dil && (kd == kh || kd == 1)) {
+        if (kh == 5 && dil == 1) return launch_dw<5, 1, 4>(x, w_packed, bias, y, B, C, D, H, W, kd, st);
+        if (kh == 7 && dil == 3) return launch_dw<7, 3, 4>(x, w_packed, bias, y, B, C, D, H, W, kd, st);
+    }
+    const i64 total = (i64)B * D * H * W * (C / 4);
+    if (total <= 0) return DLKA_OK;
+    const int blocks = (int)(cdiv(total, 256) < 148 * 32 ? cdiv(total, 256) : 148 * 32);
+    DLKA_LAUNCH("dwconv3d_generic", st,
+                dwconv3d_generic_kernel<<<blocks, 256, 0, st>>>(x, w_packed, bias, y, B, C, D, H, W, kd, kh, kw, dd, dil, dil));
+    return DLKA_OK;
 }
 
 int deform_dwconv_cl(const float *x, const float *off, const float *mask, const float *w, const float *bias, float *y,

@@ -64,7 +64,7 @@ template <> struct DsVec<2> {
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int K, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R, int VW>
+template <int KD, int K, int LD, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R, int VW>
 __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
     dwconv_smem_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ wp, const float *__restrict__ bias,
                        float *__restrict__ y, int C, int D, int H, int W, int tiles_d, int tiles_h, int tiles_w)
@@ -74,14 +74,14 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
     constexpr int LPV = DS_CCH / VW;                          // lanes (vectors) per voxel
     constexpr int DS_THREADS = LPV * (DS_TW / DS_R) * DS_TH;
     static_assert(DS_TW % DS_R == 0 && DS_THREADS <= 1024, "tile shape");
-    constexpr int P = (K - 1) / 2;
+    constexpr int P = (K - 1) / 2, PD = (KD - 1) / 2;   // halo along h / w and along d
     constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;   // plane extent (lattice voxels)
     constexpr int PLANE_F4 = PH * PW * (DS_CCH / 4);         // float4 elements per plane (128 B per voxel)
-    constexpr int NPLANES = DS_TD + K - 1;
+    constexpr int NPLANES = DS_TD + KD - 1;
     extern __shared__ __align__(128) float4 smem4[];
     float4 *sP = smem4;                                      // [2][PH][PW][8] float4 (TMA destination, 128-byte aligned)
-    float4 *sW = sP + 2 * PLANE_F4;                          // [K^3][8] float4 : weights of this channel chunk
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sW + K * K * K * (DS_CCH / 4));   // one per plane buffer
+    float4 *sW = sP + 2 * PLANE_F4;                          // [KD*K*K][8] float4 : weights of this channel chunk
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sW + KD * K * K * (DS_CCH / 4));   // one per plane buffer
 
     const int tid = threadIdx.x;
     constexpr int WRUNS = DS_TW / DS_R;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
     const int td = bid;
     const int nchunks = C / DS_CCH;
     const int chunk = blockIdx.y % nchunks, phase = blockIdx.y / nchunks;
-    const int pw_ = phase % L, ph_ = (phase / L) % L, pd_ = phase / (L * L);
+    const int pw_ = phase % L, ph_ = (phase / L) % L, pd_ = phase / (L * L);   // pd_ < LD
     const int b = blockIdx.z;
     const int c0 = chunk * DS_CCH;
     const int zd0 = td * DS_TD, zh0 = th * DS_TH, zw0 = tw * DS_TW;   // lattice tile origin
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
         ptx::fence_barrier_init();
     }
     // weights of the chunk -> smem ([tap][C] packed layout in global: 128 contiguous bytes per tap)
-    for (int i = tid; i < K * K * K * (DS_CCH / 4); i += DS_THREADS) {
+    for (int i = tid; i < KD * K * K * (DS_CCH / 4); i += DS_THREADS) {
         const int tap = i >> 3, qq = i & 7;
         cp_async16(sW + i, wp + (i64)tap * C + c0 + qq * 4, true);
     }
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
         const uint32_t bar = bar0 + 8u * buf;
         ptx::mbar_arrive_expect_tx(bar, (uint32_t)(PLANE_F4 * sizeof(float4)));
         ptx::tma_load_5d(ptx::smem_u32(sP + buf * PLANE_F4), &tmap, bar, c0, pw_ + L * (zw0 - P), ph_ + L * (zh0 - P),
-                         pd_ + L * (zd0 - P + s), b);
+                         pd_ + LD * (zd0 - PD + s), b);
     };
 
     vec acc[DS_TD][DS_R];
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
 #pragma unroll
             for (int t = 0; t < DS_TD; ++t) {
                 const int i = s - t;
-                if (i < 0 || i >= K) continue;  // uniform across the CTA
+                if (i < 0 || i >= KD) continue;  // uniform across the CTA
                 const vec *wrow = reinterpret_cast<const vec *>(sW) + ((i * K + j) * K) * LPV + q;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
     if (hr < H) {
 #pragma unroll
         for (int t = 0; t < DS_TD; ++t) {
-            const int dr = pd_ + L * (zd0 + t);
+            const int dr = pd_ + LD * (zd0 + t);
             if (dr >= D) continue;
 #pragma unroll
             for (int r = 0; r < DS_R; ++r) {
@@ -179,14 +179,14 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
     }
 }
 
-template <int K, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R, int VW>
+template <int KD, int K, int LD, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R, int VW>
 int launch_ds(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, cudaStream_t st)
 {
     constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;
     constexpr int DS_THREADS = (DS_CCH / VW) * (DS_TW / DS_R) * DS_TH;
     static_assert(PW * L <= 256 && PH * L <= 256, "TMA box extent");
-    const size_t smem = ((size_t)K * K * K * 8 + 2 * (size_t)PH * PW * 8) * sizeof(float4) + 64;
-    auto kern = dwconv_smem_kernel<K, L, DS_TD, DS_TH, DS_TW, DS_R, VW>;
+    const size_t smem = ((size_t)KD * K * K * 8 + 2 * (size_t)PH * PW * 8) * sizeof(float4) + 64;
+    auto kern = dwconv_smem_kernel<KD, K, LD, L, DS_TD, DS_TH, DS_TW, DS_R, VW>;
     static thread_local bool configured = false;
     if (!configured) {
         DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -197,29 +197,36 @@ int launch_ds(const float *x, const float *wp, const float *bias, float *y, int 
     CUtensorMap tmap;
     if (!make_tmap_cl5(&tmap, x, B, C, D, H, W, DS_CCH, PW, PH, 1, L)) return DLKA_ERR_CUDA;
     // lattice extents of the largest phase
-    const int ld = (int)cdiv(D, L), lh = (int)cdiv(H, L), lw = (int)cdiv(W, L);
+    const int ld = (int)cdiv(D, LD), lh = (int)cdiv(H, L), lw = (int)cdiv(W, L);
     const int tiles_d = (int)cdiv(ld, DS_TD), tiles_h = (int)cdiv(lh, DS_TH), tiles_w = (int)cdiv(lw, DS_TW);
-    dim3 grid((unsigned)(tiles_d * tiles_h * tiles_w), (unsigned)(L * L * L * (C / DS_CCH)), (unsigned)B);
+    dim3 grid((unsigned)(tiles_d * tiles_h * tiles_w), (unsigned)(LD * L * L * (C / DS_CCH)), (unsigned)B);
     if (grid.y > 65535u || grid.z > 65535u) return DLKA_ERR_UNSUPPORTED;
-    DLKA_LAUNCH(K == 5 ? "dwconv3d_smem_k5" : "dwconv3d_smem_k7d3", st,
+    DLKA_LAUNCH(KD == 5 && K == 5 ? "dwconv3d_smem_k5" : KD == 7 ? "dwconv3d_smem_k7d3" : "dwconv3d_smem_aniso", st,
                 (kern<<<grid, DS_THREADS, smem, st>>>(tmap, wp, bias, y, C, D, H, W, tiles_d, tiles_h, tiles_w)));
     return DLKA_OK;
 }
 
 }  // namespace
 
-bool dwconv_smem_supported(int C, int kd, int kh, int kw, int dil)
+bool dwconv_smem_supported(int C, int kd, int kh, int kw, int dd, int dh, int dw)
 {
-    if (C % DS_CCH != 0) return false;
-    return (kd == 5 && kh == 5 && kw == 5 && dil == 1) || (kd == 7 && kh == 7 && kw == 7 && dil == 3);
+    if (C % DS_CCH != 0 || kh != kw || dh != dw) return false;
+    return (kd == 5 && kh == 5 && dd == 1 && dh == 1) || (kd == 7 && kh == 7 && dd == 3 && dh == 3) ||   // synapse (transformerblock.py:637-638)
+           (kd == 5 && kh == 7 && dd == 3 && dh == 3) || (kd == 3 && kh == 5 && dd == 1 && dh == 3) ||   // acdc dims 32/64, 128
+           (kd == 3 && kh == 3 && dd == 1 && dh == 1);                                                    // acdc dim 256 (acdc/transformerblock.py:214-236)
 }
 
 // wp: packed [taps][C] weights (pack_dw layout)
-int dwconv_smem(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, int k, int dil,
-                cudaStream_t st)
+int dwconv_smem(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, int kd, int k,
+                int dd, int dil, cudaStream_t st)
 {
-    if (k == 5 && dil == 1) return launch_ds<5, 1, DLKA_DS5_TD, DLKA_DS5_TH, DLKA_DS5_TW, DLKA_DS5_R, DLKA_DS5_VW>(x, wp, bias, y, B, C, D, H, W, st);
-    if (k == 7 && dil == 3) return launch_ds<7, 3, DLKA_DS7_TD, DLKA_DS7_TH, DLKA_DS7_TW, DLKA_DS7_R, DLKA_DS7_VW>(x, wp, bias, y, B, C, D, H, W, st);
+    if (kd == 5 && k == 5 && dd == 1 && dil == 1)
+        return launch_ds<5, 5, 1, 1, DLKA_DS5_TD, DLKA_DS5_TH, DLKA_DS5_TW, DLKA_DS5_R, DLKA_DS5_VW>(x, wp, bias, y, B, C, D, H, W, st);
+    if (kd == 7 && k == 7 && dd == 3 && dil == 3)
+        return launch_ds<7, 7, 3, 3, DLKA_DS7_TD, DLKA_DS7_TH, DLKA_DS7_TW, DLKA_DS7_R, DLKA_DS7_VW>(x, wp, bias, y, B, C, D, H, W, st);
+    if (kd == 5 && k == 7 && dd == 3 && dil == 3) return launch_ds<5, 7, 3, 3, 2, 15, 22, 11, 2>(x, wp, bias, y, B, C, D, H, W, st);
+    if (kd == 3 && k == 5 && dd == 1 && dil == 3) return launch_ds<3, 5, 1, 3, 4, 16, 16, 8, 2>(x, wp, bias, y, B, C, D, H, W, st);
+    if (kd == 3 && k == 3 && dd == 1 && dil == 1) return launch_ds<3, 3, 1, 1, 4, 16, 16, 8, 2>(x, wp, bias, y, B, C, D, H, W, st);
     return DLKA_ERR_UNSUPPORTED;
 }
 

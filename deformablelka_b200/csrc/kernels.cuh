@@ -67,13 +67,14 @@ int transpose_sc_to_cs(const float *in, float *out, int B, int C, i64 S, cudaStr
 
 // ---------------- depthwise (regular) conv, channels-last, "same" output extent, stride 1 ----------
 // w: PyTorch layout [C][1][kd][kh][kw]; bias [C] or null.  pad = dil*(k-1)/2 on each axis.
+// dd / dil: dilation along d / along h and w (the ACDC variant of the block is anisotropic, acdc/transformerblock.py:214-236)
 int dwconv_cl(const float *x, const float *w, const float *bias, float *y, int B, int C, int D, int H, int W, int kd,
-              int kh, int kw, int dil, float *w_packed /*[K][C]*/, cudaStream_t st);
+              int kh, int kw, int dd, int dil, float *w_packed /*[K][C]*/, cudaStream_t st);
 
-// shared-memory plane-streaming variant (C % 32 == 0; 5^3 dil 1 and 7^3 dil 3) -- dwconv_smem.cu
-bool dwconv_smem_supported(int C, int kd, int kh, int kw, int dil);
-int dwconv_smem(const float *x, const float *w_packed, const float *bias, float *y, int B, int C, int D, int H, int W, int k,
-                int dil, cudaStream_t st);
+// shared-memory plane-streaming variant (C % 32 == 0; the five stencil shapes of the synapse / acdc blocks) -- dwconv_smem.cu
+bool dwconv_smem_supported(int C, int kd, int kh, int kw, int dd, int dh, int dw);
+int dwconv_smem(const float *x, const float *w_packed, const float *bias, float *y, int B, int C, int D, int H, int W, int kd, int k,
+                int dd, int dil, cudaStream_t st);
 
 // ---------------- depthwise deformable conv (groups == C == Co), channels-last ----------------------
 // w: [C][1][taps] PyTorch layout; Off [M][dg*ndim*K]; Mask optional; bias optional.

@@ -21,6 +21,9 @@ def _block3d_params(lka: "LKA3d_deform", attn=None) -> dict:
     if attn is not None:
         p.update({"proj_1_weight": attn.proj_1.weight, "proj_1_bias": attn.proj_1.bias,
                   "proj_2_weight": attn.proj_2.weight, "proj_2_bias": attn.proj_2.bias})
+    geom = getattr(lka, "dw_geom", None)
+    if geom is not None:
+        p["dw_geom"] = geom
     return p
 
 

@@ -9,7 +9,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import Block2dParams, Block3dParams, Workspace, check, dptr, lib, stream_ptr
+from ._lib import Block2dParams, Block3dParams, DwGeom3d, Workspace, check, dptr, lib, stream_ptr
 
 
 def _triple(v):
@@ -215,6 +215,14 @@ def _params_struct(cls, tensors: dict):
     s = cls()
     for name, _ in cls._fields_:
         t = tensors.get(name)
+        if name == "dw_geom":   # ((k0), (dil0), (k1), (dil1)) or None = the synapse network's shapes
+            if t is not None:
+                g = DwGeom3d()
+                for dst, src in zip((g.conv0_k, g.conv0_dil, g.conv_spatial_k, g.conv_spatial_dil), t):
+                    dst[0], dst[1], dst[2] = (int(v) for v in src)
+                keep.append(g)
+                s.dw_geom = ctypes.pointer(g)
+            continue
         if t is None:
             setattr(s, name, None)
             continue

@@ -155,6 +155,18 @@ DLKA_API int dlka_deform_conv_pack2d_forward(const float *input, const float *of
  *      and  LKA_Attention3d_deform.forward  (same file :664-673).
  * The attention parameters (proj_1 / proj_2) are ignored by dlka_lka3d_deform_forward.
  * ------------------------------------------------------------------------------------------ */
+/* Depthwise stencil shapes of the block.  NULL in dlkaBlock3dParams.dw_geom selects the synapse network's
+ * (transformerblock.py:637-638: 5^3 dil 1, 7^3 dil 3).  The ACDC network uses the same block with shapes chosen per
+ * channel count (3D/d_lka_former/network_architecture/acdc/transformerblock.py:214-236):
+ *   dim 32, 64: conv0 5^3;  conv_spatial (5,7,7) dil (3,3,3)      dim 128: conv0 5^3;  conv_spatial (3,5,5) dil (1,3,3)
+ *   dim 256:    conv0 3^3;  conv_spatial 3^3 dil 1
+ * Axes are (D1, D2, D3) as nn.Conv3d sees them; kernels are odd, padding is dil*(k-1)/2 ("same"), and the library
+ * requires k[1]==k[2], dil[1]==dil[2] (true for every shape the reference uses).                                  */
+typedef struct dlkaDwGeom3d {
+    int conv0_k[3], conv0_dil[3];
+    int conv_spatial_k[3], conv_spatial_dil[3];
+} dlkaDwGeom3d;
+
 typedef struct dlkaBlock3dParams {
     const float *proj_1_weight, *proj_1_bias;             /* [C,C,1,1,1], [C]   transformerblock.py:659 */
     const float *conv0_weight, *conv0_bias;               /* [C,1,5,5,5], [C]   :637 (pad 2)            */
@@ -163,6 +175,7 @@ typedef struct dlkaBlock3dParams {
     const float *deform_weight, *deform_bias;             /* [C,C,3,3,3], [C]   synapse/deform_conv.py:37-39 */
     const float *conv1_weight, *conv1_bias;               /* [C,C,1,1,1], [C]   :641                    */
     const float *proj_2_weight, *proj_2_bias;             /* [C,C,1,1,1], [C]   :662                    */
+    const dlkaDwGeom3d *dw_geom;                          /* host pointer; NULL = synapse shapes above  */
 } dlkaBlock3dParams;
 
 /* x, y: [B, C, D1, D2, D3] (NCDHW as nn.Conv3d sees it). */

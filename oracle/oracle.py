@@ -358,6 +358,37 @@ class LKA_Attention3d_deform(nn.Module):
         return x.reshape(B, C, H * W * D).permute(0, 2, 1)
 
 
+class LKA3d_deform_ACDC(LKA3d_deform):
+    """Restates the ACDC variant (acdc/transformerblock.py:210-253): same forward, depthwise stencil shapes per dim."""
+
+    def __init__(self, dim):
+        nn.Module.__init__(self)
+        if dim == 32 or dim == 64:
+            kernel_dwd, dilation_dwd, padding_dwd, kernel_dw, padding_dw = (5, 7, 7), (3, 3, 3), (6, 9, 9), 5, 2
+        elif dim == 128:
+            kernel_dwd, dilation_dwd, padding_dwd, kernel_dw, padding_dw = (3, 5, 5), (1, 3, 3), (1, 6, 6), 5, 2
+        elif dim == 256:
+            kernel_dwd, dilation_dwd, padding_dwd, kernel_dw, padding_dw = 3, 1, 1, 3, 1
+        else:
+            raise ValueError("Unknown dim: {}".format(dim))
+        self.conv0 = nn.Conv3d(dim, dim, kernel_size=kernel_dw, padding=padding_dw, groups=dim)
+        self.conv_spatial = nn.Conv3d(dim, dim, kernel_size=kernel_dwd, stride=1, padding=padding_dwd, groups=dim,
+                                      dilation=dilation_dwd)
+        self.conv1 = nn.Conv3d(dim, dim, 1)
+        self.deform_conv = DeformConvPack3D(in_channels=dim, out_channels=dim, kernel_size=(3, 3, 3), stride=1, padding=1)
+
+
+class LKA_Attention3d_deform_ACDC(LKA_Attention3d_deform):
+    """Restates the ACDC attention wrapper (acdc/transformerblock.py:255-275)."""
+
+    def __init__(self, d_model):
+        nn.Module.__init__(self)
+        self.proj_1 = nn.Conv3d(d_model, d_model, 1)
+        self.activation = nn.GELU()
+        self.spatial_gating_unit = LKA3d_deform_ACDC(d_model)
+        self.proj_2 = nn.Conv3d(d_model, d_model, 1)
+
+
 def randomize_offsets_(module: nn.Module, std: float = 0.05, bias_range: float = 1.0, seed: int = 0) -> None:
     """re-initialise the zero-initialised 3D ``conv_offset`` so offsets are non-trivial."""
     g = torch.Generator().manual_seed(seed)

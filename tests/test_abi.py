@@ -85,6 +85,17 @@ def test_state_dict_keys_match_reference_and_oracle(oracle):
     assert set(o3.state_dict().keys()) == exp
     o3.load_state_dict(m3.state_dict())
     assert (m3.spatial_gating_unit.deform_conv.conv_offset.weight == 0).all()  # zero-init, deform_conv.py:89-91
+    # ACDC variant (row N4): same keys, stencil shapes per dim (acdc/transformerblock.py:214-236)
+    from deformablelka_b200 import acdc
+    for dim, k0, k1 in ((32, (5, 5, 5), (5, 7, 7)), (64, (5, 5, 5), (5, 7, 7)), (128, (5, 5, 5), (3, 5, 5)), (256, (3, 3, 3), (3, 3, 3))):
+        ma, oa = acdc.LKA_Attention3d_deform(dim), oracle.LKA_Attention3d_deform_ACDC(dim)
+        assert set(ma.state_dict().keys()) == exp
+        assert {k: tuple(v.shape) for k, v in ma.state_dict().items()} == {k: tuple(v.shape) for k, v in oa.state_dict().items()}
+        assert tuple(ma.spatial_gating_unit.conv0.weight.shape[2:]) == k0
+        assert tuple(ma.spatial_gating_unit.conv_spatial.weight.shape[2:]) == k1
+        assert ma.spatial_gating_unit.conv_spatial.padding == oa.spatial_gating_unit.conv_spatial.padding
+    with pytest.raises(ValueError):
+        acdc.LKA3d_deform(96)   # "Unknown dim", acdc/transformerblock.py:237
 
 
 def test_host_argument_checks_mirror_reference():

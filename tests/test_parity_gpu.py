@@ -244,6 +244,41 @@ def test_block3d_vs_oracle(dl, oracle, C, dims, std, br, math):
     assert rel_err(got_l, ref_l) < TOL
 
 
+# ACDC variant of the block (row N4): stencil shapes per channel count, acdc/transformerblock.py:214-236.  The volumes are
+# ragged against every tile shape (lattice tiles, bricks) and thinner than the (5,7,7)-dil-3 reach along the first axis.
+@pytest.mark.parametrize("C,dims", [(32, (4, 13, 11)), (64, (6, 9, 10)), (128, (3, 8, 9)), (256, (2, 5, 5)), (32, (16, 20, 20))])
+def test_block3d_acdc_vs_oracle(dl, oracle, C, dims, math):
+    from deformablelka_b200 import acdc
+    torch.manual_seed(12)
+    H, W, D = dims
+    B = 2
+    ref_m = oracle.LKA_Attention3d_deform_ACDC(C).eval()
+    oracle.randomize_offsets_(ref_m, std=0.05, bias_range=1.0)
+    m = acdc.LKA_Attention3d_deform(C)
+    m.load_state_dict(ref_m.state_dict())
+    m = m.to(DEV)
+    x = torch.randn(B, H * W * D, C)
+    with torch.no_grad():
+        ref = ref_m(x, B, C, H, W, D)
+        got = m(x.to(DEV), B, C, H, W, D)
+        xv = torch.randn(B, C, H, W, D)
+        ref_l = ref_m.spatial_gating_unit(xv)
+        got_l = m.spatial_gating_unit(xv.to(DEV))
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < TOL
+    assert rel_err(got_l, ref_l) < TOL
+
+
+def test_block3d_unsupported_stencil_is_loud(dl):
+    """A stencil shape the library has no kernel for (k along axis 2 != axis 3) is refused, not approximated."""
+    from deformablelka_b200 import acdc
+    m = acdc.LKA_Attention3d_deform(32).to(DEV)
+    m.spatial_gating_unit.dw_geom = ((5, 5, 5), (1, 1, 1), (5, 7, 5), (3, 3, 3))
+    x = torch.randn(1, 4 * 4 * 4, 32, device=DEV)
+    with pytest.raises(RuntimeError):
+        m(x, 1, 32, 4, 4, 4)
+
+
 # ----------------------------------------------------------------------------- properties at larger size
 def test_block3d_batch_shard_consistency_and_identity(dl, oracle, math):
     """Size-independent properties on a mid-size volume: (a) B=2 equals two B=1 runs (the data-parallel
