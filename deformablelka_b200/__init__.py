@@ -10,7 +10,8 @@ from .deform_conv3d import DeformConv as DeformConv3d, DeformConvFunction, Defor
 from .deformable_LKA import DeformConv, DeformConv2d, deformable_LKA, deformable_LKA_Attention  # noqa: F401
 from .lka3d import LKA3d_deform, LKA_Attention3d_deform  # noqa: F401
 from . import acdc  # noqa: F401  (ACDC variant of the 3D block: acdc.LKA3d_deform, acdc.LKA_Attention3d_deform)
-from .blocks import DWConvLKA, Mlp, TransformerBlock_3D_single_deform_LKA, deformableLKABlock  # noqa: F401
+from .blocks import (DWConvLKA, FinalPatchExpand_X4, Mlp, MyDecoderLayer, PatchExpand,  # noqa: F401
+                     TransformerBlock_3D_single_deform_LKA, deformableLKABlock)
 
 __all__ = [
     "ops", "DeformConv", "DeformConv2d", "deformable_LKA", "deformable_LKA_Attention",

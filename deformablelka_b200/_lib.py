@@ -112,6 +112,14 @@ def _load() -> ctypes.CDLL:
     lib.dlka_lka_transformer3d_block_workspace_bytes.argtypes = [I] * 5
     lib.dlka_lka_transformer3d_block_forward.restype = c_int
     lib.dlka_lka_transformer3d_block_forward.argtypes = [POINTER(Transformer3dParams), V, V] + [I] * 6 + [V, c_size_t, V]
+    lib.dlka_linear_tokens_workspace_bytes.restype = c_size_t
+    lib.dlka_linear_tokens_workspace_bytes.argtypes = [I, I]
+    lib.dlka_linear_tokens_forward.restype = c_int
+    lib.dlka_linear_tokens_forward.argtypes = [V] * 5 + [ctypes.c_longlong, I, I, I, V, c_size_t, V]
+    lib.dlka_patch_expand2d_workspace_bytes.restype = c_size_t
+    lib.dlka_patch_expand2d_workspace_bytes.argtypes = [I] * 5
+    lib.dlka_patch_expand2d_forward.restype = c_int
+    lib.dlka_patch_expand2d_forward.argtypes = [V] * 4 + [ctypes.c_float, V] + [I] * 6 + [V, c_size_t, V]
     lib.dlka_host_pipe_create.restype = c_int
     lib.dlka_host_pipe_create.argtypes = [POINTER(c_void_p), c_int]
     for name in ("dlka_host_pipe_destroy", "dlka_host_pipe_wait"):

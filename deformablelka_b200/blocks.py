@@ -72,6 +72,84 @@ class deformableLKABlock(nn.Module):
                                                   self.mlp.hidden_features, self.norm1.eps, self.norm2.eps)
 
 
+class PatchExpand(nn.Module):
+    """2D/networks/MaxViT_deform_LKA.py:488-513 -- Linear(dim, 2*dim, bias=False) -> pixel shuffle x2 -> LayerNorm(dim/2)."""
+
+    def __init__(self, input_resolution, dim, dim_scale=2, norm_layer=nn.LayerNorm):
+        super().__init__()
+        if dim_scale != 2:
+            raise NotImplementedError("PatchExpand: only dim_scale=2 (the only value the reference constructs, :574)")
+        self.input_resolution = input_resolution
+        self.dim = dim
+        self.expand = nn.Linear(dim, 2 * dim, bias=False)
+        self.norm = norm_layer(dim // dim_scale)
+
+    def forward(self, x):
+        H, W = self.input_resolution
+        return ops.patch_expand2d_forward(x, self.expand.weight, self.norm.weight, self.norm.bias, self.norm.eps, H, W, 2)
+
+
+class FinalPatchExpand_X4(nn.Module):
+    """:516-545 -- Linear(dim, 16*dim, bias=False) -> pixel shuffle x4 -> LayerNorm(dim)."""
+
+    def __init__(self, input_resolution, dim, dim_scale=4, norm_layer=nn.LayerNorm):
+        super().__init__()
+        if dim_scale != 4:
+            raise NotImplementedError("FinalPatchExpand_X4: dim_scale must be 4")
+        self.input_resolution = input_resolution
+        self.dim = dim
+        self.dim_scale = dim_scale
+        self.expand = nn.Linear(dim, 16 * dim, bias=False)
+        self.output_dim = dim
+        self.norm = norm_layer(self.output_dim)
+
+    def forward(self, x):
+        H, W = self.input_resolution
+        return ops.patch_expand2d_forward(x, self.expand.weight, self.norm.weight, self.norm.bias, self.norm.eps, H, W, 4)
+
+
+class MyDecoderLayer(nn.Module):
+    """One 2D decoder stage (:548-620): x1_linear + skip add, two deformableLKABlocks, patch expansion, and on the last stage
+    the 1x1 class head.  Same constructor arguments and parameter names as the reference; five library calls."""
+
+    def __init__(self, input_size, in_out_chan, head_count, token_mlp_mode, n_class=9, norm_layer=nn.LayerNorm, is_last=False):
+        super().__init__()
+        out_dim, x1_dim = in_out_chan[1], in_out_chan[4]
+        self.x1_linear = nn.Linear(x1_dim, out_dim)
+        if not is_last:
+            self.layer_up = PatchExpand(input_resolution=input_size, dim=out_dim, dim_scale=2, norm_layer=norm_layer)
+            self.last_layer = None
+        else:
+            self.layer_up = FinalPatchExpand_X4(input_resolution=input_size, dim=out_dim, dim_scale=4, norm_layer=norm_layer)
+            self.last_layer = nn.Conv2d(out_dim, n_class, 1)
+        self.layer_lka_1 = deformableLKABlock(dim=out_dim)
+        self.layer_lka_2 = deformableLKABlock(dim=out_dim)
+        for m in self.modules():   # init_weights, :585-598
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.Conv2d):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
+    def forward(self, x1, x2=None):
+        if x2 is None:
+            return self.layer_up(x1)
+        b, h, w, c = x2.shape
+        cat_linear_x = ops.linear_tokens_forward(x1, self.x1_linear.weight, self.x1_linear.bias, add=x2.reshape(b, -1, c))
+        t = self.layer_lka_2(self.layer_lka_1(cat_linear_x, h, w), h, w)
+        if self.last_layer is None:
+            return self.layer_up(t)
+        up = self.layer_up(t)                                     # [b, 16*h*w, out_dim] tokens = NHWC
+        logits = ops.linear_tokens_forward(up, self.last_layer.weight.flatten(1), self.last_layer.bias)
+        return logits.view(b, 4 * h, 4 * w, -1).permute(0, 3, 1, 2).contiguous()   # NCHW like nn.Conv2d's output
+
+
 class _ConvNoBias3d(nn.Module):
     """monai ``Convolution`` keeps its conv under ``.conv`` -> parameter key ``<name>.conv.weight``."""
 

@@ -154,3 +154,62 @@ int dlka_lka_transformer3d_block_forward(const dlkaTransformer3dParams *P, const
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Rest of row N3 (2D decoder, 2D/networks/MaxViT_deform_LKA.py:488-620): the token Linear of MyDecoderLayer (x1_linear, with
+// the skip tensor added in the epilogue, :604-607) and PatchExpand / FinalPatchExpand_X4 (Linear without bias -> pixel shuffle
+// -> LayerNorm, :488-545) as one call each.  The Linear runs on the tcgen05 dense kernel, the shuffle is an index remap
+// inside the LayerNorm kernel: no rearranged copy is ever materialised.
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+size_t dlka_linear_tokens_workspace_bytes(int K, int N)
+{
+    if (K <= 0 || N <= 0) return 0;
+    return dense_scratch_floats(N, K) * sizeof(float) + 512;
+}
+
+// y[M,N] = x[M,K] @ weight[N,K]^T (+ bias) (+ add[M,N])
+int dlka_linear_tokens_forward(const float *x, const float *weight, const float *bias, const float *add, float *y, long long M, int K,
+                               int N, int math, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!x || !weight || !y) return DLKA_ERR_INVALID_ARGUMENT;
+    if (M <= 0 || K <= 0 || N <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    if (K % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    DLKA_TRY(device_ok());
+    Arena ar(workspace, workspace_bytes);
+    float *wp = ar.take<float>(dense_scratch_floats(N, K));
+    if (!ar.ok()) return DLKA_ERR_WORKSPACE;
+    return dense_cl(x, K, (i64)M, K, N, weight, bias, add ? EPI_ADD : EPI_NONE, add, N, y, N, math, wp, (cudaStream_t)stream);
+}
+
+size_t dlka_patch_expand2d_workspace_bytes(int B, int H, int W, int dim, int scale)
+{
+    if (B <= 0 || H <= 0 || W <= 0 || dim <= 0 || (scale != 2 && scale != 4)) return 0;
+    const size_t M = (size_t)B * H * W, F = scale == 2 ? 2 * (size_t)dim : 16 * (size_t)dim;
+    return M * F * sizeof(float) + dense_scratch_floats((int)F, dim) * sizeof(float) + 1024;
+}
+
+// scale 2: PatchExpand.forward          x [B, H*W, dim] -> y [B, 4*H*W, dim/2]     (expand_weight [2*dim, dim], norm over dim/2)
+// scale 4: FinalPatchExpand_X4.forward  x [B, H*W, dim] -> y [B, 16*H*W, dim]      (expand_weight [16*dim, dim], norm over dim)
+int dlka_patch_expand2d_forward(const float *x, const float *expand_weight, const float *norm_weight, const float *norm_bias, float eps,
+                                float *y, int B, int H, int W, int dim, int scale, int math, void *workspace, size_t workspace_bytes,
+                                void *stream)
+{
+    if (!x || !expand_weight || !norm_weight || !norm_bias || !y) return DLKA_ERR_INVALID_ARGUMENT;
+    if (B <= 0 || H <= 0 || W <= 0 || dim <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    if (scale != 2 && scale != 4) return DLKA_ERR_UNSUPPORTED;
+    const int cg = scale == 2 ? dim / 2 : dim, F = scale * scale * cg;
+    if (dim % 8 != 0) return DLKA_ERR_UNSUPPORTED;
+    DLKA_TRY(device_ok());
+    cudaStream_t st = (cudaStream_t)stream;
+    const i64 M = (i64)B * H * W;
+    Arena ar(workspace, workspace_bytes);
+    float *e = ar.take<float>((size_t)M * F);
+    float *wp = ar.take<float>(dense_scratch_floats(F, dim));
+    if (!ar.ok()) return DLKA_ERR_WORKSPACE;
+    DLKA_TRY(dense_cl(x, dim, M, dim, F, expand_weight, nullptr, EPI_NONE, nullptr, 0, e, F, math, wp, st));
+    return layernorm_shuffle_cl(e, norm_weight, norm_bias, y, B, H, W, scale, cg, eps, st);
+}
+
+}  // extern "C"

@@ -84,6 +84,9 @@ int deform_dwconv_cl(const float *x, const float *off, const float *mask, const 
 // ---------------- layers around the attention block (row N1) -- norm_mlp.cu ----------------
 int layernorm_cl(const float *x, const float *pos, i64 pos_rows, const float *gamma, const float *beta, float *y, i64 M, int C,
                  float eps, cudaStream_t st);
+// LayerNorm over C of [B*H*W][P*P][C] rows, written pixel-shuffled to tokens [B][(H*P)*(W*P)][C] (PatchExpand, MaxViT_deform_LKA.py:488-545)
+int layernorm_shuffle_cl(const float *x, const float *gamma, const float *beta, float *y, int B, int H, int W, int P, int C, float eps,
+                         cudaStream_t st);
 int scale_residual_cl(const float *x, const float *pos, i64 pos_rows, const float *scale, const float *y, float *out, i64 M, int C,
                       cudaStream_t st);
 int dwconv2d3_cl(const float *x, const float *w, const float *bias, float *y, int B, int C, int H, int W, int gelu, float *w_packed,

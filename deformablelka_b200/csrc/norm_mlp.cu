@@ -12,13 +12,26 @@ namespace {
 // one warp per token row; C <= 32 * 4 * LN_MAXV
 constexpr int LN_MAXV = 4;
 
+// shuffle (P > 0): the input rows are [B*H*W][P*P] groups of C channels (output of PatchExpand's Linear) and group (p1, p2)
+// of token (b, h, w) is written to token (b, h*P + p1, w*P + p2) -- einops "b h w (p1 p2 c) -> b (h p1) (w p2) c"
+// (2D/networks/MaxViT_deform_LKA.py:510,540) fused into the LayerNorm that follows it.
 __global__ void __launch_bounds__(256) layernorm_cl_kernel(const float *__restrict__ x, const float *__restrict__ pos,
                                                            const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                           float *__restrict__ y, i64 M, int C, i64 pos_rows, float eps)
+                                                           float *__restrict__ y, i64 M, int C, i64 pos_rows, float eps, int P, int H,
+                                                           int W)
 {
     const int lane = threadIdx.x & 31;
     const i64 row = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
+    i64 orow = row;
+    if (P > 0) {
+        const int g = (int)(row % (P * P));
+        i64 t = row / (P * P);
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H);
+        const i64 b = t / H;
+        orow = (b * (H * P) + h * P + g / P) * (i64)(W * P) + w * P + g % P;
+    }
     const float *xr = x + row * C;
     const float *pr = pos ? pos + (row % pos_rows) * C : nullptr;
     float4 v[LN_MAXV];
@@ -48,7 +61,7 @@ __global__ void __launch_bounds__(256) layernorm_cl_kernel(const float *__restri
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq / (float)C + eps);  // biased variance, as torch.nn.LayerNorm
-    float *yr = y + row * C;
+    float *yr = y + orow * C;
 #pragma unroll
     for (int i = 0; i < LN_MAXV; ++i) {
         const int c = (i * 32 + lane) * 4;
@@ -148,7 +161,20 @@ int layernorm_cl(const float *x, const float *pos, i64 pos_rows, const float *ga
     const int rows_per_block = 8;
     DLKA_LAUNCH("layernorm_cl", st,
                 layernorm_cl_kernel<<<(unsigned)cdiv(M, rows_per_block), rows_per_block * 32, 0, st>>>(x, pos, gamma, beta, y, M, C,
-                                                                                                       pos_rows > 0 ? pos_rows : 1, eps));
+                                                                                                       pos_rows > 0 ? pos_rows : 1, eps, 0, 1, 1));
+    return DLKA_OK;
+}
+
+int layernorm_shuffle_cl(const float *x, const float *gamma, const float *beta, float *y, int B, int H, int W, int P, int C, float eps,
+                         cudaStream_t st)
+{
+    if (C % 4 != 0 || C > 32 * 4 * LN_MAXV || P < 1) return DLKA_ERR_UNSUPPORTED;
+    const i64 M = (i64)B * H * W * P * P;
+    if (M <= 0) return DLKA_OK;
+    const int rows_per_block = 8;
+    DLKA_LAUNCH("layernorm_shuffle_cl", st,
+                layernorm_cl_kernel<<<(unsigned)cdiv(M, rows_per_block), rows_per_block * 32, 0, st>>>(x, nullptr, gamma, beta, y, M, C, 1,
+                                                                                                       eps, P, H, W));
     return DLKA_OK;
 }
 

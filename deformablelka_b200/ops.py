@@ -456,3 +456,45 @@ def deformable_lka_attention2d_forward(params: dict, x: torch.Tensor, math=None)
                                                          ws.data_ptr(), ws.numel(), stream_ptr(x.device))
     check(st, "dlka_deformable_lka_attention2d_forward")
     return y
+
+
+def linear_tokens_forward(x: torch.Tensor, weight: torch.Tensor, bias=None, add=None, math=None) -> torch.Tensor:
+    """nn.Linear on tokens [..., K] -> [..., N], optionally + add (MyDecoderLayer.x1_linear and its skip add,
+    2D/networks/MaxViT_deform_LKA.py:604-607)."""
+    if x.shape[-1] != weight.shape[1]:
+        raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({tuple(x.shape)} and {tuple(weight.t().shape)})")
+    x = x.contiguous()
+    K, N = weight.shape[1], weight.shape[0]
+    M = x.numel() // K
+    y = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32)
+    w = weight.detach().contiguous()
+    b = bias.detach().contiguous() if bias is not None else None
+    if add is not None:
+        add = add.contiguous()
+        if add.numel() != M * N:
+            raise RuntimeError(f"skip tensor of {add.numel()} elements does not match the [{M}, {N}] output")
+    ws = Workspace.get(x.device, lib.dlka_linear_tokens_workspace_bytes(K, N))
+    with torch.cuda.device(x.device):
+        st = lib.dlka_linear_tokens_forward(dptr(x, "x"), dptr(w, "weight"), dptr(b) if b is not None else None,
+                                            dptr(add) if add is not None else None, dptr(y), M, K, N, _math(math),
+                                            ws.data_ptr(), ws.numel(), stream_ptr(x.device))
+    check(st, "dlka_linear_tokens_forward")
+    return y
+
+
+def patch_expand2d_forward(x: torch.Tensor, expand_weight, norm_weight, norm_bias, eps: float, H: int, W: int, scale: int,
+                           math=None) -> torch.Tensor:
+    """PatchExpand.forward (scale 2) / FinalPatchExpand_X4.forward (scale 4) on tokens [B, H*W, dim]
+    (2D/networks/MaxViT_deform_LKA.py:488-545)."""
+    B, L, dim = x.shape
+    assert L == H * W, "input feature has wrong size"   # MaxViT_deform_LKA.py:506,536
+    x = x.contiguous()
+    cg = dim // 2 if scale == 2 else dim
+    y = torch.empty(B, scale * scale * H * W, cg, device=x.device, dtype=torch.float32)
+    w, g, b = (t.detach().contiguous() for t in (expand_weight, norm_weight, norm_bias))
+    ws = Workspace.get(x.device, lib.dlka_patch_expand2d_workspace_bytes(B, H, W, dim, scale))
+    with torch.cuda.device(x.device):
+        st = lib.dlka_patch_expand2d_forward(dptr(x, "x"), dptr(w, "expand.weight"), dptr(g), dptr(b), float(eps), dptr(y),
+                                             B, H, W, dim, scale, _math(math), ws.data_ptr(), ws.numel(), stream_ptr(x.device))
+    check(st, "dlka_patch_expand2d_forward")
+    return y

@@ -296,6 +296,20 @@ DLKA_API int dlka_lka_transformer3d_block_forward(const dlkaTransformer3dParams 
                                          int B, int C, int D1, int D2, int D3, int math,
                                          void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * 2D decoder glue (rest of row N3): 2D/networks/MaxViT_deform_LKA.py
+ *   dlka_linear_tokens_forward     MyDecoderLayer.x1_linear + the skip add        (:604-607)   y = x W^T + b (+ add)
+ *   dlka_patch_expand2d_forward    PatchExpand.forward (scale 2, :488-513) / FinalPatchExpand_X4.forward (scale 4, :516-545):
+ *                                  Linear without bias -> "b h w (p1 p2 c) -> b (h p1) (w p2) c" -> LayerNorm, no rearranged copy
+ * ------------------------------------------------------------------------------------------ */
+DLKA_API size_t dlka_linear_tokens_workspace_bytes(int K, int N);
+DLKA_API int dlka_linear_tokens_forward(const float *x, const float *weight, const float *bias, const float *add, float *y,
+                               long long M, int K, int N, int math, void *workspace, size_t workspace_bytes, void *stream);
+DLKA_API size_t dlka_patch_expand2d_workspace_bytes(int B, int H, int W, int dim, int scale);
+DLKA_API int dlka_patch_expand2d_forward(const float *x, const float *expand_weight, const float *norm_weight, const float *norm_bias,
+                                float eps, float *y, int B, int H, int W, int dim, int scale, int math,
+                                void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

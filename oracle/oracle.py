@@ -389,6 +389,75 @@ class LKA_Attention3d_deform_ACDC(LKA_Attention3d_deform):
         self.proj_2 = nn.Conv3d(d_model, d_model, 1)
 
 
+class PatchExpand(nn.Module):
+    """Restates PatchExpand (2D/networks/MaxViT_deform_LKA.py:488-513); the einops rearrange is spelled out with view/permute."""
+
+    def __init__(self, input_resolution, dim, dim_scale=2, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.input_resolution, self.dim = input_resolution, dim
+        self.expand = nn.Linear(dim, 2 * dim, bias=False) if dim_scale == 2 else nn.Identity()
+        self.norm = norm_layer(dim // dim_scale)
+
+    @staticmethod
+    def _shuffle(x, B, H, W, p, c):   # "b h w (p1 p2 c) -> b (h p1) (w p2) c"
+        return x.view(B, H, W, p, p, c).permute(0, 1, 3, 2, 4, 5).reshape(B, H * p, W * p, c)
+
+    def forward(self, x):
+        H, W = self.input_resolution
+        x = self.expand(x)
+        B, L, C = x.shape
+        assert L == H * W, "input feature has wrong size"
+        x = self._shuffle(x, B, H, W, 2, C // 4).reshape(B, -1, C // 4)
+        return self.norm(x.clone())
+
+
+class FinalPatchExpand_X4(nn.Module):
+    """Restates FinalPatchExpand_X4 (:516-545)."""
+
+    def __init__(self, input_resolution, dim, dim_scale=4, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.input_resolution, self.dim, self.dim_scale = input_resolution, dim, dim_scale
+        self.expand = nn.Linear(dim, 16 * dim, bias=False)
+        self.output_dim = dim
+        self.norm = norm_layer(self.output_dim)
+
+    def forward(self, x):
+        H, W = self.input_resolution
+        x = self.expand(x)
+        B, L, C = x.shape
+        assert L == H * W, "input feature has wrong size"
+        x = PatchExpand._shuffle(x, B, H, W, self.dim_scale, C // (self.dim_scale ** 2)).reshape(B, -1, self.output_dim)
+        return self.norm(x.clone())
+
+
+class MyDecoderLayer(nn.Module):
+    """Restates MyDecoderLayer (:548-620) from the oracle's own blocks."""
+
+    def __init__(self, input_size, in_out_chan, head_count, token_mlp_mode, n_class=9, norm_layer=nn.LayerNorm, is_last=False):
+        super().__init__()
+        out_dim, x1_dim = in_out_chan[1], in_out_chan[4]
+        self.x1_linear = nn.Linear(x1_dim, out_dim)
+        if not is_last:
+            self.layer_up = PatchExpand(input_resolution=input_size, dim=out_dim, dim_scale=2, norm_layer=norm_layer)
+            self.last_layer = None
+        else:
+            self.layer_up = FinalPatchExpand_X4(input_resolution=input_size, dim=out_dim, dim_scale=4, norm_layer=norm_layer)
+            self.last_layer = nn.Conv2d(out_dim, n_class, 1)
+        self.layer_lka_1 = deformableLKABlock(dim=out_dim)
+        self.layer_lka_2 = deformableLKABlock(dim=out_dim)
+
+    def forward(self, x1, x2=None):
+        if x2 is None:
+            return self.layer_up(x1)
+        b, h, w, c = x2.shape
+        x2 = x2.view(b, -1, c)
+        cat_linear_x = self.x1_linear(x1) + x2
+        t = self.layer_lka_2(self.layer_lka_1(cat_linear_x, h, w), h, w)
+        if self.last_layer:
+            return self.last_layer(self.layer_up(t).view(b, 4 * h, 4 * w, -1).permute(0, 3, 1, 2))
+        return self.layer_up(t)
+
+
 def randomize_offsets_(module: nn.Module, std: float = 0.05, bias_range: float = 1.0, seed: int = 0) -> None:
     """re-initialise the zero-initialised 3D ``conv_offset`` so offsets are non-trivial."""
     g = torch.Generator().manual_seed(seed)

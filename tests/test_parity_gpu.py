@@ -415,6 +415,51 @@ def test_lka_block2d_vs_oracle(dl, oracle, C, H, W, scale, math):
     assert rel_err(got, ref) < TOL
 
 
+# ----------------------------------------------------------------------------- rest of row N3: the 2D decoder stage
+@pytest.mark.parametrize("dim,H,W,scale", [(96, 7, 7, 2), (192, 5, 6, 2), (768, 3, 2, 2), (96, 6, 5, 4), (32, 4, 4, 4)])
+def test_patch_expand2d_vs_oracle(dl, oracle, dim, H, W, scale, math):
+    torch.manual_seed(20)
+    ref_m = (oracle.PatchExpand((H, W), dim) if scale == 2 else oracle.FinalPatchExpand_X4((H, W), dim)).eval()
+    with torch.no_grad():
+        ref_m.norm.weight.uniform_(0.5, 1.5); ref_m.norm.bias.normal_(0, 0.2)
+    m = dl.PatchExpand((H, W), dim) if scale == 2 else dl.FinalPatchExpand_X4((H, W), dim)
+    assert sorted(m.state_dict().keys()) == sorted(ref_m.state_dict().keys())
+    m.load_state_dict(ref_m.state_dict())
+    x = torch.randn(2, H * W, dim)
+    with torch.no_grad():
+        ref = ref_m(x)
+        got = m.to(DEV)(x.to(DEV))
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < TOL
+    with pytest.raises(AssertionError):
+        m(torch.randn(2, H * W + 1, dim, device=DEV))   # "input feature has wrong size"
+
+
+@pytest.mark.parametrize("dim,H,W,last", [(96, 6, 5, False), (32, 4, 6, True), (192, 3, 4, False)])
+def test_decoder_layer2d_vs_oracle(dl, oracle, dim, H, W, last, math):
+    torch.manual_seed(21)
+    chans = [dim] * 5
+    ref_m = oracle.MyDecoderLayer((H, W), chans, 1, "mix_skip", n_class=9, is_last=last).eval()
+    _scale_offset_nets(ref_m, 1.0)
+    with torch.no_grad():
+        for blk in (ref_m.layer_lka_1, ref_m.layer_lka_2):
+            blk.layer_scale_1.uniform_(0.2, 1.0); blk.layer_scale_2.uniform_(0.2, 1.0)
+        ref_m.x1_linear.bias.normal_(0, 0.2)
+    m = dl.MyDecoderLayer((H, W), chans, 1, "mix_skip", n_class=9, is_last=last)
+    assert sorted(m.state_dict().keys()) == sorted(ref_m.state_dict().keys())
+    m.load_state_dict(ref_m.state_dict())
+    m = m.to(DEV)
+    x1, x2 = torch.randn(2, H * W, dim), torch.randn(2, H, W, dim)
+    with torch.no_grad():
+        ref = ref_m(x1, x2)
+        got = m(x1.to(DEV), x2.to(DEV))
+        ref0 = ref_m(x1)                 # no skip connection: only the patch expansion (:618-619)
+        got0 = m(x1.to(DEV))
+    assert got.shape == ref.shape and got0.shape == ref0.shape
+    assert rel_err(got, ref) < TOL
+    assert rel_err(got0, ref0) < TOL
+
+
 @pytest.mark.parametrize("C,dims,pos", [(32, (6, 5, 8), True), (96, (4, 6, 5), False)])
 def test_transformer3d_attention_half_vs_oracle(dl, oracle, C, dims, pos, math):
     torch.manual_seed(17)
