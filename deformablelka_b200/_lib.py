@@ -112,6 +112,10 @@ def _load() -> ctypes.CDLL:
     lib.dlka_lka_transformer3d_block_workspace_bytes.argtypes = [I] * 5
     lib.dlka_lka_transformer3d_block_forward.restype = c_int
     lib.dlka_lka_transformer3d_block_forward.argtypes = [POINTER(Transformer3dParams), V, V] + [I] * 6 + [V, c_size_t, V]
+    lib.dlka_deform_conv3d_backward_workspace_bytes.restype = c_size_t
+    lib.dlka_deform_conv3d_backward_workspace_bytes.argtypes = [I] * 20
+    lib.dlka_deform_conv3d_backward.restype = c_int
+    lib.dlka_deform_conv3d_backward.argtypes = [V] * 8 + [I] * 22 + [V, c_size_t, V]
     lib.dlka_linear_tokens_workspace_bytes.restype = c_size_t
     lib.dlka_linear_tokens_workspace_bytes.argtypes = [I, I]
     lib.dlka_linear_tokens_forward.restype = c_int

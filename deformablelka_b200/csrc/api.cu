@@ -463,6 +463,79 @@ int dlka_deform_conv3d_forward(const float *input, const float *weight, const fl
     return run_deform_op(g, input, weight, bias, offset, nullptr, output, math, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------- 3D operator, backward (row N2)
+namespace {
+struct DeformBwdPlan {
+    float *x_cl, *off_cl, *gout_cl, *gin_cl, *goff_cl, *wt, *gwt, *colbuf, *colT, *gchunk, *gchunkT, *wscratch;
+    int Mc;
+};
+
+bool plan_deform_bwd(Arena &ar, const ConvGeo &g, DeformBwdPlan &p)
+{
+    const size_t Vi = (size_t)g.D * g.H * g.W, M = (size_t)g.B * g.Do * g.Ho * g.Wo, KC = (size_t)g.K * g.C;
+    p.Mc = deform3d_bwd_chunk_rows((i64)M);
+    p.x_cl = ar.take<float>(g.B * Vi * g.C);
+    p.gin_cl = ar.take<float>(g.B * Vi * g.C);
+    p.off_cl = ar.take<float>(M * 3 * g.K);
+    p.goff_cl = ar.take<float>(M * 3 * g.K);
+    p.gout_cl = ar.take<float>(M * g.Co);
+    p.wt = ar.take<float>(KC * g.Co);
+    p.gwt = ar.take<float>(KC * g.Co);
+    p.colbuf = ar.take<float>((size_t)p.Mc * KC);
+    p.colT = ar.take<float>((size_t)p.Mc * KC);
+    p.gchunk = ar.take<float>((size_t)p.Mc * g.Co);
+    p.gchunkT = ar.take<float>((size_t)p.Mc * g.Co);
+    const size_t s1 = dense_scratch_floats((int)KC, g.Co), s2 = dense_scratch_floats(g.Co, p.Mc);
+    p.wscratch = ar.take<float>(s1 > s2 ? s1 : s2);
+    return ar.ok();
+}
+}  // namespace
+
+size_t dlka_deform_conv3d_backward_workspace_bytes(int B, int C, int D, int H, int W, int Co, int kd, int kh, int kw, int sd, int sh,
+                                                   int sw, int pd, int ph, int pw, int dild, int dilh, int dilw, int group,
+                                                   int deformable_group)
+{
+    ConvGeo g = make_geo(B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw, dild, dilh, dilw, group, deformable_group, 3);
+    if (bad_geo(g)) return 0;
+    Arena ar(nullptr, 0);
+    DeformBwdPlan p;
+    plan_deform_bwd(ar, g, p);
+    return ar.off + 256;
+}
+
+// D3D.deform_conv_backward (3D/dcn/src/vision.cpp:6, cuda/deform_conv_cuda.cu:128-285): all tensors in the reference's layouts
+// (NCDHW, offset [B, 3*K, Do, Ho, Wo], weight [Co, C, kd, kh, kw]); the four gradients are fully overwritten.
+int dlka_deform_conv3d_backward(const float *input, const float *weight, const float *offset, const float *grad_output,
+                                float *grad_input, float *grad_offset, float *grad_weight, float *grad_bias, int B, int C, int D, int H,
+                                int W, int Co, int kd, int kh, int kw, int sd, int sh, int sw, int pd, int ph, int pw, int dild, int dilh,
+                                int dilw, int group, int deformable_group, int im2col_step, int math, void *workspace,
+                                size_t workspace_bytes, void *stream)
+{
+    if (!input || !weight || !offset || !grad_output || !grad_input || !grad_offset || !grad_weight || !grad_bias)
+        return DLKA_ERR_INVALID_ARGUMENT;
+    if (group <= 0 || deformable_group <= 0 || im2col_step <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    ConvGeo g = make_geo(B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw, dild, dilh, dilw, group, deformable_group, 3);
+    if (bad_geo(g)) return DLKA_ERR_INVALID_ARGUMENT;
+    const int step = B < im2col_step ? B : im2col_step;  // deform_conv_cuda.cu:176-178
+    if (B % step != 0) return DLKA_ERR_INVALID_ARGUMENT;
+    if (group != 1 || deformable_group != 1 || C % 4 != 0) return DLKA_ERR_UNSUPPORTED;   // what the D-LKA block uses
+    DLKA_TRY(check_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ar(workspace, workspace_bytes);
+    DeformBwdPlan p;
+    if (!plan_deform_bwd(ar, g, p)) return DLKA_ERR_WORKSPACE;
+    const i64 Vi = (i64)g.D * g.H * g.W, Vo = (i64)g.Do * g.Ho * g.Wo;
+    DLKA_TRY(transpose_cs_to_sc(input, p.x_cl, g.B, g.C, Vi, st));
+    DLKA_TRY(transpose_cs_to_sc(offset, p.off_cl, g.B, 3 * g.K, Vo, st));
+    DLKA_TRY(transpose_cs_to_sc(grad_output, p.gout_cl, g.B, g.Co, Vo, st));
+    DLKA_CUDA_TRY(cudaMemsetAsync(p.gin_cl, 0, (size_t)g.B * Vi * g.C * sizeof(float), st));
+    DLKA_TRY(deform3d_backward_cl(g, p.x_cl, p.off_cl, weight, p.gout_cl, p.gin_cl, p.goff_cl, grad_weight, grad_bias, p.wt, p.gwt,
+                                  p.colbuf, p.colT, p.gchunk, p.gchunkT, p.wscratch, math, st));
+    DLKA_TRY(transpose_sc_to_cs(p.gin_cl, grad_input, g.B, g.C, Vi, st));
+    DLKA_TRY(transpose_sc_to_cs(p.goff_cl, grad_offset, g.B, 3 * g.K, Vo, st));
+    return DLKA_OK;
+}
+
 int dlka_deform_conv3d_sample_indices(const float *offset, int32_t *low, int32_t *mask, int B, int D, int H, int W, int kd, int kh,
                                       int kw, int sd, int sh, int sw, int pd, int ph, int pw, int dild, int dilh, int dilw,
                                       int deformable_group, void *stream)

@@ -100,6 +100,13 @@ int attention2d_cl(const dlkaBlock2dParams *params, const float *x_cl, float *y_
 int dense_cl(const float *x, int ldX, i64 M, int Ci, int Co, const float *w, const float *bias, int epi, const float *E, int ldE,
              float *y, int ldY, int math, float *wscratch, cudaStream_t st);
 size_t dense_scratch_floats(int Co, int Ci);
+
+// ---------------- backward of the 3D deformable conv (deform_bwd.cu), channels-last, groups = dg = 1 ----------------
+int deform3d_bwd_chunk_rows(i64 M);   // rows per streamed chunk (multiple of 64)
+int deform3d_backward_cl(const ConvGeo &g, const float *x, const float *off, const float *w, const float *gout, float *gin, float *goff,
+                         float *gw, float *gb, float *wt, float *gwt, float *colbuf, float *colT, float *gchunk, float *gchunkT,
+                         float *wscratch, int math, cudaStream_t st);
+
 // dense 3x3x3 conv C->C (stride 1, pad 1) on channels-last tokens with folded per-channel scale/shift and
 // LeakyReLU (+ residual): the two convolutions of UnetResBlock (row N3).  SIMT fp32 fallback when math != bf16x3.
 int conv3_bn_act_cl(const float *x, const float *w, const float *scale, const float *shift, int act, float slope, const float *E,

@@ -1,9 +1,9 @@
 """3D operator boundary: mirrors 3D/dcn/functions/deform_conv_func.py and 3D/dcn/modules/deform_conv.py
 (identical copies: 3D/d_lka_former/network_architecture/synapse/{deform_conv_func,deform_conv}.py).
 
-``D3D.deform_conv_forward`` is replaced by ``ops.deform_conv3d_forward`` (C ABI
-``dlka_deform_conv3d_forward``).  Forward only: the north star is the forward pass; ``backward``
-raises (SURVEY.md 8f N2 lists it as a later row).
+``D3D.deform_conv_forward`` / ``D3D.deform_conv_backward`` are replaced by ``ops.deform_conv3d_forward`` /
+``ops.deform_conv3d_backward`` (C ABI ``dlka_deform_conv3d_forward`` / ``dlka_deform_conv3d_backward``; the backward is
+SURVEY.md 8f row N2, groups = deformable groups = 1).  Inference (no grad) takes the fused one-call path.
 """
 from __future__ import annotations
 
@@ -12,6 +12,7 @@ import math
 import torch
 from torch import nn
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 from torch.nn import init
 from torch.nn.modules.utils import _triple
 
@@ -34,8 +35,13 @@ class DeformConvFunction(Function):
         return output
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_output):
-        raise NotImplementedError("deformablelka_b200 implements the forward pass only (backward: SURVEY.md 8f N2)")
+        input, offset, weight, bias = ctx.saved_tensors
+        grad_input, grad_offset, grad_weight, grad_bias = ops.deform_conv3d_backward(
+            input, weight, bias, offset, grad_output, ctx.kernel_size, ctx.stride, ctx.padding, ctx.dilation, ctx.group,
+            ctx.deformable_groups, ctx.im2col_step)
+        return grad_input, grad_offset, grad_weight, grad_bias, None, None, None, None, None, None
 
 
 class DeformConv(nn.Module):
@@ -96,6 +102,13 @@ class DeformConvPack(DeformConv):
         self.conv_offset.bias.data.zero_()
 
     def forward(self, input):
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # training: the reference's own two steps (synapse/deform_conv.py:93-105) so autograd sees conv_offset (stock
+            # nn.Conv3d) and DeformConvFunction (library forward + dlka_deform_conv3d_backward)
+            with torch.backends.cudnn.flags(allow_tf32=False):   # offsets are sampling positions: keep them fp32
+                offset = self.conv_offset(input)
+            return DeformConvFunction.apply(input.contiguous(), offset, self.weight, self.bias, self.stride, self.padding,
+                                            self.dilation, self.groups, self.deformable_groups, self.im2col_step)
         return ops.deform_conv_pack3d(input, self.conv_offset.weight, self.conv_offset.bias, self.weight, self.bias,
                                       self.stride, self.padding, self.dilation, self.groups, self.deformable_groups,
                                       self.im2col_step)

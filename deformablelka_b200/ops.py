@@ -458,6 +458,53 @@ def deformable_lka_attention2d_forward(params: dict, x: torch.Tensor, math=None)
     return y
 
 
+def deform_conv3d_backward(input: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, offset: torch.Tensor,
+                           grad_output: torch.Tensor, kernel_size, stride, padding, dilation, group: int,
+                           deformable_group: int, im2col_step: int = 64, math=None):
+    """Same argument meaning and error behaviour as ``D3D.deform_conv_backward`` (deform_conv_cuda.cu:128-285); returns
+    (grad_input, grad_offset, grad_weight, grad_bias)."""
+    if not input.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")  # deform_conv.h:84
+    if not input.is_contiguous():
+        raise RuntimeError("input tensor has to be contiguous")  # deform_conv_cuda.cu:150
+    if not weight.is_contiguous():
+        raise RuntimeError("weight tensor has to be contiguous")  # :151
+    kd, kh, kw = _triple(kernel_size)
+    sd, sh, sw = _triple(stride)
+    pd, ph, pw = _triple(padding)
+    dd, dh, dw = _triple(dilation)
+    B, C, D, H, W = input.shape
+    Co, Cg, kd_, kh_, kw_ = weight.shape
+    if (kd_, kh_, kw_) != (kd, kh, kw):
+        raise RuntimeError(f"Input shape and kernel shape wont match: ({kd} x {kh} x {kw} vs {kd_} x {kh_} x {kw_}).")  # :186
+    if C != Cg * group:
+        raise RuntimeError(f"Input shape and kernel channels wont match: ({C} vs {Cg * group}).")  # :189
+    step = min(B, im2col_step)
+    if B % step:
+        raise RuntimeError(f"batch({B}) must divide im2col_step({step})")  # :178
+    Do, Ho, Wo = _out_extent(D, pd, dd, kd, sd), _out_extent(H, ph, dh, kh, sh), _out_extent(W, pw, dw, kw, sw)
+    if grad_output.shape[0] != B:
+        raise RuntimeError(f"Input shape and grad_out batch wont match: ({B} vs {grad_output.shape[0]}).")  # :196
+    if grad_output.shape[1] != Co:
+        raise RuntimeError(f"Input shape and grad_out channels_out wont match: ({Co} vs {grad_output.shape[1]}).")  # :199
+    if tuple(grad_output.shape[2:]) != (Do, Ho, Wo):
+        raise RuntimeError(f"Input shape and grad_out shape wont match: ({Do} x {Ho} x {Wo} vs "
+                           f"{grad_output.shape[2]} x {grad_output.shape[3]} x {grad_output.shape[4]}).")  # :202
+    offset = offset.contiguous()
+    grad_output = grad_output.contiguous()
+    gi, go = torch.empty_like(input), torch.empty_like(offset)
+    gw, gb = torch.empty_like(weight), torch.empty(Co, dtype=torch.float32, device=input.device)
+    ws = Workspace.get(input.device, lib.dlka_deform_conv3d_backward_workspace_bytes(
+        B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw, dd, dh, dw, group, deformable_group))
+    with torch.cuda.device(input.device):
+        st = lib.dlka_deform_conv3d_backward(
+            dptr(input, "input"), dptr(weight, "weight"), dptr(offset, "offset"), dptr(grad_output, "grad_output"),
+            dptr(gi), dptr(go), dptr(gw), dptr(gb), B, C, D, H, W, Co, kd, kh, kw, sd, sh, sw, pd, ph, pw, dd, dh, dw,
+            group, deformable_group, im2col_step, _math(math), ws.data_ptr(), ws.numel(), stream_ptr(input.device))
+    check(st, "dlka_deform_conv3d_backward")
+    return gi, go, gw, gb
+
+
 def linear_tokens_forward(x: torch.Tensor, weight: torch.Tensor, bias=None, add=None, math=None) -> torch.Tensor:
     """nn.Linear on tokens [..., K] -> [..., N], optionally + add (MyDecoderLayer.x1_linear and its skip add,
     2D/networks/MaxViT_deform_LKA.py:604-607)."""

@@ -87,6 +87,22 @@ DLKA_API int dlka_deform_conv3d_forward(const float *input, const float *weight,
                                int group, int deformable_group, int im2col_step, int math,
                                void *workspace, size_t workspace_bytes, void *stream);
 
+/* Backward of the same operator (row N2).  Replaces D3D.deform_conv_backward
+ * (3D/dcn/src/vision.cpp:6, deform_conv.h:49-86, cuda/deform_conv_cuda.cu:128-285): grad_input [B,C,D,H,W],
+ * grad_offset [B,3*K,Do,Ho,Wo], grad_weight [Co,C,kd,kh,kw], grad_bias [Co], all fully overwritten.
+ * groups == deformable groups == 1 and C % 4 == 0 (the D-LKA configuration); anything else is DLKA_ERR_UNSUPPORTED.
+ * The gradients are those of the forward definition; the reference's pad_h/pad_w index defect in
+ * deformable_col2im_coord (deform_im2col_cuda.cuh:448) is not reproduced.                                          */
+DLKA_API size_t dlka_deform_conv3d_backward_workspace_bytes(int B, int C, int D, int H, int W, int Co,
+                                                   int kd, int kh, int kw, int sd, int sh, int sw,
+                                                   int pd, int ph, int pw, int dild, int dilh, int dilw,
+                                                   int group, int deformable_group);
+DLKA_API int dlka_deform_conv3d_backward(const float *input, const float *weight, const float *offset, const float *grad_output,
+                                float *grad_input, float *grad_offset, float *grad_weight, float *grad_bias,
+                                int B, int C, int D, int H, int W, int Co, int kd, int kh, int kw, int sd, int sh, int sw,
+                                int pd, int ph, int pw, int dild, int dilh, int dilw, int group, int deformable_group,
+                                int im2col_step, int math, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Integer planes of the 3D sampler for bit-exact parity checks:
  *   low [B*dg, Vo, K, 3] int32 = floor(p) per axis,  mask [B*dg, Vo, K] int32:
  *   bit0 = sample valid (cuh:248), bits 1..8 = corner v1..v8 read (cuh:43-65).

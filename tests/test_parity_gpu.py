@@ -514,3 +514,63 @@ def test_transformer3d_whole_block_vs_oracle(dl, oracle, C, dims, pos, math):
     assert rel_err(got_tail_torch, ref) < TOL
     with pytest.raises(RuntimeError, match="eval"):
         md.train()(x.to(DEV))
+
+
+# ----------------------------------------------------------------------------- row N2: backward of the 3D deformable conv
+@pytest.mark.parametrize("B,C,Co,dims,k,stride,pad,dil,scale", [
+    (2, 8, 12, (4, 5, 6), 3, 1, 1, 1, 1.5),        # offsets beyond the volume: validity / corner masks in the gradients
+    (1, 32, 32, (4, 4, 4), 3, 1, 1, 1, 0.3),
+    (2, 16, 8, (7, 6, 5), 3, 2, 1, 1, 0.7),        # stride 2
+    (1, 8, 8, (6, 7, 8), 3, 1, 2, 2, 0.7),         # dilation 2
+    (1, 8, 16, (5, 5, 5), (1, 3, 3), 1, (0, 1, 1), 1, 0.5),
+    (1, 8, 8, (24, 20, 20), 3, 1, 1, 1, 0.5),      # 9600 rows: two streamed chunks (accumulating grad_weight GEMM, zero padding)
+])
+def test_deform_conv3d_backward_vs_autograd_oracle(dl, oracle, B, C, Co, dims, k, stride, pad, dil, scale, math):
+    from torch.nn.modules.utils import _triple
+    torch.manual_seed(30)
+    D, H, W = dims
+    kd, kh, kw = _triple(k)
+    st, pd, dl_ = _triple(stride), _triple(pad), _triple(dil)
+    ext = [(n + 2 * p - (d * (kk - 1) + 1)) // s + 1 for n, p, d, kk, s in zip(dims, pd, dl_, (kd, kh, kw), st)]
+    x = torch.randn(B, C, D, H, W, requires_grad=True)
+    w = (torch.randn(Co, C, kd, kh, kw) * 0.2).requires_grad_()
+    b = torch.randn(Co, requires_grad=True)
+    off = (torch.randn(B, 3 * kd * kh * kw, *ext) * scale).requires_grad_()
+    gout = torch.randn(B, Co, *ext)
+    ref = oracle.deform_conv3d_autograd(x, off, w, b, st, pd, dl_)
+    ref.backward(gout)
+    gi, go, gw, gb = dl.ops.deform_conv3d_backward(x.detach().to(DEV), w.detach().to(DEV), b.detach().to(DEV), off.detach().to(DEV),
+                                                   gout.to(DEV), (kd, kh, kw), st, pd, dl_, 1, 1)
+    for name, got, want in (("grad_input", gi, x.grad), ("grad_offset", go, off.grad), ("grad_weight", gw, w.grad),
+                            ("grad_bias", gb, b.grad)):
+        assert got.shape == want.shape, name
+        assert rel_err(got, want) < TOL, name
+
+
+def test_deform_conv_pack3d_autograd_end_to_end(dl, oracle, math):
+    """loss.backward() through the drop-in module (DeformConvFunction.backward, deform_conv_func.py:38-56): gradients of
+    every parameter and of the input against autograd through the oracle restatement."""
+    torch.manual_seed(31)
+    C, dims = 16, (5, 6, 4)
+    m = dl.DeformConvPack(C, C, (3, 3, 3), 1, 1)
+    oracle.randomize_offsets_(m, std=0.1, bias_range=1.0)
+    mo = oracle.DeformConvPack3D(C, C, (3, 3, 3), 1, 1)
+    mo.load_state_dict(m.state_dict())
+    x = torch.randn(2, C, *dims)
+    xo = x.clone().requires_grad_()
+    off = mo.conv_offset(xo)
+    oracle.deform_conv3d_autograd(xo, off, mo.weight, mo.bias).square().sum().backward()
+    m = m.to(DEV)
+    xg = x.to(DEV).requires_grad_()
+    m(xg).square().sum().backward()
+    assert rel_err(xg.grad, xo.grad) < TOL
+    for (n, p), (_, po) in zip(m.named_parameters(), mo.named_parameters()):
+        assert rel_err(p.grad, po.grad) < TOL, n
+
+
+def test_deform_conv3d_backward_refuses_groups(dl):
+    x = torch.randn(1, 8, 3, 3, 3, device=DEV)
+    w = torch.randn(8, 4, 3, 3, 3, device=DEV)
+    with pytest.raises(RuntimeError):
+        dl.ops.deform_conv3d_backward(x, w, torch.zeros(8, device=DEV), torch.zeros(1, 81, 3, 3, 3, device=DEV),
+                                      torch.zeros(1, 8, 3, 3, 3, device=DEV), 3, 1, 1, 1, 2, 1)
