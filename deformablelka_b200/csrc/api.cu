@@ -354,6 +354,18 @@ int dense_cl(const float *x, int ldX, i64 M, int Ci, int Co, const float *w, con
     return contraction(a, w, math, wscratch, st);
 }
 
+int dense_splitk_cl(const float *x, int ldX, i64 M, int Ci, int Co, const float *w, float *partial, int ksplit_steps, int *nsplit,
+                    float *wscratch, cudaStream_t st)
+{
+    IgemmArgs a = dense_args(x, ldX, M, Ci, Co, nullptr, 0, nullptr, EPI_NONE, nullptr, 0, partial, Co);
+    if (!tc_supported(a) || ksplit_steps <= 0) return DLKA_ERR_UNSUPPORTED;
+    a.ksplit_steps = ksplit_steps;
+    a.ysplit_stride = M * (i64)Co;
+    *nsplit = (int)cdiv(Ci / tc_kc(Ci), ksplit_steps);
+    DLKA_TRY(tc_pack_weight(w, wscratch, Co, Ci, 1, st));
+    return igemm_tc(a, wscratch, st);
+}
+
 size_t dense_scratch_floats(int Co, int Ci) { return contraction_scratch_floats(Co, Ci, 1, 1); }
 
 size_t conv3_scratch_floats(int C) { return contraction_scratch_floats(C, C, 27, 1); }
@@ -466,7 +478,7 @@ int dlka_deform_conv3d_forward(const float *input, const float *weight, const fl
 // ---------------------------------------------------------------------------- 3D operator, backward (row N2)
 namespace {
 struct DeformBwdPlan {
-    float *x_cl, *off_cl, *gout_cl, *gin_cl, *goff_cl, *wt, *gwt, *colbuf, *colT, *gchunk, *gchunkT, *wscratch;
+    float *x_cl, *off_cl, *gout_cl, *gin_cl, *goff_cl, *wt, *gwt, *colbuf, *colT, *gchunk, *gchunkT, *partial, *wscratch;
     int Mc;
 };
 
@@ -485,6 +497,7 @@ bool plan_deform_bwd(Arena &ar, const ConvGeo &g, DeformBwdPlan &p)
     p.colT = ar.take<float>((size_t)p.Mc * KC);
     p.gchunk = ar.take<float>((size_t)p.Mc * g.Co);
     p.gchunkT = ar.take<float>((size_t)p.Mc * g.Co);
+    p.partial = ar.take<float>(((size_t)p.Mc / 256 + 1) * KC * g.Co);   // split-K slices of >= 8 K steps of >= 32 rows
     const size_t s1 = dense_scratch_floats((int)KC, g.Co), s2 = dense_scratch_floats(g.Co, p.Mc);
     p.wscratch = ar.take<float>(s1 > s2 ? s1 : s2);
     return ar.ok();
@@ -530,7 +543,7 @@ int dlka_deform_conv3d_backward(const float *input, const float *weight, const f
     DLKA_TRY(transpose_cs_to_sc(grad_output, p.gout_cl, g.B, g.Co, Vo, st));
     DLKA_CUDA_TRY(cudaMemsetAsync(p.gin_cl, 0, (size_t)g.B * Vi * g.C * sizeof(float), st));
     DLKA_TRY(deform3d_backward_cl(g, p.x_cl, p.off_cl, weight, p.gout_cl, p.gin_cl, p.goff_cl, grad_weight, grad_bias, p.wt, p.gwt,
-                                  p.colbuf, p.colT, p.gchunk, p.gchunkT, p.wscratch, math, st));
+                                  p.colbuf, p.colT, p.gchunk, p.gchunkT, p.partial, p.wscratch, math, st));
     DLKA_TRY(transpose_sc_to_cs(p.gin_cl, grad_input, g.B, g.C, Vi, st));
     DLKA_TRY(transpose_sc_to_cs(p.goff_cl, grad_offset, g.B, 3 * g.K, Vo, st));
     return DLKA_OK;

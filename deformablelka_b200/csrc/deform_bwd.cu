@@ -80,29 +80,37 @@ __device__ __forceinline__ BwdRow decode_row(const ConvGeo &g, i64 m)
     return r;
 }
 
-// one thread per (row of the chunk, tap); loops over the channels in float4 steps
+// LPG lanes per (row of the chunk, tap): lane l owns channels 4l, 4l + 4*LPG, ... so gcol reads, corner reads and the vector
+// reductions into grad_input are contiguous across the group; the three coordinate gradients are reduced with shuffles.
 //   grad_input[corner] += w_corner * gcol           (deformable_col2im, cuh:300-350)
 //   grad_offset[m][3*tap + a] = sum_c gcol[c] * d val_c / d p_a   (deformable_col2im_coord, cuh:352-405)
-__global__ void __launch_bounds__(128) bwd_scatter_kernel(const float *__restrict__ gcol, const float *__restrict__ x,
+template <int LPG>
+__global__ void __launch_bounds__(256) bwd_scatter_kernel(const float *__restrict__ gcol, const float *__restrict__ x,
                                                           const float *__restrict__ off, float *__restrict__ gin,
                                                           float *__restrict__ goff, ConvGeo g, i64 m0, int Mc, i64 M)
 {
     const int K = g.K, C = g.C;
-    const i64 total = (i64)Mc * K;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
-        const int tap = (int)(i % K);
-        const int r = (int)(i / K);
+    const i64 total = (i64)Mc * K;                       // Mc: valid rows of this chunk
+    const int lg = threadIdx.x % LPG;
+    const i64 ngroups = (i64)gridDim.x * (blockDim.x / LPG);
+    // the loop condition is warp-uniform (index of the warp's first group), so the full-mask shuffles below are executed by
+    // all 32 lanes even in the last, partially filled round
+    const int gw_ = (threadIdx.x % 32) / LPG;            // group within the warp
+    for (i64 i = (i64)blockIdx.x * (blockDim.x / LPG) + threadIdx.x / LPG; i - gw_ < total; i += ngroups) {
+        const bool act = i < total;
+        const i64 ic = act ? i : total - 1;
+        const int tap = (int)(ic % K);
+        const int r = (int)(ic / K);
         const i64 m = m0 + r;
-        if (m >= M) continue;
         const BwdRow ro = decode_row(g, m);
         const int kk = tap % g.kw, jj = (tap / g.kw) % g.kh, ii = tap / (g.kw * g.kh);
         const float *o = off + m * (3 * (i64)K) + 3 * tap;
-        const float pd = sample_pos(ro.d, g.sd, g.pd, ii, g.dd, o[0]);
-        const float ph = sample_pos(ro.h, g.sh, g.ph, jj, g.dh, o[1]);
-        const float pw = sample_pos(ro.w, g.sw, g.pw, kk, g.dw, o[2]);
+        const float pd = sample_pos(ro.d, g.sd, g.pd, ii, g.dd, __ldg(o));
+        const float ph = sample_pos(ro.h, g.sh, g.ph, jj, g.dh, __ldg(o + 1));
+        const float pw = sample_pos(ro.w, g.sw, g.pw, kk, g.dw, __ldg(o + 2));
         const Sample3 s = make_sample3(pd, ph, pw, g.D, g.H, g.W);
         float gd = 0.f, gh = 0.f, gw = 0.f;
-        if (s.mask & 1) {
+        if (act && (s.mask & 1)) {
             const float ld = s.l[0], lh = s.l[1], lw = s.l[2], hd = 1.f - ld, hh = 1.f - lh, hw = 1.f - lw;
             const i64 sW = C, sH = (i64)g.W * C, sD = (i64)g.H * g.W * C;
             const i64 base = (i64)ro.b * g.D * sD + (i64)s.lo[0] * sD + (i64)s.lo[1] * sH + (i64)s.lo[2] * sW;
@@ -112,7 +120,7 @@ __global__ void __launch_bounds__(128) bwd_scatter_kernel(const float *__restric
             const float ch[8] = {-hd * hw, -hd * lw, hd * hw, hd * lw, -ld * hw, -ld * lw, ld * hw, ld * lw};   // d weight / d p_h
             const float cw[8] = {-hd * hh, hd * hh, -hd * lh, hd * lh, -ld * hh, ld * hh, -ld * lh, ld * lh};   // d weight / d p_w
             const float *gc = gcol + (i64)r * K * C + (i64)tap * C;
-            for (int c = 0; c < C; c += 4) {
+            for (int c = lg * 4; c < C; c += LPG * 4) {
                 const float4 gv = *reinterpret_cast<const float4 *>(gc + c);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -127,8 +135,26 @@ __global__ void __launch_bounds__(128) bwd_scatter_kernel(const float *__restric
                 }
             }
         }
-        float *go = goff + m * (3 * (i64)K) + 3 * tap;
-        go[0] = gd; go[1] = gh; go[2] = gw;
+#pragma unroll
+        for (int o2 = LPG / 2; o2 > 0; o2 >>= 1) {   // every lane of the group runs the same trip count: full-mask shuffles are safe
+            gd += __shfl_xor_sync(0xffffffffu, gd, o2);
+            gh += __shfl_xor_sync(0xffffffffu, gh, o2);
+            gw += __shfl_xor_sync(0xffffffffu, gw, o2);
+        }
+        if (act && lg == 0) {
+            float *go = goff + m * (3 * (i64)K) + 3 * tap;
+            go[0] = gd; go[1] = gh; go[2] = gw;
+        }
+    }
+}
+
+// gwt (+)= sum_z partial[z]
+__global__ void bwd_reduce_partials_kernel(const float *__restrict__ partial, float *__restrict__ gwt, i64 n, int nsplit, int accumulate)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        float s = accumulate ? gwt[i] : 0.f;
+        for (int z = 0; z < nsplit; ++z) s += partial[(i64)z * n + i];
+        gwt[i] = s;
     }
 }
 
@@ -177,7 +203,7 @@ int deform3d_bwd_chunk_rows(i64 M) { return (int)(M < 8192 ? cdiv(M, 64) * 64 : 
 // all pointers channels-last; gin / gwt zero-initialised by the caller; workspace pieces supplied by the caller (api.cu)
 int deform3d_backward_cl(const ConvGeo &g, const float *x, const float *off, const float *w, const float *gout, float *gin, float *goff,
                          float *gw, float *gb, float *wt, float *gwt, float *colbuf, float *colT, float *gchunk, float *gchunkT,
-                         float *wscratch, int math, cudaStream_t st)
+                         float *partial, float *wscratch, int math, cudaStream_t st)
 {
     const int K = g.K, C = g.C, Co = g.Co, KC = K * C;
     const i64 M = (i64)g.B * g.Do * g.Ho * g.Wo;
@@ -190,16 +216,33 @@ int deform3d_backward_cl(const ConvGeo &g, const float *x, const float *off, con
         const i64 rows = M - m0 < Mc ? M - m0 : Mc;
         // columns = W^T . grad_output (deform_conv_cuda.cu:226-230), for this chunk only
         DLKA_TRY(dense_cl(gout + m0 * Co, Co, rows, Co, KC, wt, nullptr, EPI_NONE, nullptr, 0, colbuf, KC, math, wscratch, st));
-        DLKA_LAUNCH("bwd_scatter", st,
-                    bwd_scatter_kernel<<<grid_for(rows * K, 128), 128, 0, st>>>(colbuf, x, off, gin, goff, g, m0, (int)rows, M));
+        {
+            const int lpg = C / 4 >= 32 ? 32 : C / 4 > 8 ? 16 : C / 4 > 4 ? 8 : 4;   // (C/4 = 24 -> 16 lanes, two passes)
+            const int blocks = grid_for(rows * K * lpg, 256);
+            if (lpg == 32) DLKA_LAUNCH("bwd_scatter", st, bwd_scatter_kernel<32><<<blocks, 256, 0, st>>>(colbuf, x, off, gin, goff, g, m0, (int)rows, M));
+            else if (lpg == 16) DLKA_LAUNCH("bwd_scatter", st, bwd_scatter_kernel<16><<<blocks, 256, 0, st>>>(colbuf, x, off, gin, goff, g, m0, (int)rows, M));
+            else if (lpg == 8) DLKA_LAUNCH("bwd_scatter", st, bwd_scatter_kernel<8><<<blocks, 256, 0, st>>>(colbuf, x, off, gin, goff, g, m0, (int)rows, M));
+            else DLKA_LAUNCH("bwd_scatter", st, bwd_scatter_kernel<4><<<blocks, 256, 0, st>>>(colbuf, x, off, gin, goff, g, m0, (int)rows, M));
+        }
         // grad_weight += grad_output . columns^T with columns = im2col(input) (deform_conv_cuda.cu:251-273)
         DLKA_LAUNCH("bwd_im2col", st,
                     bwd_im2col_kernel<<<grid_for((i64)Mc * K * (C / 4), 256), 256, 0, st>>>(x, off, colbuf, g, m0, Mc, M));
         DLKA_TRY(transpose_sc_to_cs(colbuf, colT, 1, KC, Mc, st));                       // [Mc][KC] -> [KC][Mc]
         DLKA_LAUNCH("bwd_copy_rows", st, bwd_copy_rows_kernel<<<grid_for((i64)Mc * Co, 256), 256, 0, st>>>(gout, gchunk, m0, Mc, M, Co));
         DLKA_TRY(transpose_sc_to_cs(gchunk, gchunkT, 1, Co, Mc, st));                    // [Mc][Co] -> [Co][Mc]
-        DLKA_TRY(dense_cl(colT, Mc, KC, Mc, Co, gchunkT, nullptr, first ? EPI_NONE : EPI_ADD, first ? nullptr : gwt, Co, gwt, Co, math,
-                          wscratch, st));
+        // K dimension = the chunk's rows: split-K over grid.z (a [KC x Co] output alone would occupy only KC/128 CTAs)
+        int nsplit = 0;
+        const int rc = (math == DLKA_MATH_BF16X3) ? dense_splitk_cl(colT, Mc, KC, Mc, Co, gchunkT, partial, 8, &nsplit, wscratch, st)
+                                                  : DLKA_ERR_UNSUPPORTED;
+        if (rc == DLKA_OK) {
+            DLKA_LAUNCH("bwd_reduce_partials", st,
+                        bwd_reduce_partials_kernel<<<grid_for((i64)KC * Co, 256), 256, 0, st>>>(partial, gwt, (i64)KC * Co, nsplit, first ? 0 : 1));
+        } else if (rc == DLKA_ERR_UNSUPPORTED) {
+            DLKA_TRY(dense_cl(colT, Mc, KC, Mc, Co, gchunkT, nullptr, first ? EPI_NONE : EPI_ADD, first ? nullptr : gwt, Co, gwt, Co, math,
+                              wscratch, st));
+        } else {
+            return rc;
+        }
         first = false;
     }
     DLKA_LAUNCH("bwd_unpack_gw", st, bwd_unpack_gw_kernel<<<grid_for((i64)Co * KC, 256), 256, 0, st>>>(gwt, gw, Co, C, K));

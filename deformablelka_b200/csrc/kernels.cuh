@@ -27,6 +27,10 @@ struct IgemmArgs {
     int ldE;
     float *Y;          // output [M][ldY]
     int ldY;
+    // split-K (tcgen05 dense path only): grid.z slices of `ksplit_steps` K steps each write partial products to
+    // Y + z * ysplit_stride (bias / epilogue operand applied by slice 0 only); 0 = no split
+    int ksplit_steps;
+    i64 ysplit_stride;
 };
 
 int igemm_simt_npad(int n_per_group);
@@ -97,6 +101,9 @@ int affine_act_cl(float *y, const float *scale, const float *shift, const float 
 // ---------------- internal block-level helpers exported by api.cu for blocks_api.cu ----------------
 int attention2d_cl(const dlkaBlock2dParams *params, const float *x_cl, float *y_cl, int B, int C, int H, int W, int math,
                    void *workspace, size_t workspace_bytes, cudaStream_t st);
+// split-K variant: partial[z][M][Co] for z < cdiv(Ci / KC, ksplit_steps); returns the number of slices in *nsplit (tcgen05 path only)
+int dense_splitk_cl(const float *x, int ldX, i64 M, int Ci, int Co, const float *w, float *partial, int ksplit_steps, int *nsplit,
+                    float *wscratch, cudaStream_t st);
 int dense_cl(const float *x, int ldX, i64 M, int Ci, int Co, const float *w, const float *bias, int epi, const float *E, int ldE,
              float *y, int ldY, int math, float *wscratch, cudaStream_t st);
 size_t dense_scratch_floats(int Co, int Ci);
@@ -105,7 +112,7 @@ size_t dense_scratch_floats(int Co, int Ci);
 int deform3d_bwd_chunk_rows(i64 M);   // rows per streamed chunk (multiple of 64)
 int deform3d_backward_cl(const ConvGeo &g, const float *x, const float *off, const float *w, const float *gout, float *gin, float *goff,
                          float *gw, float *gb, float *wt, float *gwt, float *colbuf, float *colT, float *gchunk, float *gchunkT,
-                         float *wscratch, int math, cudaStream_t st);
+                         float *partial /* [Mc/512 + 1][K*C*Co] split-K partial products */, float *wscratch, int math, cudaStream_t st);
 
 // dense 3x3x3 conv C->C (stride 1, pad 1) on channels-last tokens with folded per-channel scale/shift and
 // LeakyReLU (+ residual): the two convolutions of UnetResBlock (row N3).  SIMT fp32 fallback when math != bf16x3.

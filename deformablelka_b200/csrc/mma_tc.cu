@@ -17,6 +17,9 @@
 //   j * LBO + (r / 8) * 128 + (r % 8) * 16   -> a 128-row slot is contiguous per chunk (LBO = 2048 + pad).
 #include <cuda_bf16.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
 
@@ -144,7 +147,9 @@ __global__ void __launch_bounds__((CTRL_WARPS + NPW) * 32, (MODE == IGEMM_DENSE 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const i64 m0 = (i64)blockIdx.x * (MT * 128);
     const int n_tile = blockIdx.y;
-    const int KS = a.KS;
+    // split-K: slice blockIdx.z covers K steps [ks0, ks0 + KS)
+    const int ks0 = a.g.ksplit_steps ? (int)blockIdx.z * a.g.ksplit_steps : 0;
+    const int KS = a.g.ksplit_steps ? (a.KS - ks0 < a.g.ksplit_steps ? a.KS - ks0 : a.g.ksplit_steps) : a.KS;
     const int nkc = a.g.geo.C / KC;
     const uint32_t tmem_cols = (MT * NT <= 32) ? 32u : (MT * NT <= 64) ? 64u : (MT * NT <= 128) ? 128u : (MT * NT <= 256) ? 256u : 512u;
 
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__((CTRL_WARPS + NPW) * 32, (MODE == IGEMM_DENSE 
     if (warp >= CTRL_WARPS) {  // bias vector + row decode, once per CTA
         for (int i = tid - CTRL_WARPS * 32; i < 128; i += NPT) {
             const int n = n_tile * a.NT + i;
-            sBias[i] = (a.g.bias && i < a.NT && n < a.g.geo.Co) ? __ldg(a.g.bias + n) : 0.f;
+            sBias[i] = (a.g.bias && blockIdx.z == 0 && i < a.NT && n < a.g.geo.Co) ? __ldg(a.g.bias + n) : 0.f;
         }
         for (int r = tid - CTRL_WARPS * 32; r < MT * 128; r += NPT) {
             i64 m = m0 + r;
@@ -216,19 +221,19 @@ __global__ void __launch_bounds__((CTRL_WARPS + NPW) * 32, (MODE == IGEMM_DENSE 
     } else if (warp == 1) {
         // ===================== weight loader (bulk async copy) =====================
         if (elect_one()) {
-            const uint8_t *src = a.Bp + (i64)n_tile * KS * B_SLOT;
+            const uint8_t *src = a.Bp + (i64)n_tile * a.KS * B_SLOT;
             for (int ks = 0; ks < KS; ++ks) {
                 const int bs = ks % SB;
                 mbar_wait(emptyB(bs), ((ks / SB) & 1) ^ 1);
                 mbar_arrive_expect_tx(fullB(bs), (uint32_t)B_SLOT);
-                bulk_g2s(smem_u32(sB + bs * B_SLOT), src + (i64)ks * B_SLOT, (uint32_t)B_SLOT, fullB(bs));
+                bulk_g2s(smem_u32(sB + bs * B_SLOT), src + (i64)(ks0 + ks) * B_SLOT, (uint32_t)B_SLOT, fullB(bs));
             }
         }
     } else if (warp >= CTRL_WARPS) {
         // ===================== A producers =====================
         const int ptid = tid - CTRL_WARPS * 32;
         for (int ks = 0; ks < KS; ++ks) {
-            const int tap = ks / nkc, kc = ks - tap * nkc;
+            const int tap = (ks0 + ks) / nkc, kc = (ks0 + ks) - tap * nkc;
             for (int h = 0; h < MT; ++h) {
                 const int it = ks * MT + h, as = it % SA;
                 mbar_wait(emptyA(as), ((it / SA) & 1) ^ 1);
@@ -272,7 +277,8 @@ __global__ void __launch_bounds__((CTRL_WARPS + NPW) * 32, (MODE == IGEMM_DENSE 
         const bool mv = m < a.g.M;
         const int Nvalid = a.g.geo.Co;
         const bool vec_y = (a.g.ldY & 3) == 0, vec_e = (a.g.ldE & 3) == 0;
-        const bool has_e = a.g.epi == EPI_MUL || a.g.epi == EPI_ADD;
+        const bool has_e = (a.g.epi == EPI_MUL || a.g.epi == EPI_ADD) && blockIdx.z == 0;
+        float *Yz = a.g.Y + (i64)blockIdx.z * a.g.ysplit_stride;
         float4 ev[EP_MAXIT][4];
         if (has_e) {
 #pragma unroll
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__((CTRL_WARPS + NPW) * 32, (MODE == IGEMM_DENSE 
 #pragma unroll
                     for (int e = 0; e < 4; ++e) o[e] = a.g.epi == EPI_MUL ? o[e] * e4[e] : o[e] + e4[e];
                 }
-                float *yp = a.g.Y + m * (i64)a.g.ldY + n;
+                float *yp = Yz + m * (i64)a.g.ldY + n;
                 if (vec_y && n + 3 < Nvalid) {
                     *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);
                 } else {
@@ -374,12 +380,18 @@ int launch_tc(const TcArgs &a, int n_tiles, cudaStream_t st)
                         (MODE == IGEMM_DEFORM ? (size_t)SA * 128 * 64 : 0) + (size_t)MT * 128 * sizeof(RowInfo) +
                         (2 * SA + 2 * SB + 1) * 8 + 16 + 16 + 128 * sizeof(float) + 128;
     auto kern = tc_igemm_kernel<MODE, KC, MT, NPW, SA, SB>;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    // the attribute is per function and process-wide: keep a process-wide monotonic maximum (a thread_local cache let a second
+    // host thread -- e.g. the autograd engine's -- lower the limit under a launch that needs more)
+    static std::atomic<size_t> configured{0};
+    static std::mutex configure_lock;
+    if (smem > configured.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> guard(configure_lock);
+        if (smem > configured.load(std::memory_order_relaxed)) {
+            DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured.store(smem, std::memory_order_release);
+        }
     }
-    dim3 grid((unsigned)cdiv(a.g.M, MT * 128), (unsigned)n_tiles);
+    dim3 grid((unsigned)cdiv(a.g.M, MT * 128), (unsigned)n_tiles, (unsigned)(a.g.ksplit_steps ? cdiv(a.KS, a.g.ksplit_steps) : 1));
     const char *name = MODE == IGEMM_DENSE ? "tc_dense" : MODE == IGEMM_CONV ? "tc_conv" : "tc_deform";
     DLKA_LAUNCH(name, st, (kern<<<grid, (CTRL_WARPS + NPW) * 32, smem, st>>>(a)));
     return DLKA_OK;

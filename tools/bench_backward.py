@@ -53,3 +53,10 @@ if d3d is not None:
     out["reference_forward_ms"] = timed(lambda: d3d.deform_conv_forward(x, w, b, off, *g), args.steps)
     out["reference_backward_ms"] = timed(lambda: d3d.deform_conv_backward(x, w, b, off, gout, *g), args.steps)
 print(json.dumps(out))
+# per-kernel breakdown of one backward call (CUDA events inside the library)
+dl._lib.profile_enable(True)
+dl.ops.deform_conv3d_backward(x, w, b, off, gout, 3, 1, 1, 1, 1, 1, 64)
+torch.cuda.synchronize()
+prof = dl._lib.profile_summary()
+dl._lib.profile_enable(False)
+print(json.dumps({k: [v[0], round(v[1], 3)] for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}))
