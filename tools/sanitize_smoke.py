@@ -30,5 +30,16 @@ for math in ("bf16x3", "fp32"):
                                          torch.randn(1, 81, 5, 6, 7, device=dev) * 4, 3, 1, 1, 1, 1, 1)
         xh = torch.randn(2, 5 * 7 * 9, 32).pin_memory()
         y = m3.forward_host(xh, 2, 32, 5, 7, 9)
+        y = t3(torch.randn(1, 32, 5, 7, 9, device=dev)) if hasattr(t3, "forward") else None        # whole block incl. UnetResBlock (N3)
+        for dim, dims in ((32, (4, 9, 7)), (128, (3, 6, 5)), (256, (2, 4, 3))):                       # ACDC stencil shapes (N4)
+            ma = dl.acdc.LKA_Attention3d_deform(dim)
+            ma.spatial_gating_unit.deform_conv.conv_offset.bias.uniform_(-2, 2)
+            ma = ma.to(dev)
+            y = ma(torch.randn(1, dims[0] * dims[1] * dims[2], dim, device=dev), 1, dim, *dims)
+        dec = dl.MyDecoderLayer((5, 6), [32] * 5, 1, "mix_skip", n_class=9, is_last=True).to(dev)   # 2D decoder stage (N3)
+        y = dec(torch.randn(1, 30, 32, device=dev), torch.randn(1, 5, 6, 32, device=dev))
+        g = dl.ops.deform_conv3d_backward(x, torch.randn(32, 32, 3, 3, 3, device=dev), torch.randn(32, device=dev),   # N2
+                                          torch.randn(1, 81, 5, 6, 7, device=dev) * 4, torch.randn(1, 32, 5, 6, 7, device=dev),
+                                          3, 1, 1, 1, 1, 1)
     torch.cuda.synchronize()
     print("ok", math, flush=True)
