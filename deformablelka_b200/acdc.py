@@ -43,3 +43,25 @@ class LKA_Attention3d_deform(lka3d.LKA_Attention3d_deform):
         self.activation = nn.GELU()
         self.spatial_gating_unit = LKA3d_deform(d_model)
         self.proj_2 = nn.Conv3d(d_model, d_model, 1)
+
+
+def _transformer_block():
+    from .blocks import TransformerBlock_3D_single_deform_LKA as _Base
+
+    class TransformerBlock_3D_single_deform_LKA(_Base):
+        """acdc/transformerblock.py:146-207 -- the same block around the ACDC attention (same names, ctor, keys; the whole
+        forward is still one library call, the stencil shapes travel in dlkaDwGeom3d)."""
+
+        @staticmethod
+        def _attention_class():
+            return LKA_Attention3d_deform
+
+    return TransformerBlock_3D_single_deform_LKA
+
+
+def __getattr__(name):   # lazy: blocks.py imports lka3d, which must not import this module back at import time
+    if name == "TransformerBlock_3D_single_deform_LKA":
+        cls = _transformer_block()
+        globals()[name] = cls
+        return cls
+    raise AttributeError(name)

@@ -190,12 +190,16 @@ class TransformerBlock_3D_single_deform_LKA(nn.Module):
             raise ValueError("hidden_size should be divisible by num_heads.")
         self.norm = nn.LayerNorm(hidden_size)
         self.gamma = nn.Parameter(1e-6 * torch.ones(hidden_size), requires_grad=True)
-        self.epa_block = LKA_Attention3d_deform(d_model=hidden_size)
+        self.epa_block = self._attention_class()(d_model=hidden_size)
         self.conv51 = UnetResBlock(3, hidden_size, hidden_size, kernel_size=3, stride=1, norm_name="batch")
         self.conv8 = nn.Sequential(nn.Dropout3d(0.1, False), nn.Conv3d(hidden_size, hidden_size, 1))
         self.pos_embed = None
         if pos_embed:
             self.pos_embed = nn.Parameter(torch.zeros(1, input_size, hidden_size))
+
+    @staticmethod
+    def _attention_class():
+        return LKA_Attention3d_deform   # the ACDC network's block (acdc.py) swaps in its own stencil shapes
 
     def attention_half(self, x_tokens, B, C, H, W, D):
         """x' = x + pos_embed; x' + gamma * epa_block(norm(x'))  -- one library call (transformerblock.py:620-624)."""

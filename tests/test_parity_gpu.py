@@ -269,6 +269,33 @@ def test_block3d_acdc_vs_oracle(dl, oracle, C, dims, math):
     assert rel_err(got_l, ref_l) < TOL
 
 
+def test_transformer3d_whole_block_acdc_vs_oracle(dl, oracle, math):
+    """The ACDC network's transformer block (acdc/transformerblock.py:146-207): attention half with the ACDC stencil shapes,
+    UnetResBlock and conv8, one library call, against the oracle's block restatement with the ACDC attention swapped in."""
+    from deformablelka_b200 import acdc
+    torch.manual_seed(13)
+    C, (H, W, D) = 128, (3, 6, 5)
+    N = H * W * D
+    m = acdc.TransformerBlock_3D_single_deform_LKA(N, C, C, 4, pos_embed=True).eval()
+    assert isinstance(m.epa_block, acdc.LKA_Attention3d_deform)
+    oracle.randomize_offsets_(m)
+    with torch.no_grad():
+        m.gamma.uniform_(0.2, 1.0)
+        m.pos_embed.normal_(0, 0.5)
+        for bn in (m.conv51.norm1, m.conv51.norm2):
+            bn.running_mean.normal_(0, 0.2); bn.running_var.uniform_(0.5, 1.5); bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.2)
+    ref_attn = oracle.LKA_Attention3d_deform_ACDC(C).eval()
+    ref_attn.load_state_dict(m.epa_block.state_dict())
+    ref_res = oracle.UnetResBlock3D(C).eval()
+    ref_res.load_state_dict(m.conv51.state_dict())
+    x = torch.randn(2, C, H, W, D)
+    with torch.no_grad():
+        ref = oracle.transformer3d_block(m.norm, m.gamma, ref_attn, m.pos_embed, ref_res, m.conv8[1], x)
+        got = m.to(DEV)(x.to(DEV))
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < TOL
+
+
 def test_block3d_unsupported_stencil_is_loud(dl):
     """A stencil shape the library has no kernel for (k along axis 2 != axis 3) is refused, not approximated."""
     from deformablelka_b200 import acdc
