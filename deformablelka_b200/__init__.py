@@ -9,7 +9,7 @@ from ._lib import LIB_PATH, launch_count  # noqa: F401
 from .deform_conv3d import DeformConv as DeformConv3d, DeformConvFunction, DeformConvPack  # noqa: F401
 from .deformable_LKA import DeformConv, DeformConv2d, deformable_LKA, deformable_LKA_Attention  # noqa: F401
 from .lka3d import LKA3d_deform, LKA_Attention3d_deform  # noqa: F401
-from . import acdc  # noqa: F401  (ACDC variant of the 3D block: acdc.LKA3d_deform, acdc.LKA_Attention3d_deform)
+from . import acdc, sliding_window  # noqa: F401  (ACDC variant of the 3D block: acdc.LKA3d_deform, acdc.LKA_Attention3d_deform)
 from .blocks import (DWConvLKA, FinalPatchExpand_X4, Mlp, MyDecoderLayer, PatchExpand,  # noqa: F401
                      TransformerBlock_3D_single_deform_LKA, deformableLKABlock)
 

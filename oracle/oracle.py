@@ -501,6 +501,72 @@ class MyDecoderLayer(nn.Module):
         return self.layer_up(t)
 
 
+def sliding_window_predict_oracle(network, x, patch_size, num_classes, step_size=0.5, do_mirroring=True, mirror_axes=(0, 1, 2),
+                                  use_gaussian=True):
+    """numpy restatement of SegmentationNetwork._internal_predict_3D_3Dconv_tiled in its default (host aggregation, fp32)
+    mode (3D/d_lka_former/network_architecture/neural_network.py:292-428), with _compute_steps_for_sliding_window (:267-290),
+    _get_gaussian (:251-264) and _internal_maybe_mirror_and_pred_3D (:502-556) spelled out the way the reference writes them
+    (explicit loops, the eight mirror cases).  pad_nd_image is batchgenerators' (not in the reference tree): symmetric
+    constant padding, remainder above.  Returns (segmentation, class_probabilities)."""
+    import numpy as np
+    from scipy.ndimage import gaussian_filter
+    x = np.asarray(x, dtype=np.float32)
+    assert len(x.shape) == 4
+    new_shape = [max(a, b) for a, b in zip(x.shape[1:], patch_size)]
+    diff = [n - o for n, o in zip(new_shape, x.shape[1:])]
+    below = [d // 2 for d in diff]
+    above = [d // 2 + d % 2 for d in diff]
+    data = np.pad(x, [(0, 0)] + [(b, a) for b, a in zip(below, above)], mode="constant")
+    slicer = [slice(b, b + o) for b, o in zip(below, x.shape[1:])]
+    image_size = data.shape[1:]
+    target = [i * step_size for i in patch_size]
+    num_steps = [int(np.ceil((i - k) / j)) + 1 for i, j, k in zip(image_size, target, patch_size)]
+    steps = []
+    for dim in range(3):
+        max_step_value = image_size[dim] - patch_size[dim]
+        actual = max_step_value / (num_steps[dim] - 1) if num_steps[dim] > 1 else 99999999999
+        steps.append([int(np.round(actual * i)) for i in range(num_steps[dim])])
+    num_tiles = len(steps[0]) * len(steps[1]) * len(steps[2])
+    gaussian = None
+    if use_gaussian and num_tiles > 1:
+        tmp = np.zeros(patch_size)
+        tmp[tuple(i // 2 for i in patch_size)] = 1
+        gaussian = gaussian_filter(tmp, [i * (1. / 8) for i in patch_size], 0, mode="constant", cval=0)
+        gaussian = (gaussian / np.max(gaussian) * 1).astype(np.float32)
+        gaussian[gaussian == 0] = np.min(gaussian[gaussian != 0])
+    add = gaussian if gaussian is not None else np.ones(patch_size, dtype=np.float32)
+    agg = np.zeros([num_classes] + list(data.shape[1:]), dtype=np.float32)
+    nb = np.zeros([num_classes] + list(data.shape[1:]), dtype=np.float32)
+
+    def pred_one(patch):
+        xt = torch.from_numpy(np.ascontiguousarray(patch))
+        res = torch.zeros([1, num_classes] + list(xt.shape[2:]))
+        n = 2 ** len(mirror_axes) if do_mirroring else 1
+        cases = [((), True), ((4,), 2 in mirror_axes), ((3,), 1 in mirror_axes), ((4, 3), 2 in mirror_axes and 1 in mirror_axes),
+                 ((2,), 0 in mirror_axes), ((4, 2), 0 in mirror_axes and 2 in mirror_axes),
+                 ((3, 2), 0 in mirror_axes and 1 in mirror_axes),
+                 ((4, 3, 2), 0 in mirror_axes and 1 in mirror_axes and 2 in mirror_axes)]
+        for m, (dims, on) in enumerate(cases[:8 if do_mirroring else 1]):
+            if not on:
+                continue
+            with torch.no_grad():
+                p = torch.softmax(network(torch.flip(xt, dims) if dims else xt), 1)
+            res += 1 / n * (torch.flip(p, dims) if dims else p)
+        if gaussian is not None:
+            res[:, :] *= torch.from_numpy(gaussian)
+        return res[0].numpy()
+
+    for lx in steps[0]:
+        for ly in steps[1]:
+            for lz in steps[2]:
+                ux, uy, uz = lx + patch_size[0], ly + patch_size[1], lz + patch_size[2]
+                agg[:, lx:ux, ly:uy, lz:uz] += pred_one(data[None, :, lx:ux, ly:uy, lz:uz])
+                nb[:, lx:ux, ly:uy, lz:uz] += add
+    sl = tuple([slice(None)] + slicer)
+    probs = agg[sl] / nb[sl]
+    return probs.argmax(0), probs
+
+
 def randomize_offsets_(module: nn.Module, std: float = 0.05, bias_range: float = 1.0, seed: int = 0) -> None:
     """re-initialise the zero-initialised 3D ``conv_offset`` so offsets are non-trivial."""
     g = torch.Generator().manual_seed(seed)
