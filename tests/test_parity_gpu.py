@@ -601,3 +601,37 @@ def test_deform_conv3d_backward_refuses_groups(dl):
     with pytest.raises(RuntimeError):
         dl.ops.deform_conv3d_backward(x, w, torch.zeros(8, device=DEV), torch.zeros(1, 81, 3, 3, 3, device=DEV),
                                       torch.zeros(1, 8, 3, 3, 3, device=DEV), 3, 1, 1, 1, 2, 1)
+
+
+# ----------------------------------------------------------------------------- 1x1 projections at large M (generic kernel by
+# default; the persistent variant of dense_persist.cu when the library is built with -DDLKA_DENSE_PERSIST)
+@pytest.mark.parametrize("M,K,N,bias,add", [(20000, 96, 96, True, True), (19001, 64, 128, True, False), (40000, 32, 9, False, True),
+                                             (18944, 96, 81, True, False)])
+def test_linear_tokens_large_m_vs_torch(dl, M, K, N, bias, add, math):
+    """Many 128-row tiles per SM: ragged last tile, N not a multiple of 16, bias / residual epilogues."""
+    torch.manual_seed(40)
+    x = torch.randn(M, K)
+    w = torch.randn(N, K) * 0.2
+    b = torch.randn(N) if bias else None
+    e = torch.randn(M, N) if add else None
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double() if bias else None)
+    if add:
+        ref = ref + e.double()
+    got = dl.ops.linear_tokens_forward(x.to(DEV), w.to(DEV), b.to(DEV) if bias else None, add=e.to(DEV) if add else None)
+    assert got.shape == (M, N)
+    assert rel_err(got, ref.float()) < TOL
+
+
+def test_attention2d_medium_vs_oracle(dl, oracle, math):
+    """2 x 100 x 100 pixels = 20000 rows through proj_1 + GELU, conv1 * u and proj_2 + x."""
+    torch.manual_seed(41)
+    C, H, W = 32, 100, 100
+    ref_m = oracle.deformable_LKA_Attention(C).eval()
+    _scale_offset_nets(ref_m, 1.0)
+    m = dl.deformable_LKA_Attention(C)
+    m.load_state_dict(ref_m.state_dict())
+    x = torch.randn(2, C, H, W)
+    with torch.no_grad():
+        ref = ref_m(x)
+        got = m.to(DEV)(x.to(DEV))
+    assert rel_err(got, ref) < TOL
