@@ -8,10 +8,15 @@
 //   * a CTA owns a compact 4 x 4 x 8 brick of output voxels (128 MMA rows), not 128 consecutive voxels,
 //   * K is walked chunk-major: 32 channels (= one 128-byte line per voxel) over all taps, then the next 32,
 //     so the working set of a pass (brick + halo, one line per voxel, ~100 KB) stays in L1,
-//   * shared memory is kept under ~100 KB so the L1 carve-out is large.
-// Roles: warp 0 MMA issuer, warp 1 weight loader (cp.async.bulk), warps 4-7 sample-parameter producers
-// (positions, clamped corner offsets, masked trilinear weights: 64 B per (row, tap)) and later the epilogue,
-// warps 8-23 gather/blend/convert producers that fill the UMMA A slots.
+//   * shared memory is kept under ~136 KB so the L1 carve-out stays large.
+// Roles (default, L1 path): warp 0 MMA issuer, warp 1 weight loader (cp.async.bulk), warps 4-7 sample-parameter producers
+// (positions, clamped corner offsets, masked trilinear weights: 64 B per (row, tap)), warps 8-23 gather / blend / convert
+// producers that fill the UMMA A slots (two groups on alternate K steps); all 20 producer warps then run the fused
+// epilogue chain (+bias -> conv1 -> * u -> proj_2 -> + x on the accumulator tile).
+// -DDLKA_DF_REGION=1 builds the alternative gather path: brick + halo of a 32-channel chunk staged in shared memory by one
+// TMA tile copy, 8 gather warps with 168 registers (setmaxnreg), software-pipelined predicated shared / global corner
+// loads.  Correct (same tests) but measured slower (13.8 vs 12.3 ms): both paths end up bound by the SM's L1 / shared
+// data path, see DESIGN.md 4.  -DDF_TRACE-style clock64 stamps (deform3d_set_trace, tools/df_trace.py) show the pipeline.
 #include <cuda_bf16.h>
 
 #include <cstring>
