@@ -131,6 +131,16 @@ def _load() -> ctypes.CDLL:
         getattr(lib, name).argtypes = [c_void_p]
     lib.dlka_host_pipe_join.restype = c_int
     lib.dlka_host_pipe_join.argtypes = [c_void_p, c_void_p]
+    lib.dlka_host_pipe_slot_done.restype = c_int
+    lib.dlka_host_pipe_slot_done.argtypes = [c_void_p, c_int]
+    lib.dlka_host_numa_node.restype = c_int
+    lib.dlka_host_numa_node.argtypes = [c_int]
+    lib.dlka_host_bind_thread.restype = c_int
+    lib.dlka_host_bind_thread.argtypes = [c_int]
+    lib.dlka_host_alloc.restype = c_int
+    lib.dlka_host_alloc.argtypes = [POINTER(c_void_p), c_size_t, c_int, c_int]
+    lib.dlka_host_free.restype = c_int
+    lib.dlka_host_free.argtypes = [c_void_p]
     lib.dlka_lka_attention3d_deform_forward_host_async.restype = c_int
     lib.dlka_lka_attention3d_deform_forward_host_async.argtypes = (
         [c_void_p, POINTER(Block3dParams), V, V] + [I] * 6 + [V, c_size_t, V, c_size_t, V])

@@ -15,8 +15,14 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .deformable_LKA import _block2d_params, deformable_LKA_Attention
-from .lka3d import LKA_Attention3d_deform, _block3d_params
+from .deformable_LKA import _block2d_params, _refuse_autograd, deformable_LKA_Attention
+from .lka3d import LKA_Attention3d_deform, _block3d_params, needs_autograd
+
+
+def _pixel_shuffle_tokens(x, B, H, W, p):
+    """"b h w (p1 p2 c) -> b (h p1) (w p2) c" on tokens [B, H*W, p*p*c] (differentiable training path of the patch expansion)."""
+    c = x.shape[-1] // (p * p)
+    return x.view(B, H, W, p, p, c).permute(0, 1, 3, 2, 4, 5).reshape(B, H * p * W * p, c)
 
 
 class DWConvLKA(nn.Module):
@@ -61,6 +67,7 @@ class deformableLKABlock(nn.Module):
         self.layer_scale_2 = nn.Parameter(layer_scale_init_value * torch.ones((dim)), requires_grad=True)
 
     def forward(self, x, H, W):
+        _refuse_autograd(self, x, "deformableLKABlock")
         blk = {
             "norm1_weight": self.norm1.weight, "norm1_bias": self.norm1.bias, "layer_scale_1": self.layer_scale_1,
             "norm2_weight": self.norm2.weight, "norm2_bias": self.norm2.bias, "layer_scale_2": self.layer_scale_2,
@@ -86,6 +93,9 @@ class PatchExpand(nn.Module):
 
     def forward(self, x):
         H, W = self.input_resolution
+        if needs_autograd(self, x):   # training: stock layers, autograd sees expand / norm
+            assert x.shape[1] == H * W, "input feature has wrong size"
+            return self.norm(_pixel_shuffle_tokens(self.expand(x), x.shape[0], H, W, 2))
         return ops.patch_expand2d_forward(x, self.expand.weight, self.norm.weight, self.norm.bias, self.norm.eps, H, W, 2)
 
 
@@ -105,6 +115,9 @@ class FinalPatchExpand_X4(nn.Module):
 
     def forward(self, x):
         H, W = self.input_resolution
+        if needs_autograd(self, x):
+            assert x.shape[1] == H * W, "input feature has wrong size"
+            return self.norm(_pixel_shuffle_tokens(self.expand(x), x.shape[0], H, W, 4))
         return ops.patch_expand2d_forward(x, self.expand.weight, self.norm.weight, self.norm.bias, self.norm.eps, H, W, 4)
 
 
@@ -141,11 +154,17 @@ class MyDecoderLayer(nn.Module):
         if x2 is None:
             return self.layer_up(x1)
         b, h, w, c = x2.shape
-        cat_linear_x = ops.linear_tokens_forward(x1, self.x1_linear.weight, self.x1_linear.bias, add=x2.reshape(b, -1, c))
+        grad = needs_autograd(self, x1, x2)
+        if grad:   # the two deformableLKABlocks below refuse (2D operator has no backward); the linear parts are stock layers
+            cat_linear_x = self.x1_linear(x1) + x2.reshape(b, -1, c)
+        else:
+            cat_linear_x = ops.linear_tokens_forward(x1, self.x1_linear.weight, self.x1_linear.bias, add=x2.reshape(b, -1, c))
         t = self.layer_lka_2(self.layer_lka_1(cat_linear_x, h, w), h, w)
         if self.last_layer is None:
             return self.layer_up(t)
         up = self.layer_up(t)                                     # [b, 16*h*w, out_dim] tokens = NHWC
+        if grad:
+            return self.last_layer(up.view(b, 4 * h, 4 * w, -1).permute(0, 3, 1, 2))
         logits = ops.linear_tokens_forward(up, self.last_layer.weight.flatten(1), self.last_layer.bias)
         return logits.view(b, 4 * h, 4 * w, -1).permute(0, 3, 1, 2).contiguous()   # NCHW like nn.Conv2d's output
 
@@ -203,6 +222,8 @@ class TransformerBlock_3D_single_deform_LKA(nn.Module):
 
     def attention_half(self, x_tokens, B, C, H, W, D):
         """x' = x + pos_embed; x' + gamma * epa_block(norm(x'))  -- one library call (transformerblock.py:620-624)."""
+        if needs_autograd(self, x_tokens):
+            raise RuntimeError("attention_half is a fused inference entry and a gradient is required: use forward()")
         ep = self.epa_block
         return ops.lka_transformer3d_prenorm_forward(_block3d_params(ep.spatial_gating_unit, ep), self.norm.weight,
                                                      self.norm.bias, self.norm.eps, self.gamma, self.pos_embed, x_tokens,
@@ -218,7 +239,11 @@ class TransformerBlock_3D_single_deform_LKA(nn.Module):
         """The whole block on tokens [B, N, C] in ONE library call (rows N1 + N3): attention half, UnetResBlock
         (two 3x3x3 convs on tcgen05 with folded BatchNorm + LeakyReLU + residual) and conv8 + residual."""
         if self.training:
-            raise RuntimeError("deformablelka_b200 is a forward/inference build: call .eval() (BatchNorm / Dropout3d)")
+            raise RuntimeError("forward_tokens is the fused inference entry: call .eval() (BatchNorm / Dropout3d), or use "
+                               "forward(), which takes the differentiable path in training mode")
+        if needs_autograd(self, tokens):
+            raise RuntimeError("forward_tokens is the fused inference entry and a gradient is required: wrap it in "
+                               "torch.no_grad(), or use forward(), which takes the differentiable path")
         ep = self.epa_block
         s1, t1 = self._fold_bn(self.conv51.norm1)
         s2, t2 = self._fold_bn(self.conv51.norm2)
@@ -231,9 +256,22 @@ class TransformerBlock_3D_single_deform_LKA(nn.Module):
 
     def forward(self, x):
         B, C, H, W, D = x.shape
+        if self.training or needs_autograd(self, x):
+            return self.forward_autograd(x)
         tokens = x.reshape(B, C, H * W * D).permute(0, 2, 1).contiguous()          # (B, N, C): layout plumbing only
         out = self.forward_tokens(tokens, B, C, H, W, D)
         return out.reshape(B, H, W, D, C).permute(0, 4, 1, 2, 3)                    # (B, C, H, W, D) view, as the reference
+
+    def forward_autograd(self, x):
+        """Training / gradient path (transformerblock.py:617-630 composed from this module's own sub-modules): LayerNorm, the
+        attention block's differentiable composition (DeformConvFunction inside), BatchNorm / Dropout3d in their current mode."""
+        B, C, H, W, D = x.shape
+        t = x.reshape(B, C, H * W * D).permute(0, 2, 1)
+        if self.pos_embed is not None:
+            t = t + self.pos_embed
+        attn = t + self.gamma * self.epa_block(self.norm(t), B, C, H, W, D)
+        attn_skip = attn.reshape(B, H, W, D, C).permute(0, 4, 1, 2, 3)
+        return attn_skip + self.conv8(self.conv51(attn_skip))
 
     def forward_reference_tail(self, x):
         """Attention half native, UnetResBlock / conv8 through stock PyTorch layers (cross-check of row N3)."""

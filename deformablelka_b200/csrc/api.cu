@@ -48,21 +48,25 @@ int record_cuda_error(cudaError_t e, const char *what)
 
 namespace {
 
+// The CURRENT device must be an sm_100 part.  Only a positive answer is cached, per device ordinal (a transient
+// cudaGetDevice failure must not poison the thread, and one process may drive several devices).
 int check_device()
 {
-    static thread_local int cached = 1;  // 1 = unknown
-    if (cached != 1) return cached;
+    static std::atomic<int> ok[64];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return cached = record_cuda_error(e, "cudaGetDevice");
+    if (e != cudaSuccess) return record_cuda_error(e, "cudaGetDevice");
+    const bool cacheable = dev >= 0 && dev < 64;
+    if (cacheable && ok[dev].load(std::memory_order_relaxed)) return DLKA_OK;
     int major = 0;
     e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-    if (e != cudaSuccess) return cached = record_cuda_error(e, "cudaDeviceGetAttribute");
+    if (e != cudaSuccess) return record_cuda_error(e, "cudaDeviceGetAttribute");
     if (major != 10) {
         snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "device compute capability %d.x is not sm_100", major);
-        return cached = DLKA_ERR_NO_DEVICE;
+        return DLKA_ERR_NO_DEVICE;
     }
-    return cached = DLKA_OK;
+    if (cacheable) ok[dev].store(1, std::memory_order_relaxed);
+    return DLKA_OK;
 }
 
 IgemmArgs dense_args(const float *X, int ldX, i64 M, int Ci, int Co, const float *Wp, int Npad, const float *bias, int epi,
@@ -773,16 +777,21 @@ int dlka_lka_attention3d_deform_forward_host(const dlkaBlock3dParams *params, co
     float *xd = (float *)dev_scratch, *yd = xd + n;
     // Per-sample software pipeline over three streams: H2D of sample b+1 and D2H of sample b-1 overlap the compute of
     // sample b (samples are independent: SURVEY.md 8e).  Compute stays on the caller's stream.
-    static thread_local cudaStream_t s_in = nullptr, s_out = nullptr;
-    if (!s_in) {
-        DLKA_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-        DLKA_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    // the helper streams live for this (synchronous) call only: nothing is bound to whichever device was current first
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    DLKA_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    if (cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess) {
+        const cudaError_t ce = cudaGetLastError();
+        cudaStreamDestroy(s_in);
+        return record_cuda_error(ce, "cudaStreamCreateWithFlags");
     }
     const size_t n1 = n / B;
-    std::vector<cudaEvent_t> ev(2 * (size_t)B + 2);
-    for (auto &e : ev) DLKA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    std::vector<cudaEvent_t> ev(2 * (size_t)B + 2, nullptr);
     int rc = DLKA_OK;
+    for (auto &e : ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { e = nullptr; rc = DLKA_ERR_CUDA; break; }
     do {
+        if (rc != DLKA_OK) break;
         cudaEvent_t e_start = ev[2 * B], e_done = ev[2 * B + 1];
         if (cudaEventRecord(e_start, st) != cudaSuccess || cudaStreamWaitEvent(s_in, e_start, 0) != cudaSuccess ||
             cudaStreamWaitEvent(s_out, e_start, 0) != cudaSuccess) { rc = DLKA_ERR_CUDA; break; }
@@ -802,10 +811,15 @@ int dlka_lka_attention3d_deform_forward_host(const dlkaBlock3dParams *params, co
         if (rc != DLKA_OK) break;
         if (cudaEventRecord(e_done, s_out) != cudaSuccess || cudaStreamWaitEvent(st, e_done, 0) != cudaSuccess) rc = DLKA_ERR_CUDA;
     } while (0);
+    const cudaError_t first = rc == DLKA_ERR_CUDA ? cudaGetLastError() : cudaSuccess;
     const cudaError_t se = cudaStreamSynchronize(st);
     cudaStreamSynchronize(s_in);
     cudaStreamSynchronize(s_out);
-    for (auto &e : ev) cudaEventDestroy(e);
+    for (auto &e : ev)
+        if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(s_in);
+    cudaStreamDestroy(s_out);
+    if (rc == DLKA_ERR_CUDA && first != cudaSuccess) return record_cuda_error(first, "dlka_lka_attention3d_deform_forward_host");
     if (rc == DLKA_ERR_CUDA) return record_cuda_error(cudaGetLastError(), "dlka_lka_attention3d_deform_forward_host");
     if (rc != DLKA_OK) return rc;
     if (se != cudaSuccess) return record_cuda_error(se, "cudaStreamSynchronize");

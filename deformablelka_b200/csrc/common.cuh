@@ -4,6 +4,9 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/dlka.h"
 
 typedef long long i64;
@@ -54,6 +57,34 @@ struct KernelScope {
         int _s = (expr);                                                      \
         if (_s != DLKA_OK) return _s;                                         \
     } while (0)
+
+// Opt-in to more than 48 KB of dynamic shared memory.  cudaFuncAttributeMaxDynamicSharedMemorySize is kept per function AND
+// per device (context), so the cache is indexed by the current device ordinal: one process driving several GPUs
+// (nn.DataParallel, the reference 2D trainers' multi-GPU mode) configures each of them.  Monotonic and mutex-protected, so
+// a second host thread (the autograd engine's) can never lower the limit under a launch that needs more.
+struct SmemOptIn {
+    static constexpr int MAX_DEVICES = 64;
+    std::atomic<size_t> configured[MAX_DEVICES];
+    std::mutex lock;
+    template <typename Kern>
+    int ensure(Kern kern, size_t smem)
+    {
+        int dev = 0;
+        DLKA_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= MAX_DEVICES) {   // beyond the cache: set it every time (cheap)
+            DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            return DLKA_OK;
+        }
+        if (smem > configured[dev].load(std::memory_order_acquire)) {
+            std::lock_guard<std::mutex> guard(lock);
+            if (smem > configured[dev].load(std::memory_order_relaxed)) {
+                DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured[dev].store(smem, std::memory_order_release);
+            }
+        }
+        return DLKA_OK;
+    }
+};
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline i64 cdiv(i64 a, i64 b) { return (a + b - 1) / b; }

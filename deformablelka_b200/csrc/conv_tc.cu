@@ -321,15 +321,8 @@ int launch_ct(const ConvTileArgs &a, int n_tiles, cudaStream_t st)
     auto kern = conv_tiled_kernel<MT>;
     // the attribute is per function and process-wide: keep a process-wide monotonic maximum (a thread_local cache let a second
     // host thread -- e.g. the autograd engine's -- lower the limit under a launch that needs more)
-    static std::atomic<size_t> configured{0};
-    static std::mutex configure_lock;
-    if (smem > configured.load(std::memory_order_acquire)) {
-        std::lock_guard<std::mutex> guard(configure_lock);
-        if (smem > configured.load(std::memory_order_relaxed)) {
-            DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured.store(smem, std::memory_order_release);
-        }
-    }
+    static SmemOptIn optin;   // per launch site (= per kernel instantiation), per device
+    DLKA_TRY(optin.ensure(kern, smem));
     dim3 grid((unsigned)((i64)a.g.B * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)n_tiles);
     DLKA_LAUNCH("tc_conv_tiled", st, (kern<<<grid, (CT_CTRL_WARPS + CT_NPW) * 32, smem, st>>>(a)));
     return DLKA_OK;

@@ -712,15 +712,8 @@ int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, const DeformChain
     const size_t smem = df_smem_bytes(a.NT);
     // the attribute is per function and process-wide: keep a process-wide monotonic maximum (a thread_local cache let a second
     // host thread -- e.g. the autograd engine's -- lower the limit under a launch that needs more)
-    static std::atomic<size_t> configured{0};
-    static std::mutex configure_lock;
-    if (smem > configured.load(std::memory_order_acquire)) {
-        std::lock_guard<std::mutex> guard(configure_lock);
-        if (smem > configured.load(std::memory_order_relaxed)) {
-            DLKA_CUDA_TRY(cudaFuncSetAttribute(deform3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured.store(smem, std::memory_order_release);
-        }
-    }
+    static SmemOptIn optin;   // per launch site (= per kernel instantiation), per device
+    DLKA_TRY(optin.ensure(deform3d_tc_kernel, smem));
     dim3 grid((unsigned)((i64)g.B * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)n_tiles);
     CUtensorMap tmapX;
     memset(&tmapX, 0, sizeof(tmapX));

@@ -187,11 +187,8 @@ int launch_ds(const float *x, const float *wp, const float *bias, float *y, int 
     static_assert(PW * L <= 256 && PH * L <= 256, "TMA box extent");
     const size_t smem = ((size_t)KD * K * K * 8 + 2 * (size_t)PH * PW * 8) * sizeof(float4) + 64;
     auto kern = dwconv_smem_kernel<KD, K, LD, L, DS_TD, DS_TH, DS_TW, DS_R, VW>;
-    static thread_local bool configured = false;
-    if (!configured) {
-        DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static SmemOptIn optin;   // per template instance, per device
+    DLKA_TRY(optin.ensure(kern, smem));
     // tensor map of the channels-last activation; box = one plane of the lattice tile (32 channels x PW x PH voxels),
     // traversal stride L along w and h picks the sub-lattice of the CTA's phase
     CUtensorMap tmap;

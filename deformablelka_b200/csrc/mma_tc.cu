@@ -382,15 +382,8 @@ int launch_tc(const TcArgs &a, int n_tiles, cudaStream_t st)
     auto kern = tc_igemm_kernel<MODE, KC, MT, NPW, SA, SB>;
     // the attribute is per function and process-wide: keep a process-wide monotonic maximum (a thread_local cache let a second
     // host thread -- e.g. the autograd engine's -- lower the limit under a launch that needs more)
-    static std::atomic<size_t> configured{0};
-    static std::mutex configure_lock;
-    if (smem > configured.load(std::memory_order_acquire)) {
-        std::lock_guard<std::mutex> guard(configure_lock);
-        if (smem > configured.load(std::memory_order_relaxed)) {
-            DLKA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured.store(smem, std::memory_order_release);
-        }
-    }
+    static SmemOptIn optin;   // per launch site (= per kernel instantiation), per device
+    DLKA_TRY(optin.ensure(kern, smem));
     dim3 grid((unsigned)cdiv(a.g.M, MT * 128), (unsigned)n_tiles, (unsigned)(a.g.ksplit_steps ? cdiv(a.KS, a.g.ksplit_steps) : 1));
     const char *name = MODE == IGEMM_DENSE ? "tc_dense" : MODE == IGEMM_CONV ? "tc_conv" : "tc_deform";
     DLKA_LAUNCH(name, st, (kern<<<grid, (CTRL_WARPS + NPW) * 32, smem, st>>>(a)));

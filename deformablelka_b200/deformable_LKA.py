@@ -17,6 +17,16 @@ import torch.nn as nn
 from torch.nn.modules.utils import _pair
 
 from . import ops
+from .lka3d import needs_autograd
+
+
+def _refuse_autograd(module, x, what):
+    """The fused 2D entries have no backward: refuse instead of returning a tensor that is cut off from the graph."""
+    if needs_autograd(module, x):
+        raise RuntimeError(
+            f"{what}: the fused forward is inference-only and a gradient is required (grad mode is on and the input or a "
+            "parameter requires grad). Wrap the call in torch.no_grad() / call .requires_grad_(False) for inference; "
+            "training through the 2D deformable operator is not implemented in deformablelka_b200")
 
 
 class DeformConv2d(nn.Module):
@@ -46,6 +56,9 @@ class DeformConv2d(nn.Module):
             nn.init.uniform_(self.bias, -bound, bound)
 
     def forward(self, input, offset, mask=None):
+        _refuse_autograd(self, input, "DeformConv2d")
+        if offset.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError("DeformConv2d: offset requires grad, but the 2D deformable operator has no backward here")
         return ops.deform_conv2d(input, offset, self.weight, self.bias, self.stride, self.padding, self.dilation, mask)
 
 
@@ -60,6 +73,7 @@ class DeformConv(nn.Module):
                                         padding=padding, groups=groups, stride=stride, dilation=dilation, bias=False)
 
     def forward(self, x):
+        _refuse_autograd(self, x, "DeformConv")
         return ops.deform_conv_pack2d(x, self.offset_net.weight, self.offset_net.bias, self.deform_conv.weight,
                                       self.deform_conv.bias, self.deform_conv.stride, self.deform_conv.padding,
                                       self.deform_conv.dilation)
@@ -89,6 +103,7 @@ class deformable_LKA(nn.Module):
 
     def forward(self, x):
         # u * conv1(conv_spatial(conv0(x)))  in one library call (deformable_LKA.py:98-104)
+        _refuse_autograd(self, x, "deformable_LKA")
         return ops.deformable_lka2d_forward(_block2d_params(self), x)
 
 
@@ -102,4 +117,5 @@ class deformable_LKA_Attention(nn.Module):
 
     def forward(self, x):
         # proj_1 -> GELU -> gating unit -> proj_2 -> + shortcut (deformable_LKA.py:133-140)
+        _refuse_autograd(self, x, "deformable_LKA_Attention")
         return ops.deformable_lka_attention2d_forward(_block2d_params(self.spatial_gating_unit, self), x)

@@ -1,12 +1,29 @@
 """3D drop-in modules: ``LKA3d_deform`` and ``LKA_Attention3d_deform`` with the reference's names, ctor
 arguments and state_dict keys (3D/d_lka_former/network_architecture/synapse/transformerblock.py:634-673).
-Each forward is ONE call into libdlka_b200."""
+
+Inference (no gradient needed): each forward is ONE call into libdlka_b200.
+Training (grad enabled and the input or a parameter requires grad): the fused call has no backward, so the forward is
+composed the way the reference composes it -- stock ``nn.Conv3d`` layers around ``self.deform_conv``, whose
+``DeformConvFunction`` runs the library forward and ``dlka_deform_conv3d_backward`` -- and autograd sees every parameter.
+A fused module never returns a tensor that is silently cut off from the graph."""
 from __future__ import annotations
 
+import torch
 import torch.nn as nn
 
 from . import ops
 from .deform_conv3d import DeformConvPack
+
+
+def needs_autograd(module: nn.Module, *tensors) -> bool:
+    """True when a backward pass could be asked for: grad mode on and an input or a parameter of `module` requires grad.
+    The differentiable compositions are CUDA-only like everything else here (no CPU path, 3D/dcn/src/deform_conv.h:46)."""
+    if not torch.is_grad_enabled():
+        return False
+    need = any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in module.parameters())
+    if need and not all(t is None or t.is_cuda for t in tensors):
+        raise RuntimeError("Not implemented on the CPU (deformablelka_b200 is CUDA-only)")
+    return need
 
 
 def _block3d_params(lka: "LKA3d_deform", attn=None) -> dict:
@@ -36,6 +53,10 @@ class LKA3d_deform(nn.Module):
         self.conv1 = nn.Conv3d(dim, dim, 1)
 
     def forward(self, x):
+        if needs_autograd(self, x):
+            # differentiable composition (transformerblock.py:644-652); deform_conv routes to DeformConvFunction
+            attn = self.conv_spatial(self.conv0(x)).contiguous()
+            return x * self.conv1(self.deform_conv(attn))
         return ops.lka3d_deform_forward(_block3d_params(self), x)
 
 
@@ -48,6 +69,11 @@ class LKA_Attention3d_deform(nn.Module):
         self.proj_2 = nn.Conv3d(d_model, d_model, 1)
 
     def forward(self, x, B, C, H, W, D):
+        if needs_autograd(self, x):
+            # differentiable composition (transformerblock.py:664-673): tokens -> NCDHW view -> ... -> tokens
+            v = x.permute(0, 2, 1).reshape(B, C, H, W, D)
+            t = self.proj_2(self.spatial_gating_unit(self.activation(self.proj_1(v)))) + v
+            return t.reshape(B, C, H * W * D).permute(0, 2, 1)
         return ops.lka_attention3d_deform_forward(_block3d_params(self.spatial_gating_unit, self), x, B, C, H, W, D)
 
     def host_pipe(self, depth: int = 2):

@@ -365,9 +365,52 @@ def lka_transformer3d_block_forward(attn_params: dict, tail: dict, eps: float, s
     return y
 
 
+_NUMA_POLICY = {"off": 0, "local": 1, "interleave": 2}
+
+
+def host_numa_policy(policy=None) -> int:
+    """Placement of pinned host buffers: "local" (the device's NUMA node, default), "interleave" (all nodes) or "off";
+    the DLKA_HOST_NUMA environment variable overrides the default."""
+    import os
+    name = policy if policy is not None else os.environ.get("DLKA_HOST_NUMA", "local")
+    try:
+        return _NUMA_POLICY[str(name).lower()]
+    except KeyError:
+        raise ValueError(f"unknown host NUMA policy {name!r}; expected one of {sorted(_NUMA_POLICY)}")
+
+
+def bind_host_thread(device) -> int:
+    """Pin the calling host thread to the cores of `device`'s NUMA node (and prefer that node for its allocations).
+    Returns the node, or -1 when the topology is unknown (nothing changed)."""
+    device = torch.device(device)
+    return int(lib.dlka_host_bind_thread(device.index if device.index is not None else torch.cuda.current_device()))
+
+
+def pinned_empty(shape, device, policy=None) -> torch.Tensor:
+    """A page-locked fp32 host tensor placed for `device` (dlka_host_alloc: mbind before first touch + cudaHostRegister).
+    The memory is released when the tensor (and every view of it) is garbage-collected."""
+    import weakref
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    n = 1
+    for d in shape:
+        n *= int(d)
+    ptr = ctypes.c_void_p()
+    with torch.cuda.device(idx):
+        check(lib.dlka_host_alloc(ctypes.byref(ptr), max(n, 1) * 4, idx, host_numa_policy(policy)), "dlka_host_alloc")
+    buf = (ctypes.c_float * max(n, 1)).from_address(ptr.value)
+    t = torch.frombuffer(buf, dtype=torch.float32, count=n).view(*shape)
+    weakref.finalize(buf, lib.dlka_host_free, ptr)   # `buf` is kept alive by the tensor's storage
+    return t
+
+
 class HostPipe:
     """Streaming host-buffer pipeline (dlka_host_pipe_*): keeps `depth` steps in flight so that the H2D copy of the next
-    step and the D2H copy of the previous one overlap the compute of the current step."""
+    step and the D2H copy of the previous one overlap the compute of the current step.
+
+    Lifetime rules enforced here: every step's host tensors and contiguous parameter copies are held in a per-slot list
+    until that slot is reused (by then the library has ordered the new step after the old one's copies) or until wait();
+    the device staging buffer is never regrown while steps are in flight."""
 
     def __init__(self, device, depth: int = 2):
         self.device = torch.device(device)
@@ -376,22 +419,38 @@ class HostPipe:
         with torch.cuda.device(self.device):
             check(lib.dlka_host_pipe_create(ctypes.byref(self._h), depth), "dlka_host_pipe_create")
         self._scratch = None
-        self._keep = []
+        self._keep = [None] * depth
+        self._step = 0
 
     def submit(self, params: dict, x_host: torch.Tensor, y_host: torch.Tensor, B, C, H, W, D, math=None) -> None:
         assert x_host.device.type == "cpu" and y_host.device.type == "cpu" and x_host.is_contiguous() and y_host.is_contiguous()
         n = B * H * W * D * C
         need = self.depth * 2 * n * 4
         if self._scratch is None or self._scratch.numel() < need:
+            self.wait()                               # copies on the library's private streams may still use the old buffer
+            self._scratch = None
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        slot = self._step % self.depth
+        if self._keep[slot] is not None:
+            # the slot's previous step must have finished its D2H copy before its host tensors may be dropped
+            with torch.cuda.device(self.device):
+                while True:
+                    done = lib.dlka_host_pipe_slot_done(self._h, slot)
+                    if done < 0:
+                        check(done, "dlka_host_pipe_slot_done")
+                    if done:
+                        break
+                    torch.cuda.current_stream(self.device).synchronize()
+                    check(lib.dlka_host_pipe_wait(self._h), "dlka_host_pipe_wait")
         s, keep = _params_struct(Block3dParams, params)
-        self._keep = [keep, x_host, y_host]
         ws = Workspace.get(self.device, lib.dlka_lka_attention3d_deform_workspace_bytes(1, C, H, W, D))
         with torch.cuda.device(self.device):
             st = lib.dlka_lka_attention3d_deform_forward_host_async(
                 self._h, ctypes.byref(s), x_host.data_ptr(), y_host.data_ptr(), B, C, H, W, D, _math(math),
                 self._scratch.data_ptr(), self._scratch.numel(), ws.data_ptr(), ws.numel(), stream_ptr(self.device))
+        self._keep[slot] = [keep, x_host, y_host, ws]
         check(st, "dlka_lka_attention3d_deform_forward_host_async")
+        self._step += 1
 
     def join(self) -> None:
         """Order the current CUDA stream after every result copy enqueued so far (no host sync)."""
@@ -400,13 +459,14 @@ class HostPipe:
 
     def wait(self) -> None:
         with torch.cuda.device(self.device):
-            check(lib.dlka_host_pipe_wait(self._h), "dlka_host_pipe_wait")
             torch.cuda.current_stream(self.device).synchronize()
+            check(lib.dlka_host_pipe_wait(self._h), "dlka_host_pipe_wait")
+        self._keep = [None] * self.depth
 
     def __del__(self):
         try:
             if self._h:
-                lib.dlka_host_pipe_destroy(self._h)
+                lib.dlka_host_pipe_destroy(self._h)   # synchronises the private streams first
                 self._h = ctypes.c_void_p()
         except Exception:
             pass

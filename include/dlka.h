@@ -227,6 +227,19 @@ DLKA_API int dlka_lka_attention3d_deform_forward_host_async(dlkaHostPipe *pipe, 
                                                    const float *x_host, float *y_host, int B, int C, int D1, int D2,
                                                    int D3, int math, void *dev_scratch, size_t dev_scratch_bytes,
                                                    void *workspace, size_t workspace_bytes, void *stream);
+/* 1 when slot `slot` (= step index % depth) has finished its last D2H copy (its buffers may be released), 0 while in flight */
+DLKA_API int dlka_host_pipe_slot_done(dlkaHostPipe *pipe, int slot);
+
+/* Host-side placement for the `_host` entries (the reference's only multi-GPU mode is nn.DataParallel out of un-placed
+ * host tensors, 2D/trainer_MaxViT_deform_LKA.py:60-66; at 805 MB per direction per step the copy rate is the end-to-end rate).
+ * dlka_host_numa_node: NUMA node of CUDA device `device` from sysfs, -1 if unknown.
+ * dlka_host_bind_thread: pin the calling thread to that node's cores and prefer it for page allocation; returns the node or -1.
+ * dlka_host_alloc: page-locked buffer, policy 0 = no placement, 1 = on the device's node, 2 = interleaved over all nodes;
+ *                  mmap + mbind before first touch + cudaHostRegister(portable).  Release with dlka_host_free.           */
+DLKA_API int dlka_host_numa_node(int device);
+DLKA_API int dlka_host_bind_thread(int device);
+DLKA_API int dlka_host_alloc(void **ptr, size_t bytes, int device, int policy);
+DLKA_API int dlka_host_free(void *ptr);
 
 /* ------------------------------------------------------------------------------------------
  * Block: 2D D-LKA.

@@ -21,7 +21,7 @@ def _load_golden(path):
     return torch.from_numpy(z["x"]), torch.from_numpy(z["y"]), sd
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref2d_*.npz"))), ids=os.path.basename)
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref2d_*_s[0-9].npz"))), ids=os.path.basename)
 @pytest.mark.parametrize("impl", ["torchvision", "c"])
 def test_golden_2d_reference_module(oracle, path, impl):
     x, y, sd = _load_golden(path)

@@ -40,7 +40,7 @@ def math(request, monkeypatch):
 
 
 # ----------------------------------------------------------------------------- golden (reference 2D module)
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref2d_*.npz"))), ids=os.path.basename)
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref2d_*_s[0-9].npz"))), ids=os.path.basename)
 def test_golden_2d(dl, path, math):
     z = np.load(path)
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
@@ -89,7 +89,8 @@ def test_deform_conv2d_module_mirrors_torchvision_module(dl):
     mine = dl.DeformConv2d(8, 8, 3, padding=1, groups=8, bias=False)
     mine.load_state_dict(ref.state_dict())
     x = torch.randn(1, 8, 9, 9); off = torch.randn(1, 18, 9, 9)
-    assert rel_err(mine.to(DEV)(x.to(DEV), off.to(DEV)), ref(x, off)) < TOL
+    with torch.no_grad():
+        assert rel_err(mine.to(DEV)(x.to(DEV), off.to(DEV)), ref(x, off)) < TOL
 
 
 # ----------------------------------------------------------------------------- 3D operator vs oracle
@@ -302,7 +303,7 @@ def test_block3d_unsupported_stencil_is_loud(dl):
     m = acdc.LKA_Attention3d_deform(32).to(DEV)
     m.spatial_gating_unit.dw_geom = ((5, 5, 5), (1, 1, 1), (5, 7, 5), (3, 3, 3))
     x = torch.randn(1, 4 * 4 * 4, 32, device=DEV)
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError), torch.no_grad():
         m(x, 1, 32, 4, 4, 4)
 
 
@@ -335,7 +336,7 @@ def test_block3d_batch_shard_consistency_and_identity(dl, oracle, math):
 
 def test_streams_and_noncontiguous_inputs(dl):
     torch.manual_seed(12)
-    m = dl.deformable_LKA_Attention(16).to(DEV)
+    m = dl.deformable_LKA_Attention(16).to(DEV).requires_grad_(False)
     x = torch.randn(2, 16, 10, 12, device=DEV)
     y = m(x)
     s = torch.cuda.Stream()
@@ -539,8 +540,9 @@ def test_transformer3d_whole_block_vs_oracle(dl, oracle, C, dims, pos, math):
     assert got.shape == ref.shape
     assert rel_err(got, ref) < TOL
     assert rel_err(got_tail_torch, ref) < TOL
-    with pytest.raises(RuntimeError, match="eval"):
-        md.train()(x.to(DEV))
+    with pytest.raises(RuntimeError, match="eval"):   # the fused entry is inference-only ...
+        md.train().forward_tokens(x.to(DEV).reshape(2, C, N).permute(0, 2, 1).contiguous(), 2, C, H, W, D)
+    md.eval()
 
 
 # ----------------------------------------------------------------------------- row N2: backward of the 3D deformable conv
