@@ -4,6 +4,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -123,6 +124,16 @@ bool bad_geo(const ConvGeo &g)
            g.groups <= 0 || g.dg <= 0 || g.C % g.groups || g.Co % g.groups || g.C % g.dg || g.Do <= 0 || g.Ho <= 0 || g.Wo <= 0;
 }
 
+// DLKA_DEFORM_PS=0 selects the round-1 kernel (deform_tc.cu) for A/B measurements; both are product code paths with the same tests
+bool deform_ps_enabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("DLKA_DEFORM_PS");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 bool is_depthwise(const ConvGeo &g) { return g.groups == g.C && g.Co == g.C && g.C > 1; }
 
 // ---- workspace plans -------------------------------------------------------------------
@@ -153,6 +164,19 @@ int run_deform_op(const ConvGeo &g, const float *input, const float *weight, con
     DeformOpPlan p;
     if (!plan_deform_op(ar, g, mask != nullptr, p)) return DLKA_ERR_WORKSPACE;
     const i64 Vi = (i64)g.D * g.H * g.W, Vo = (i64)g.Do * g.Ho * g.Wo;
+    {
+        // 3D operator on the persistent kernel (deform_ps.cu): the NCDHW input is transposed straight into the chunk-major
+        // gather layout (same bytes as the channels-last copy it replaces)
+        IgemmArgs a = conv_args(IGEMM_DEFORM, g, p.x_cl, p.off_cl, nullptr, nullptr, 0, bias, EPI_NONE, nullptr, 0, p.y_cl, g.Co);
+        if (math == DLKA_MATH_BF16X3 && !mask && deform_ps_enabled() && deform3d_ps_supported(a, 0)) {
+            DLKA_TRY(transpose_cs_to_chunk(input, p.x_cl, g.B, g.C, Vi, st));
+            DLKA_TRY(deform3d_ps_pack(weight, p.wp, g.Co, g.C, g.K, st));
+            a.Off = offset;   // read in place: a warp's 32 brick rows are 4 runs of 8 consecutive voxels of the NCDHW tensor
+            DLKA_TRY(deform3d_ps(a, (i64)g.B * Vi * 32, p.wp, nullptr, 2, st));
+            DLKA_TRY(transpose_sc_to_cs(p.y_cl, output, g.B, g.Co, Vo, st));
+            return DLKA_OK;
+        }
+    }
     DLKA_TRY(transpose_cs_to_sc(input, p.x_cl, g.B, g.C, Vi, st));
     DLKA_TRY(transpose_cs_to_sc(offset, p.off_cl, g.B, g.dg * g.ndim * g.K, Vo, st));
     if (mask) DLKA_TRY(transpose_cs_to_sc(mask, p.mask_cl, g.B, g.dg * g.K, Vo, st));
@@ -182,7 +206,10 @@ bool plan_block3d(Arena &ar, int B, int C, int D1, int D2, int D3, Block3dPlan &
     p.t1 = ar.take<float>(M * C);
     p.t2 = ar.take<float>(M * C);
     p.t3 = ar.take<float>(M * C);
-    p.off = ar.take<float>(M * OFF3D_LD);
+    {   // offsets: [M][84] rows (round-1 kernels) or brick-major bricks x 81 x 128 (deform_ps.cu); ragged volumes pad the bricks
+        const size_t brick = deform3d_ps_offset_floats(B, D1, D2, D3, 81);
+        p.off = ar.take<float>(M * OFF3D_LD > brick ? M * OFF3D_LD : brick);
+    }
     p.wp_proj1 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
     p.wp_conv1 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
     p.wp_proj2 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
@@ -215,17 +242,48 @@ int run_lka3d_core(const dlkaBlock3dParams &P, const float *u, Block3dPlan &p, i
     if (bad_dw_geom(G)) return DLKA_ERR_UNSUPPORTED;
     DLKA_TRY(dwconv_cl(u, P.conv0_weight, P.conv0_bias, p.t2, B, C, D1, D2, D3, G.conv0_k[0], G.conv0_k[1], G.conv0_k[2],
                        G.conv0_dil[0], G.conv0_dil[1], p.wp_dw5, st));
-    DLKA_TRY(dwconv_cl(p.t2, P.conv_spatial_weight, P.conv_spatial_bias, p.t3, B, C, D1, D2, D3, G.conv_spatial_k[0],
-                       G.conv_spatial_k[1], G.conv_spatial_k[2], G.conv_spatial_dil[0], G.conv_spatial_dil[1], p.wp_dw7, st));
-    // conv_offset: Conv3d(C -> 81, k3, stride 1, pad 1)  (synapse/deform_conv.py:80-85)
+    // deformable 3x3x3 conv C -> C, groups 1, dg 1 (transformerblock.py:639); conv_offset: Conv3d(C -> 81, k3, stride 1, pad 1)
+    // (synapse/deform_conv.py:80-85)
     const ConvGeo go = make_geo(B, C, D1, D2, D3, 81, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3);
-    IgemmArgs ao = conv_args(IGEMM_CONV, go, p.t3, nullptr, nullptr, nullptr, 0, P.conv_offset_bias, EPI_NONE, nullptr, 0, p.off,
-                             OFF3D_LD);
-    DLKA_TRY(contraction(ao, P.conv_offset_weight, math, p.wp_off, st));
-    // deformable 3x3x3 conv C -> C, groups 1, dg 1 (transformerblock.py:639)
     const ConvGeo gd = make_geo(B, C, D1, D2, D3, C, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3);
     IgemmArgs ad = conv_args(IGEMM_DEFORM, gd, p.t3, p.off, nullptr, nullptr, 0, P.deform_bias, EPI_NONE, nullptr, 0, p.t2, C);
     ad.ldOff = OFF3D_LD;
+    IgemmArgs ao = conv_args(IGEMM_CONV, go, p.t3, nullptr, nullptr, nullptr, 0, P.conv_offset_bias, EPI_NONE, nullptr, 0, p.off,
+                             OFF3D_LD);
+    // persistent deformable kernel (deform_ps.cu): the large-kernel stencil writes its output CHUNK-MAJOR
+    // ([C/32][B][D][H][W][32]), which the offset conv and the deformable gather then read -- no extra pass over the tensor
+    const i64 xch = (i64)B * D1 * D2 * D3 * 32;
+    IgemmArgs ao_cm = ao;
+    ao_cm.xch = xch;
+    ao_cm.ybrick = 1;
+    const bool use_ps = math == DLKA_MATH_BF16X3 && deform_ps_enabled() && deform3d_ps_supported(ad, fuse_proj2 ? 2 : 1) &&
+                        dwconv_smem_supported(C, G.conv_spatial_k[0], G.conv_spatial_k[1], G.conv_spatial_k[2], G.conv_spatial_dil[0],
+                                              G.conv_spatial_dil[1], G.conv_spatial_dil[2]) &&
+                        conv_tiled_supported(ao_cm);
+    DLKA_TRY(dwconv_cl(p.t2, P.conv_spatial_weight, P.conv_spatial_bias, p.t3, B, C, D1, D2, D3, G.conv_spatial_k[0],
+                       G.conv_spatial_k[1], G.conv_spatial_k[2], G.conv_spatial_dil[0], G.conv_spatial_dil[1], p.wp_dw7, st, use_ps));
+    if (use_ps) {
+        DLKA_TRY(conv_tiled(ao_cm, P.conv_offset_weight, p.wp_off, st));
+        DeformChain ch;
+        memset(&ch, 0, sizeof(ch));
+        ch.stages = fuse_proj2 ? 2 : 1;
+        DLKA_TRY(deform3d_ps_pack(P.deform_weight, p.wp_dcn, C, C, 27, st));
+        DLKA_TRY(deform3d_ps_pack(P.conv1_weight, p.wp_conv1, C, C, 1, st));
+        ch.W1p = p.wp_conv1; ch.b1 = P.conv1_bias; ch.U = u; ch.ldU = C;
+        if (fuse_proj2) {
+            DLKA_TRY(deform3d_ps_pack(P.proj_2_weight, p.wp_proj2, C, C, 1, st));
+            ch.W2p = p.wp_proj2; ch.b2 = P.proj_2_bias; ch.R = resid; ch.ldR = C;
+            ad.Y = y_final;
+        } else {
+            ad.Y = p.t2;  // must not alias the gather source t3
+        }
+        DLKA_TRY(deform3d_ps(ad, xch, p.wp_dcn, &ch, 1, st));
+        if (!fuse_proj2) {
+            float *tmp = p.t2; p.t2 = p.t3; p.t3 = tmp;  // callers find the gate in p.t3
+        }
+        return fuse_proj2 ? 1 : DLKA_OK;
+    }
+    DLKA_TRY(contraction(ao, P.conv_offset_weight, math, p.wp_off, st));
     if (math == DLKA_MATH_BF16X3 && deform3d_chain_supported(ad)) {
         // deformable conv + conv1 + gate (+ proj_2 + shortcut) in ONE kernel: the 1x1 GEMMs run on the accumulator tile
         DeformChain ch;

@@ -41,15 +41,17 @@ constexpr int CT_LPAD = 64;        // bytes added to the plane stride (bank spre
 
 struct ConvTileArgs {
     ConvGeo g;
-    const float *X;      // [B][D][H][W][C]
+    const float *X;      // [B][D][H][W][C], or chunk-major [C/32][B][D][H][W][32] when xch != 0
+    i64 xch;             // floats between 32-channel chunks (0: channels-last)
     const uint8_t *Bp;   // packed weights [n_tiles][chunk][tap][hi|lo][plane 2][NT][8 bf16]
     const float *bias;   // [Co] or null
     int act;             // 0 none, 1 LeakyReLU(slope), 2 (+E) then LeakyReLU(slope)   (UnetResBlock, row N3)
     float slope;
     const float *E;      // residual operand [M][ldE] for act == 2
     int ldE;
-    float *Y;            // [M][ldY]
+    float *Y;            // [M][ldY], or brick-major [brick][Co][128] when ybrick (bricks of 4 x 4 x 8 output voxels)
     int ldY;
+    int ybrick, bt_d, bt_h, bt_w;   // brick grid extents
     int NT;              // N tile
     int MT;              // M tiles per CTA
     int RD, RH, RW;      // region extent (voxels)
@@ -159,12 +161,16 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
         // ===================== region producers =====================
         const int ptid = tid - CT_CTRL_WARPS * 32;
         const int rd0 = d0 - g.pd, rh0 = h0 - g.ph, rw0 = w0 - g.pw;  // region origin in input coordinates
-        const float *Xb = a.X + (i64)b * g.D * g.H * g.W * g.C;
+        // voxel stride / per-K-chunk base: channels-last (ldv = C, chunk c at + 16 c) or chunk-major (ldv = 32, 32-channel
+        // chunk c/2 at + (c/2) * xch, its second half at + 16)
+        const int ldv = a.xch ? 32 : g.C;
+        const float *Xb = a.X + (i64)b * g.D * g.H * g.W * ldv;
         const int units = RV * 4;  // (voxel, float4 of the 16-channel chunk)
         for (int c = 0; c < nchunks; ++c) {
             const int rb = c & 1;
             mbar_wait(emptyR(rb), ((c >> 1) & 1) ^ 1);
             uint8_t *buf = sR + rb * R_BUF;
+            const float *Xc = a.xch ? Xb + (i64)(c >> 1) * a.xch + (c & 1) * CT_KCH : Xb + c * CT_KCH;
             for (int u0 = ptid; u0 < units; u0 += 4 * NPT) {
                 float4 v[4];
                 int vox[4];
@@ -179,7 +185,7 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
                         const int x = vv % a.RW, y = (vv / a.RW) % a.RH, z = vv / (a.RW * a.RH);
                         const int di = rd0 + z, hi_ = rh0 + y, wi = rw0 + x;
                         if ((unsigned)di < (unsigned)g.D && (unsigned)hi_ < (unsigned)g.H && (unsigned)wi < (unsigned)g.W)
-                            v[s] = ldg4(Xb + (((i64)di * g.H + hi_) * g.W + wi) * g.C + c * CT_KCH + q * 4);
+                            v[s] = ldg4(Xc + (((i64)di * g.H + hi_) * g.W + wi) * ldv + q * 4);
                     }
                 }
 #pragma unroll
@@ -207,6 +213,10 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
             const int od = is3d ? d0 + t : 0, ohh = is3d ? h0 + oh : h0 + t * 16 + oh, oww = w0 + ow;
             const bool mv = od < g.Do && ohh < g.Ho && oww < g.Wo;
             const i64 m = (((i64)b * g.Do + od) * g.Ho + ohh) * g.Wo + oww;
+            // brick-major output: 32 consecutive lanes are 4 h-rows x 8 w of one brick slice = 32 consecutive floats per column
+            const i64 ybase = a.ybrick ? ((((i64)b * a.bt_d + (od >> 2)) * a.bt_h + (ohh >> 2)) * a.bt_w + (oww >> 3)) * (i64)g.Co * 128 +
+                                             ((od & 3) * 32 + (ohh & 3) * 8 + (oww & 7))
+                                       : 0;
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NT);
             for (int c0 = 0; c0 < NT; c0 += 16) {
                 float v[16];
@@ -231,6 +241,12 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
                         }
 #pragma unroll
                         for (int e = 0; e < 4; ++e) o[e] = o[e] > 0.f ? o[e] : a.slope * o[e];
+                    }
+                    if (a.ybrick) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (n + e < g.Co) a.Y[ybase + (i64)(n + e) * 128] = o[e];
+                        continue;
                     }
                     float *yp = a.Y + m * (i64)a.ldY + n;
                     if (vec_y && n + 3 < a.ldY) {
@@ -289,7 +305,10 @@ bool ct_plan(const IgemmArgs &g, ConvTileArgs &a)
     if (g.mode != IGEMM_CONV || geo.groups != 1 || geo.C % CT_KCH != 0) return false;
     if (geo.sd != 1 || geo.sh != 1 || geo.sw != 1) return false;
     if (g.epi != EPI_NONE) return false;
-    a.g = geo; a.X = g.X; a.bias = g.bias; a.Y = g.Y; a.ldY = g.ldY;
+    if (g.xch && geo.C % 32 != 0) return false;
+    if (g.ybrick && geo.ndim != 3) return false;
+    a.ybrick = g.ybrick; a.bt_d = (int)cdiv(geo.Do, 4); a.bt_h = (int)cdiv(geo.Ho, 4); a.bt_w = (int)cdiv(geo.Wo, 8);
+    a.g = geo; a.X = g.X; a.xch = g.xch; a.bias = g.bias; a.Y = g.Y; a.ldY = g.ldY;
     a.act = 0; a.slope = 0.f; a.E = nullptr; a.ldE = 0;
     a.NT = tc_nt(geo.Co);
     const bool is3d = geo.ndim == 3;

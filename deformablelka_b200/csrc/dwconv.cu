@@ -184,12 +184,13 @@ int launch_dw(const float *x, const float *wp, const float *bias, float *y, int 
 }  // namespace
 
 int dwconv_cl(const float *x, const float *w, const float *bias, float *y, int B, int C, int D, int H, int W, int kd,
-              int kh, int kw, int dd, int dil, float *w_packed, cudaStream_t st)
+              int kh, int kw, int dd, int dil, float *w_packed, cudaStream_t st, bool chunk_major_out)
 {
     if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
+    if (chunk_major_out && !dwconv_smem_supported(C, kd, kh, kw, dd, dil, dil)) return DLKA_ERR_UNSUPPORTED;
     if (kd < 1 || kh < 1 || kw < 1 || !(kd & 1) || !(kh & 1) || !(kw & 1) || dd < 1 || dil < 1) return DLKA_ERR_UNSUPPORTED;
     DLKA_TRY(pack_dw(w, w_packed, C, kd * kh * kw, st));
-    if (dwconv_smem_supported(C, kd, kh, kw, dd, dil, dil)) return dwconv_smem(x, w_packed, bias, y, B, C, D, H, W, kd, kh, dd, dil, st);
+    if (dwconv_smem_supported(C, kd, kh, kw, dd, dil, dil)) return dwconv_smem(x, w_packed, bias, y, B, C, D, H, W, kd, kh, dd, dil, st, chunk_major_out);
     if (C / 4 <= 256 && kh == kw && dd == dil && (kd == kh || kd == 1)) {
         if (kh == 5 && dil == 1) return launch_dw<5, 1, 4>(x, w_packed, bias, y, B, C, D, H, W, kd, st);
         if (kh == 7 && dil == 3) return launch_dw<7, 3, 4>(x, w_packed, bias, y, B, C, D, H, W, kd, st);

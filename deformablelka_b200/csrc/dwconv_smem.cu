@@ -67,7 +67,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int KD, int K, int LD, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R, int VW>
 __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
     dwconv_smem_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ wp, const float *__restrict__ bias,
-                       float *__restrict__ y, int C, int D, int H, int W, int tiles_d, int tiles_h, int tiles_w)
+                       float *__restrict__ y, int C, int D, int H, int W, int tiles_d, int tiles_h, int tiles_w, i64 ych, int yldv)
 {
     typedef DsVec<VW> V;
     typedef typename V::T vec;
@@ -173,15 +173,19 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
             for (int r = 0; r < DS_R; ++r) {
                 const int wrr = pw_ + L * (zw0 + wr * DS_R + r);
                 if (wrr < W)
-                    *reinterpret_cast<vec *>(y + ((((i64)b * D + dr) * H + hr) * W + wrr) * C + c0 + q * VW) = acc[t][r];
+                    *reinterpret_cast<vec *>(y + (i64)chunk * ych + ((((i64)b * D + dr) * H + hr) * W + wrr) * yldv + q * VW) = acc[t][r];
             }
         }
     }
 }
 
 template <int KD, int K, int LD, int L, int DS_TD, int DS_TH, int DS_TW, int DS_R, int VW>
-int launch_ds(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, cudaStream_t st)
+int launch_ds(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, cudaStream_t st, bool cm)
 {
+    // output addressing: y + chunk * ych + voxel * yldv + channel-in-chunk.  channels-last: ych = 32, yldv = C;
+    // chunk-major [C/32][B][D][H][W][32] (the gather layout of deform_ps.cu): ych = B*D*H*W*32, yldv = 32
+    const i64 ych = cm ? (i64)B * D * H * W * DS_CCH : DS_CCH;
+    const int yldv = cm ? DS_CCH : C;
     constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;
     constexpr int DS_THREADS = (DS_CCH / VW) * (DS_TW / DS_R) * DS_TH;
     static_assert(PW * L <= 256 && PH * L <= 256, "TMA box extent");
@@ -199,7 +203,7 @@ int launch_ds(const float *x, const float *wp, const float *bias, float *y, int 
     dim3 grid((unsigned)(tiles_d * tiles_h * tiles_w), (unsigned)(LD * L * L * (C / DS_CCH)), (unsigned)B);
     if (grid.y > 65535u || grid.z > 65535u) return DLKA_ERR_UNSUPPORTED;
     DLKA_LAUNCH(KD == 5 && K == 5 ? "dwconv3d_smem_k5" : KD == 7 ? "dwconv3d_smem_k7d3" : "dwconv3d_smem_aniso", st,
-                (kern<<<grid, DS_THREADS, smem, st>>>(tmap, wp, bias, y, C, D, H, W, tiles_d, tiles_h, tiles_w)));
+                (kern<<<grid, DS_THREADS, smem, st>>>(tmap, wp, bias, y, C, D, H, W, tiles_d, tiles_h, tiles_w, ych, yldv)));
     return DLKA_OK;
 }
 
@@ -215,15 +219,15 @@ bool dwconv_smem_supported(int C, int kd, int kh, int kw, int dd, int dh, int dw
 
 // wp: packed [taps][C] weights (pack_dw layout)
 int dwconv_smem(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, int kd, int k,
-                int dd, int dil, cudaStream_t st)
+                int dd, int dil, cudaStream_t st, bool cm)
 {
     if (kd == 5 && k == 5 && dd == 1 && dil == 1)
-        return launch_ds<5, 5, 1, 1, DLKA_DS5_TD, DLKA_DS5_TH, DLKA_DS5_TW, DLKA_DS5_R, DLKA_DS5_VW>(x, wp, bias, y, B, C, D, H, W, st);
+        return launch_ds<5, 5, 1, 1, DLKA_DS5_TD, DLKA_DS5_TH, DLKA_DS5_TW, DLKA_DS5_R, DLKA_DS5_VW>(x, wp, bias, y, B, C, D, H, W, st, cm);
     if (kd == 7 && k == 7 && dd == 3 && dil == 3)
-        return launch_ds<7, 7, 3, 3, DLKA_DS7_TD, DLKA_DS7_TH, DLKA_DS7_TW, DLKA_DS7_R, DLKA_DS7_VW>(x, wp, bias, y, B, C, D, H, W, st);
-    if (kd == 5 && k == 7 && dd == 3 && dil == 3) return launch_ds<5, 7, 3, 3, 2, 15, 22, 11, 2>(x, wp, bias, y, B, C, D, H, W, st);
-    if (kd == 3 && k == 5 && dd == 1 && dil == 3) return launch_ds<3, 5, 1, 3, 4, 16, 16, 8, 2>(x, wp, bias, y, B, C, D, H, W, st);
-    if (kd == 3 && k == 3 && dd == 1 && dil == 1) return launch_ds<3, 3, 1, 1, 4, 16, 16, 8, 2>(x, wp, bias, y, B, C, D, H, W, st);
+        return launch_ds<7, 7, 3, 3, DLKA_DS7_TD, DLKA_DS7_TH, DLKA_DS7_TW, DLKA_DS7_R, DLKA_DS7_VW>(x, wp, bias, y, B, C, D, H, W, st, cm);
+    if (kd == 5 && k == 7 && dd == 3 && dil == 3) return launch_ds<5, 7, 3, 3, 2, 15, 22, 11, 2>(x, wp, bias, y, B, C, D, H, W, st, cm);
+    if (kd == 3 && k == 5 && dd == 1 && dil == 3) return launch_ds<3, 5, 1, 3, 4, 16, 16, 8, 2>(x, wp, bias, y, B, C, D, H, W, st, cm);
+    if (kd == 3 && k == 3 && dd == 1 && dil == 1) return launch_ds<3, 3, 1, 1, 4, 16, 16, 8, 2>(x, wp, bias, y, B, C, D, H, W, st, cm);
     return DLKA_ERR_UNSUPPORTED;
 }
 

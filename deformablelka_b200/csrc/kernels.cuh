@@ -18,6 +18,7 @@ struct IgemmArgs {
     int Npad;          // padded columns of Wp per group
     const float *X;    // input, channels-last; dense: row stride ldX
     int ldX;
+    i64 xch;           // 0: X is channels-last [voxel][C]; else X is CHUNK-MAJOR [C/32][voxel][32] with xch floats between chunks
     const float *Off;  // deformable: offsets [M][ldOff], first dg*ndim*K columns used
     int ldOff;         // row stride of Off (0 = dg*ndim*K)
     const float *Mask; // deformable 2D (DCNv2) modulation [M][dg*K] or null
@@ -27,6 +28,7 @@ struct IgemmArgs {
     int ldE;
     float *Y;          // output [M][ldY]
     int ldY;
+    int ybrick;        // conv_tiled, 3D only: write Y BRICK-MAJOR [brick = (b, d/4, h/4, w/8)][Co][128 rows] (the offsets of deform_ps.cu)
     // split-K (tcgen05 dense path only): grid.z slices of `ksplit_steps` K steps each write partial products to
     // Y + z * ysplit_stride (bias / epilogue operand applied by slice 0 only); 0 = no split
     int ksplit_steps;
@@ -60,6 +62,14 @@ bool deform3d_tc_supported(const IgemmArgs &a);
 bool deform3d_chain_supported(const IgemmArgs &a);
 int deform3d_tc(const IgemmArgs &a, const float *w, void *bp, const DeformChain *chain, cudaStream_t st);
 
+// persistent variant with a chunk-major gather source, double-buffered accumulators and the 1x1 chain fed from tensor memory
+// (deform_ps.cu).  Weights (main and chain) are packed once with deform3d_ps_pack; X / xch as in IgemmArgs::xch.
+bool deform3d_ps_supported(const IgemmArgs &a, int chain_stages);
+size_t deform3d_ps_packed_bytes(int Co, int C, int taps);
+int deform3d_ps_pack(const float *w, void *bp, int Co, int C, int taps, cudaStream_t st);
+int deform3d_ps(const IgemmArgs &a, i64 xch, const void *bp, const DeformChain *chain, int off_mode, cudaStream_t st);
+size_t deform3d_ps_offset_floats(int B, int D, int H, int W, int cols);   // brick-major offset buffer (off_mode 1)
+
 // zero-copy tiled regular conv on tcgen05 (stride 1, groups 1, no epilogue operand) -- conv_tc.cu
 bool conv_tiled_supported(const IgemmArgs &a);
 size_t conv_tiled_packed_bytes(int Co, int C, int taps);
@@ -71,17 +81,20 @@ int conv_tiled_ex(const IgemmArgs &a, const float *w, const float *wscale, int a
 // [B][C][S] -> [B][S][C]  and back (S = spatial size)
 int transpose_cs_to_sc(const float *in, float *out, int B, int C, i64 S, cudaStream_t st);
 int transpose_sc_to_cs(const float *in, float *out, int B, int C, i64 S, cudaStream_t st);
+// [B][C][S] -> chunk-major [C/32][B][S][32] (C % 32 == 0)
+int transpose_cs_to_chunk(const float *in, float *out, int B, int C, i64 S, cudaStream_t st);
 
 // ---------------- depthwise (regular) conv, channels-last, "same" output extent, stride 1 ----------
 // w: PyTorch layout [C][1][kd][kh][kw]; bias [C] or null.  pad = dil*(k-1)/2 on each axis.
 // dd / dil: dilation along d / along h and w (the ACDC variant of the block is anisotropic, acdc/transformerblock.py:214-236)
+// chunk_major_out: write y as [C/32][B][D][H][W][32] (only with the shared-memory variant; DLKA_ERR_UNSUPPORTED otherwise)
 int dwconv_cl(const float *x, const float *w, const float *bias, float *y, int B, int C, int D, int H, int W, int kd,
-              int kh, int kw, int dd, int dil, float *w_packed /*[K][C]*/, cudaStream_t st);
+              int kh, int kw, int dd, int dil, float *w_packed /*[K][C]*/, cudaStream_t st, bool chunk_major_out = false);
 
 // shared-memory plane-streaming variant (C % 32 == 0; the five stencil shapes of the synapse / acdc blocks) -- dwconv_smem.cu
 bool dwconv_smem_supported(int C, int kd, int kh, int kw, int dd, int dh, int dw);
 int dwconv_smem(const float *x, const float *w_packed, const float *bias, float *y, int B, int C, int D, int H, int W, int kd, int k,
-                int dd, int dil, cudaStream_t st);
+                int dd, int dil, cudaStream_t st, bool chunk_major_out = false);
 
 // ---------------- depthwise deformable conv (groups == C == Co), channels-last ----------------------
 // w: [C][1][taps] PyTorch layout; Off [M][dg*ndim*K]; Mask optional; bias optional.

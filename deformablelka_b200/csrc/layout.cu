@@ -26,6 +26,26 @@ __global__ void transpose_cs_sc_kernel(const float *__restrict__ in, float *__re
     }
 }
 
+// in [B][C][S] -> out CHUNK-MAJOR [C/32][B][S][32] (the gather layout of deform_ps.cu); C % 32 == 0, blockIdx.y = chunk
+__global__ void transpose_cs_chunk_kernel(const float *__restrict__ in, float *__restrict__ out, int B, int C, i64 S)
+{
+    __shared__ float tile[32][33];
+    const i64 b = blockIdx.z;
+    const i64 s0 = (i64)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const float *src = in + b * C * S;
+    float *dst = out + ((i64)blockIdx.y * B + b) * S * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const i64 s = s0 + threadIdx.x;
+        if (s < S) tile[i][threadIdx.x] = src[(i64)(c0 + i) * S + s];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const i64 s = s0 + i;
+        if (s < S) dst[s * 32 + threadIdx.x] = tile[threadIdx.x][i];
+    }
+}
+
 __global__ void transpose_sc_cs_kernel(const float *__restrict__ in, float *__restrict__ out, int C, i64 S)
 {
     __shared__ float tile[32][33];
@@ -83,6 +103,15 @@ int transpose_cs_to_sc(const float *in, float *out, int B, int C, i64 S, cudaStr
     if (B <= 0 || C <= 0 || S <= 0) return DLKA_OK;
     dim3 block(32, 8), grid((unsigned)cdiv(S, 32), (unsigned)cdiv(C, 32), (unsigned)B);
     DLKA_LAUNCH("transpose_cs_sc", st, transpose_cs_sc_kernel<<<grid, block, 0, st>>>(in, out, C, S));
+    return DLKA_OK;
+}
+
+int transpose_cs_to_chunk(const float *in, float *out, int B, int C, i64 S, cudaStream_t st)
+{
+    if (B <= 0 || C <= 0 || S <= 0) return DLKA_OK;
+    if (C % 32 != 0) return DLKA_ERR_UNSUPPORTED;
+    dim3 block(32, 8), grid((unsigned)cdiv(S, 32), (unsigned)(C / 32), (unsigned)B);
+    DLKA_LAUNCH("transpose_cs_chunk", st, transpose_cs_chunk_kernel<<<grid, block, 0, st>>>(in, out, B, C, S));
     return DLKA_OK;
 }
 

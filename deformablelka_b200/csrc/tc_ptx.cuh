@@ -109,6 +109,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same with the A operand read from tensor memory (M = 128: lane = row, each 32-bit column holds two consecutive bf16 K
+// elements, low half first; a K = 16 slice is 8 columns) -- written there by tcgen05.st from the row-owning threads
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
@@ -138,6 +151,37 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// registers -> tensor memory: thread t of the warp writes lane (warp % 4) * 32 + t, 4 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// read-only 16-byte global load that does not allocate in L1 (streaming operands next to an L1-resident working set)
+__device__ __forceinline__ float4 ldg4_stream(const float *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// 32-byte read-only global load (LDG.E.256 on sm_100): a[0..3] the low 16 bytes, b[0..3] the high 16 bytes
+__device__ __forceinline__ void ldg8(const void *p, float4 &a, float4 &b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+// mbarrier wait with an explicit sleep between polls: for roles that wait for a large part of a tile (the epilogue warps),
+// so that their polling does not take issue slots and shared-memory cycles from the gather warps
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
 }
 
 // ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout) ----

@@ -637,3 +637,30 @@ def test_attention2d_medium_vs_oracle(dl, oracle, math):
         ref = ref_m(x)
         got = m.to(DEV)(x.to(DEV))
     assert rel_err(got, ref) < TOL
+
+
+def test_numa_placed_pinned_buffers_and_pipe_slot_lifetime(dl, oracle):
+    """ops.pinned_empty (dlka_host_alloc: mbind + cudaHostRegister) returns page-locked memory that the host pipe can stream
+    from / to; steps with different batch sizes share a slot (the slot's "inputs consumed" event is per step, not per batch
+    index); the pipe survives dropping every caller-side reference to the host tensors right after submit."""
+    torch.manual_seed(42)
+    C, H, W, D = 32, 6, 8, 5
+    m = dl.LKA_Attention3d_deform(C)
+    oracle.randomize_offsets_(m)
+    m = m.to(DEV)
+    assert dl.ops.bind_host_thread(DEV) >= -1
+    pipe = m.host_pipe(depth=2)
+    outs, refs = [], []
+    with torch.no_grad():
+        for step, B in enumerate((3, 1, 2, 3, 1)):
+            x = dl.ops.pinned_empty((B, H * W * D, C), DEV)
+            assert x.is_pinned()
+            x.normal_()
+            y = dl.ops.pinned_empty((B, H * W * D, C), DEV)
+            refs.append(m(x.to(DEV), B, C, H, W, D).cpu())
+            m.submit_host(pipe, x, y, B, C, H, W, D)
+            outs.append(y)
+            del x, y
+        pipe.wait()
+    for got, ref in zip(outs, refs):
+        assert torch.equal(got, ref)

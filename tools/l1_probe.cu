@@ -12,6 +12,10 @@ constexpr int BUF_LINES = 512;  // 64 KB per SM: L1 resident
 // mode 2: LDG.64, 16 lanes per line (2 lines / instr)     mode 3: LDS.128, 8 lanes per line   mode 4: LDS.32 one line
 // mode 5: LDG.128 all 32 lanes within ONE 512-byte span (4 consecutive lines)
 // mode 6: LDS.128 warp-uniform address (broadcast)        mode 7: LDS.128, 4 distinct 16-byte addresses (one per 8 lanes)
+// mode 8: LDG.256 (ld.global.nc.v8.f32), 4 lanes per line (8 random lines / instr)
+// mode 9: LDG.256, 8 lanes per 256-byte pair of ADJACENT lines (4 random pairs / instr: the x0 / x1 corners of a sample
+//         when the volume is laid out [chunk][d][h][w][32 ch])
+// mode 10: LDG.128, 16 lanes per adjacent line pair (2 random pairs / instr)
 template <int MODE>
 __global__ void __launch_bounds__(THREADS) probe(const float *__restrict__ g, long long *cycles, float *sink)
 {
@@ -34,6 +38,9 @@ __global__ void __launch_bounds__(THREADS) probe(const float *__restrict__ g, lo
         if (MODE == 7) line = ((h >> 8) + (lane >> 3) * 37u) % BUF_LINES;
         int within = MODE == 0 || MODE == 3 || MODE == 5 ? (lane & 7) * 4 : (MODE == 2 ? (lane & 15) * 2 : lane);
         if (MODE == 6 || MODE == 7) within = 4 * ((h >> 4) & 7);
+        if (MODE == 8) { line = ((h >> 8) + (lane >> 2) * 37u) % BUF_LINES; within = (lane & 3) * 8; }
+        if (MODE == 9) { line = (((h >> 8) + (lane >> 3) * 37u) % (BUF_LINES / 2)) * 2; within = (lane & 7) * 8; }
+        if (MODE == 10) { line = (((h >> 8) + (lane >> 4) * 37u) % (BUF_LINES / 2)) * 2; within = (lane & 15) * 4; }
         off[i] = line * 32 + within;
     }
     // warm L1
@@ -45,8 +52,13 @@ __global__ void __launch_bounds__(THREADS) probe(const float *__restrict__ g, lo
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
         for (int i = 0; i < NOFF; ++i) {
-            const int o = (off[i] + it * 32 * 5) & (BUF_LINES * 32 - 1);
-            if (MODE == 0 || MODE == 5) { const float4 v = __ldg(reinterpret_cast<const float4 *>(base + o)); acc += (v.x + v.y) + (v.z + v.w); }
+            const int o = (off[i] + it * 32 * (MODE == 9 || MODE == 10 ? 6 : 5)) & (BUF_LINES * 32 - 1);
+            if (MODE == 8 || MODE == 9) {
+                float a, b, c, d, e, f, g2, h2;
+                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=f"(a), "=f"(b), "=f"(c), "=f"(d), "=f"(e), "=f"(f), "=f"(g2), "=f"(h2) : "l"(base + o));
+                acc += ((a + b) + (c + d)) + ((e + f) + (g2 + h2));
+            } else if (MODE == 0 || MODE == 5 || MODE == 10) { const float4 v = __ldg(reinterpret_cast<const float4 *>(base + o)); acc += (v.x + v.y) + (v.z + v.w); }
             else if (MODE == 1) acc += __ldg(base + o);
             else if (MODE == 2) { const float2 v = __ldg(reinterpret_cast<const float2 *>(base + o)); acc += v.x + v.y; }
             else if (MODE == 3 || MODE == 6 || MODE == 7) { const float4 v = *reinterpret_cast<const float4 *>(sm + o); acc += (v.x + v.y) + (v.z + v.w); }
@@ -89,6 +101,9 @@ int main()
     cudaMalloc(&cyc, sizeof(long long) * nsm);
     run<0>("LDG.128  8 lanes/line, 4 random lines", 4, g, cyc, sink, nsm);
     run<5>("LDG.128  4 consecutive lines", 4, g, cyc, sink, nsm);
+    run<10>("LDG.128 16 lanes / adjacent line pair, 2 pairs", 4, g, cyc, sink, nsm);
+    run<8>("LDG.256  4 lanes/line, 8 random lines", 8, g, cyc, sink, nsm);
+    run<9>("LDG.256  8 lanes / adjacent line pair, 4 pairs", 8, g, cyc, sink, nsm);
     run<2>("LDG.64  16 lanes/line, 2 random lines", 2, g, cyc, sink, nsm);
     run<1>("LDG.32  32 lanes, 1 line", 1, g, cyc, sink, nsm);
     run<3>("LDS.128  8 lanes/line, 4 random lines", 4, g, cyc, sink, nsm);
