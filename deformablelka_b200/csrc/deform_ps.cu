@@ -43,7 +43,7 @@ constexpr int PS_SA = 3, PS_SB = 3, PS_SP = 4;
 constexpr int PS_LBO = 2048 + 32;          // A plane (8 channels x 128 rows) stride, padded to spread banks
 constexpr int PS_APLANE = (PS_KC / 8) * PS_LBO;
 constexpr int PS_ASLOT = 2 * PS_APLANE;    // hi + lo
-constexpr int PS_PREC = 48;                // parameter record: int4 pair offsets + float4 weights (low-w side) + float4 (high-w side)
+constexpr int PS_PREC = 32;                // parameter record: {base|flags, wx0, base|flags, wx1} + float4 (d, h) weight products
 constexpr int PS_GROUPS = 2;               // gather warp groups on alternate K steps
 constexpr int PS_GW = 8;                   // warps per gather group
 constexpr int PS_PARAM_WARPS = 4, PS_EPI_WARPS = 4;
@@ -72,6 +72,7 @@ struct DeformPsArgs {
     int NT;              // N tile (multiple of 16, <= 128; chain: == C == Co <= 96)
     int chain;           // 0: Y = conv + bias; 1: Y = (conv1(conv + bias) + b1) * U; 2: Y = proj_2(that) + b2 + R
     int tiles_d, tiles_h, tiles_w, ntiles;
+    int vec32;           // Y / U / R rows are 32-byte aligned: 32-byte epilogue accesses
     int KS, S1, S2;      // K steps per tile; main-loop positions at which the previous tile's chain stages are issued
 };
 
@@ -94,8 +95,13 @@ __device__ __forceinline__ void ps_tile_coords(const DeformPsArgs &a, int tile, 
 __device__ __forceinline__ void ps_make_params(const ConvGeo &g, const PsRow &ri, int ii, int jj, int kk, float od, float oh, float ow,
                                                uint8_t *rec)
 {
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);   // BYTE offsets of the 4 (d, h) line pairs inside the (chunk, sample) volume
-    float4 wl = f4zero(), wh = f4zero();
+    // record: word0 = byte offset of the (d0, h0) pair | bit 0: the h1 row differs (+ W*128) | bit 1: the d1 plane differs;
+    // wx0 / wx1 = w-interpolation weight of the pair's low / high side; p = the four (d, h) weight products.  A gather lane reads
+    // 8 B ({word0, wx of its side}) + 16 B (p) and forms its 4 corner weights as p * wx -- the same products, in the same order,
+    // as the reference's hd*hh*hw (cuh:67-68).
+    uint32_t word0 = 0u;
+    float wx0 = 0.f, wx1 = 0.f;
+    float4 pp = f4zero();
     if (ri.m >= 0) {
         const float pd = sample_pos(ri.d, g.sd, g.pd, ii, g.dd, od);
         const float ph = sample_pos(ri.h, g.sh, g.ph, jj, g.dh, oh);
@@ -111,19 +117,17 @@ __device__ __forceinline__ void ps_make_params(const ConvGeo &g, const PsRow &ri
             const float fh0 = s.lo[1] >= 0 ? hh : 0.f, fh1 = s.lo[1] + 1 <= g.H - 1 ? lh : 0.f;
             const float fxl = s.lo[2] >= 0 ? hw : 0.f, fxh = s.lo[2] + 1 <= g.W - 1 ? lw : 0.f;   // corner at lo / at lo + 1
             // side 0 reads voxel xb, side 1 voxel xb + 1
-            const float wx0 = (xb == s.lo[2] ? fxl : 0.f) + (xb == s.lo[2] + 1 ? fxh : 0.f);
-            const float wx1 = (xb + 1 == s.lo[2] ? fxl : 0.f) + (xb + 1 == s.lo[2] + 1 ? fxh : 0.f);
-            const uint32_t sH = (uint32_t)g.W * 128u, sD = (uint32_t)g.H * sH, ox = (uint32_t)xb * 128u;
-            o.x = d0 * sD + h0 * sH + ox; o.y = d0 * sD + h1 * sH + ox;
-            o.z = d1 * sD + h0 * sH + ox; o.w = d1 * sD + h1 * sH + ox;
-            const float p00 = fd0 * fh0, p01 = fd0 * fh1, p10 = fd1 * fh0, p11 = fd1 * fh1;   // (d, h) products first: cuh:67-68
-            wl = make_float4(p00 * wx0, p01 * wx0, p10 * wx0, p11 * wx0);
-            wh = make_float4(p00 * wx1, p01 * wx1, p10 * wx1, p11 * wx1);
+            wx0 = (xb == s.lo[2] ? fxl : 0.f) + (xb == s.lo[2] + 1 ? fxh : 0.f);
+            wx1 = (xb + 1 == s.lo[2] ? fxl : 0.f) + (xb + 1 == s.lo[2] + 1 ? fxh : 0.f);
+            const uint32_t sH = (uint32_t)g.W * 128u, sD = (uint32_t)g.H * sH;
+            word0 = ((uint32_t)d0 * sD + (uint32_t)h0 * sH + (uint32_t)xb * 128u) | (h1 != h0 ? 1u : 0u) | (d1 != d0 ? 2u : 0u);
+            pp = make_float4(fd0 * fh0, fd0 * fh1, fd1 * fh0, fd1 * fh1);   // (d, h) products first: cuh:67-68
         }
     }
-    *reinterpret_cast<uint4 *>(rec) = o;
-    *reinterpret_cast<float4 *>(rec + 16) = wl;
-    *reinterpret_cast<float4 *>(rec + 32) = wh;
+    // structure of arrays inside a stage: [128 x {word0, wx0, word0, wx1}] then [128 x p] -- both 16-byte stores are then
+    // bank-conflict free across the warp's 32 rows
+    *reinterpret_cast<uint4 *>(rec) = make_uint4(word0, __float_as_uint(wx0), word0, __float_as_uint(wx1));
+    *reinterpret_cast<float4 *>(rec + 128 * 16) = pp;
 }
 
 __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const DeformPsArgs a)
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
                 }
                 const int ps = gp % PS_SP;
                 mbar_wait(emptyP(ps), ((gp / PS_SP) & 1) ^ 1);
-                ps_make_params(g, ri, ii, jj, kk, od, oh, ow, sPrm + (ps * 128 + r) * PS_PREC);
+                ps_make_params(g, ri, ii, jj, kk, od, oh, ow, sPrm + ps * 128 * PS_PREC + r * 16);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(fullP(ps));
                 od = nod; oh = noh; ow = now;
@@ -318,14 +322,15 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
         const int l8 = ggt & 7, side = l8 >> 2, q8 = l8 & 3;   // q8: which 8-channel slice of the 32-channel line
         const int row0 = ggt >> 3;                              // 0..31
         const int tiles_per_sample = a.tiles_d * a.tiles_h * a.tiles_w;
+        const uint32_t sHb = (uint32_t)g.W * 128u, sDb = (uint32_t)g.H * sHb;   // byte strides of the h / d axes in the gather source
         const char *Xl = reinterpret_cast<const char *>(a.X) + l8 * 32;   // lanes 4..7 land on the next line (+128 B)
         const uint32_t boff0 = (uint32_t)(q8 * PS_LBO + side * 8);         // A operand: plane q8, channels 4*side .. +3 of its 8
         int i = 0, ks = grp;                                   // local tile, K step inside it (this group's first step)
         while (ks >= KS) { ks -= KS; ++i; }
+        int b = ((int)blockIdx.x + i * (int)gridDim.x) / tiles_per_sample;
         for (uint32_t gk = grp; i < ntl; gk += PS_GROUPS) {
             int chunk = 0;
             for (int t = ks; t >= K; t -= K) ++chunk;
-            const int b = ((int)blockIdx.x + i * (int)gridDim.x) / tiles_per_sample;
             const char *base = Xl + ((i64)chunk * a.xch + (i64)b * vol32) * 4;
             const int as = gk % PS_SA, ps = gk % PS_SP;
             mbar_wait(fullP(ps), (gk / PS_SP) & 1);
@@ -334,11 +339,14 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int row = row0 + u * 32;
-                const uint8_t *rec = sPrm + (ps * 128 + row) * PS_PREC;
-                const uint4 o = *reinterpret_cast<const uint4 *>(rec);
-                const float4 w = *reinterpret_cast<const float4 *>(rec + 16 + side * 16);
+                const uint8_t *rec = sPrm + ps * 128 * PS_PREC + row * 16;
+                const uint2 ow = *reinterpret_cast<const uint2 *>(rec + side * 8);     // {base | flags, wx of this side}
+                const float4 pp = *reinterpret_cast<const float4 *>(rec + 128 * 16);
+                const uint32_t o00 = ow.x & ~3u, dh = (ow.x & 1u) ? sHb : 0u, dd = (ow.x & 2u) ? sDb : 0u;
+                const float wx = __uint_as_float(ow.y);
+                const float4 w = make_float4(pp.x * wx, pp.y * wx, pp.z * wx, pp.w * wx);
                 float4 a0, b0, a1, b1, a2, b2, a3, b3;
-                ldg8(base + o.x, a0, b0); ldg8(base + o.y, a1, b1); ldg8(base + o.z, a2, b2); ldg8(base + o.w, a3, b3);
+                ldg8(base + o00, a0, b0); ldg8(base + (o00 + dh), a1, b1); ldg8(base + (o00 + dd), a2, b2); ldg8(base + (o00 + dd + dh), a3, b3);
                 if (u == 3) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(emptyP(ps));    // parameters consumed
@@ -360,7 +368,10 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
             __syncwarp();
             if (lane == 0) mbar_arrive(fullA(as));
             ks += PS_GROUPS;
-            while (ks >= KS) { ks -= KS; ++i; }
+            if (ks >= KS) {
+                while (ks >= KS) { ks -= KS; ++i; }
+                b = ((int)blockIdx.x + i * (int)gridDim.x) / tiles_per_sample;
+            }
         }
     } else if (warp >= 8 + PS_GROUPS * PS_GW) {
         // =============================================== epilogue: one thread per accumulator row ===============================================
@@ -380,7 +391,9 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
             const float *rp = a.R ? a.R + (i64)(live ? ro.m : 0) * a.ldR : nullptr;
             auto store_y = [&](int c0, const float(&o)[8]) {
                 if (!live) return;
-                if (vec_y && c0 + 7 < g.Co) {
+                if (a.vec32 && c0 + 7 < g.Co) {
+                    stg8(yp + c0, o);
+                } else if (vec_y && c0 + 7 < g.Co) {
                     *reinterpret_cast<float4 *>(yp + c0) = make_float4(o[0], o[1], o[2], o[3]);
                     *reinterpret_cast<float4 *>(yp + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
                 } else {
@@ -418,7 +431,11 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
             tc_fence_after();
             for (int c0 = 0; c0 < NT; c0 += 8) {
                 float v[8], o[8];
-                const float4 u0 = live ? ldg4_stream(up + c0) : f4zero(), u1 = live ? ldg4_stream(up + c0 + 4) : f4zero();
+                float4 u0 = f4zero(), u1 = f4zero();
+                if (live) {
+                    if (a.vec32) ldg8_stream(up + c0, u0, u1);
+                    else { u0 = ldg4_stream(up + c0); u1 = ldg4_stream(up + c0 + 4); }
+                }
                 tmem_ld8(tX + c0, v);
                 const float uv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
@@ -436,7 +453,11 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
                 tc_fence_after();
                 for (int c0 = 0; c0 < NT; c0 += 8) {
                     float v[8], o[8];
-                    const float4 r0 = live ? ldg4_stream(rp + c0) : f4zero(), r1 = live ? ldg4_stream(rp + c0 + 4) : f4zero();
+                    float4 r0 = f4zero(), r1 = f4zero();
+                    if (live) {
+                        if (a.vec32) ldg8_stream(rp + c0, r0, r1);
+                        else { r0 = ldg4_stream(rp + c0); r1 = ldg4_stream(rp + c0 + 4); }
+                    }
                     tmem_ld8(tX + c0, v);
                     const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -540,6 +561,10 @@ int deform3d_ps(const IgemmArgs &ga, i64 xch, const void *bp, const DeformChain 
     a.S1 = a.KS / 8 + 2 < a.KS - 1 ? a.KS / 8 + 2 : a.KS - 1;
     a.S2 = a.KS / 2 > a.S1 ? a.KS / 2 : a.S1;
     if (a.S2 > a.KS - 1) a.S2 = a.KS - 1;
+    {
+        auto al32 = [](const void *p, int ld) { return p == nullptr || (((uintptr_t)p & 31) == 0 && (ld & 7) == 0); };
+        a.vec32 = al32(a.Y, a.ldY) && al32(a.U, a.ldU) && al32(a.R, a.ldR) && (g.Co & 7) == 0;
+    }
     const size_t smem = ps_smem_bytes(a.NT);
     static SmemOptIn optin;
     DLKA_TRY(optin.ensure(deform3d_ps_kernel, smem));

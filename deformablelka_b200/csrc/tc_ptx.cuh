@@ -177,6 +177,20 @@ __device__ __forceinline__ void ldg8(const void *p, float4 &a, float4 &b)
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p));
 }
+// 32-byte streaming load (no L1 allocation) / 32-byte store: the epilogue rows of deform_ps.cu (one line touched per lane and
+// instruction, so the wider access halves the L1TEX wavefronts of that traffic)
+__device__ __forceinline__ void ldg8_stream(const void *p, float4 &a, float4 &b)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg8(void *p, const float (&o)[8])
+{
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
+                 "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                 : "memory");
+}
 // mbarrier wait with an explicit sleep between polls: for roles that wait for a large part of a tile (the epilogue warps),
 // so that their polling does not take issue slots and shared-memory cycles from the gather warps
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity)
