@@ -49,8 +49,13 @@ constexpr int PS_GW = 8;                   // warps per gather group
 constexpr int PS_PARAM_WARPS = 4, PS_EPI_WARPS = 4;
 constexpr int PS_THREADS = (4 + PS_PARAM_WARPS + PS_GROUPS * PS_GW + PS_EPI_WARPS) * 32;   // 896
 constexpr int PS_BD = 4, PS_BH = 4, PS_BW = 8;   // output brick = 128 MMA rows
-constexpr int PS_ACC_STRIDE = 128;         // tensor-memory columns between the two accumulator buffers
-constexpr int PS_TM_X = 256, PS_TM_A = 384, PS_TM_COLS = 512;
+// Tensor-memory map (512 columns).  Every GEMM stage is "N-stacked": D[:, 0:NT) accumulates hi*hi + lo*hi and D[:, NT:2NT) the
+// cross term hi*lo, produced by ONE MMA with N = 2 NT over the weight rows [hi | lo] plus one MMA with N = NT (A lo x W hi):
+// 4 MMAs per K step instead of 6 and 34 KB instead of 42 KB of operand reads.  The epilogue adds the two halves.
+//   accumulator buffers at columns 0 and S (S = 192 for NT <= 96, 256 for NT = 128), each 2 NT wide; with the chain (NT <= 96)
+//   the A operand (bf16 hi | lo, NT columns) sits at 384, and the chain's GEMM output X reuses the accumulator buffer of the
+//   tile being drained (free once stage 0 has read it).
+constexpr int PS_TM_A = 384, PS_TM_COLS = 512;
 
 struct DeformPsArgs {
     ConvGeo g;
@@ -60,8 +65,8 @@ struct DeformPsArgs {
     i64 off_cs;          //   brick-major (conv_tiled, off_mode 1): row_term = tile*3K*128 + r, off_cs = 128
     int off_mode;        //   NCDHW operator input (off_mode 2): row_term = b*3K*S + voxel, off_cs = S;  [M][ld] rows (0): m*ld, 1
     int ldOff;
-    const uint8_t *Bp;   // [chunk][tap][hi|lo][4 planes][NT][8 bf16]
-    const uint8_t *W1p;  // [chunk][hi|lo][4 planes][NT][8 bf16]   (chain)
+    const uint8_t *Bp;   // [chunk][tap][4 planes][hi NT rows | lo NT rows][8 bf16]
+    const uint8_t *W1p;  // [chunk][4 planes][hi | lo][8 bf16]   (chain)
     const uint8_t *W2p;
     const float *bias, *b1, *b2;
     const float *U;      // gate operand [M][ldU]      (chain >= 1)
@@ -135,7 +140,8 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
     extern __shared__ __align__(128) uint8_t smem[];
     const ConvGeo &g = a.g;
     const int NT = a.NT;
-    const int B_PLANE = (PS_KC / 8) * NT * 16, B_SLOT = 2 * B_PLANE;
+    const int B_LBO = 2 * NT * 16, B_SLOT = (PS_KC / 8) * B_LBO;   // weight plane (8 channels) = NT hi rows then NT lo rows
+    const uint32_t acc_stride = NT > 96 ? 256u : 192u;
     uint8_t *sA = smem;
     uint8_t *sB = sA + PS_SA * PS_ASLOT;
     uint8_t *sPrm = sB + PS_SB * B_SLOT;                                    // [SP][128][48 B]
@@ -186,25 +192,23 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
     if (warp == 0) {
         // =============================================== MMA issuer ===============================================
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_bf16(128, NT);
+            const uint32_t idesc = make_idesc_bf16(128, NT), idesc2 = make_idesc_bf16(128, 2 * NT);
             uint32_t ga = 0, gb = 0;   // running A-slot / B-slot counters
-            auto chain_stage = [&](int stage, int j) {   // stage of local tile j: X = A(tmem) * W(stage)
+            auto chain_stage = [&](int stage, int j) {   // stage of local tile j: X = A(tmem) * W(stage), into tile j's drained buffer
                 mbar_wait(stage == 1 ? barE1 : barE2, (uint32_t)j & 1u);
                 tc_fence_after();
+                const uint32_t xacc = tmem_base + (uint32_t)(j & 1) * acc_stride;
                 for (int c = 0; c < nchunks; ++c, ++gb) {
                     const int bs = gb % PS_SB;
                     mbar_wait(fullB(bs), (gb / PS_SB) & 1);
                     tc_fence_after();
-                    const uint32_t bhi = smem_u32(sB + bs * B_SLOT), blo = bhi + B_PLANE;
+                    const uint32_t bsl = smem_u32(sB + bs * B_SLOT);
+                    const uint32_t a_hi = tmem_base + PS_TM_A + (uint32_t)(c * (PS_KC / 2)), a_lo = a_hi + (uint32_t)(g.C / 2);
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t acol = tmem_base + PS_TM_A + (pass == 1 ? (uint32_t)(g.C / 2) : 0u) + (uint32_t)(c * (PS_KC / 2));
-                        const uint32_t bb = pass == 2 ? blo : bhi;
-#pragma unroll
-                        for (int kk = 0; kk < PS_KC / 16; ++kk) {
-                            const uint64_t bd = make_smem_desc(bb + kk * 2 * NT * 16, NT * 16, 128);
-                            umma_bf16_ts(tmem_base + PS_TM_X, acol + kk * 8, bd, idesc, (c | pass | kk) != 0 ? 1u : 0u);
-                        }
+                    for (int kk = 0; kk < PS_KC / 16; ++kk) {
+                        const uint64_t bd = make_smem_desc(bsl + kk * 2 * B_LBO, B_LBO, 128);
+                        umma_bf16_ts(xacc, a_hi + kk * 8, bd, idesc2, (c | kk) != 0 ? 1u : 0u);   // [hi*hi | hi*lo]
+                        umma_bf16_ts(xacc, a_lo + kk * 8, bd, idesc, 1u);                          // += lo*hi
                     }
                     umma_commit(emptyB(bs));
                 }
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
                 const int buf = i & 1;
                 if (i >= 2) mbar_wait(accEmpty(buf), (uint32_t)((i >> 1) - 1) & 1u);   // epilogue of tile i-2 has drained acc[buf]
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * PS_ACC_STRIDE);
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * acc_stride;
                 for (int ks = 0; ks < KS; ++ks, ++ga, ++gb) {
                     if (a.chain && i > 0 && ks == a.S1) chain_stage(1, i - 1);
                     if (a.chain == 2 && i > 0 && ks == a.S2) chain_stage(2, i - 1);
@@ -223,16 +227,13 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
                     mbar_wait(fullA(as), (ga / PS_SA) & 1);
                     tc_fence_after();
                     const uint32_t ahi = smem_u32(sA + as * PS_ASLOT), alo = ahi + PS_APLANE;
-                    const uint32_t bhi = smem_u32(sB + bs * B_SLOT), blo = bhi + B_PLANE;
+                    const uint32_t bsl = smem_u32(sB + bs * B_SLOT);
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t ab = pass == 1 ? alo : ahi, bb = pass == 2 ? blo : bhi;
-#pragma unroll
-                        for (int kk = 0; kk < PS_KC / 16; ++kk) {
-                            const uint64_t ad = make_smem_desc(ab + kk * 2 * PS_LBO, PS_LBO, 128);
-                            const uint64_t bd = make_smem_desc(bb + kk * 2 * NT * 16, NT * 16, 128);
-                            umma_bf16(d_tmem, ad, bd, idesc, (ks | pass | kk) != 0 ? 1u : 0u);
-                        }
+                    for (int kk = 0; kk < PS_KC / 16; ++kk) {
+                        const uint64_t bd = make_smem_desc(bsl + kk * 2 * B_LBO, B_LBO, 128);
+                        const uint64_t ad_hi = make_smem_desc(ahi + kk * 2 * PS_LBO, PS_LBO, 128), ad_lo = make_smem_desc(alo + kk * 2 * PS_LBO, PS_LBO, 128);
+                        umma_bf16(d_tmem, ad_hi, bd, idesc2, (ks | kk) != 0 ? 1u : 0u);   // N = 2 NT: [hi*hi | hi*lo]
+                        umma_bf16(d_tmem, ad_lo, bd, idesc, 1u);                          // N = NT:   += lo*hi
                     }
                     umma_commit(emptyA(as));
                     umma_commit(emptyB(bs));
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
         // =============================================== epilogue: one thread per accumulator row ===============================================
         const int q = warp & 3, row = q * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint32_t tA_hi = tlane + PS_TM_A, tA_lo = tA_hi + (uint32_t)(g.C / 2), tX = tlane + PS_TM_X;
+        const uint32_t tA_hi = tlane + PS_TM_A, tA_lo = tA_hi + (uint32_t)(g.C / 2);
         const bool vec_y = (a.ldY & 3) == 0;
         for (int i = 0; i < ntl; ++i) {
             const int buf = i & 1;
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
             tc_fence_after();
             const PsRow ro = sRow[buf * 128 + row];
             const bool live = ro.m >= 0;
-            const uint32_t tacc = tlane + (uint32_t)(buf * PS_ACC_STRIDE);
+            const uint32_t tacc = tlane + (uint32_t)buf * acc_stride, tX = tacc;   // the chain's X lives in this tile's drained buffer
             float *yp = a.Y + (i64)(live ? ro.m : 0) * a.ldY;
             const float *up = a.U ? a.U + (i64)(live ? ro.m : 0) * a.ldU : nullptr;
             const float *rp = a.R ? a.R + (i64)(live ? ro.m : 0) * a.ldR : nullptr;
@@ -411,20 +412,18 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
             };
             // ---- stage 0: deformable-conv accumulator + bias ----
             for (int c0 = 0; c0 < NT; c0 += 8) {
-                float v[8], o[8];
+                float v[8], x[8], o[8];
                 tmem_ld8(tacc + c0, v);
+                tmem_ld8(tacc + NT + c0, x);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = v[e] + sBias[c0 + e];
+                for (int e = 0; e < 8; ++e) o[e] = (v[e] + x[e]) + sBias[c0 + e];
                 if (a.chain) restage(c0, o);
                 else store_y(c0, o);
             }
             if (a.chain) tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(accEmpty(buf));          // the accumulator buffer (and the row table) may be reused
-                if (a.chain) mbar_arrive(barE1);
-            }
+            if (lane == 0) mbar_arrive(a.chain ? barE1 : accEmpty(buf));   // no chain: buffer and row table are free again
             if (!a.chain) continue;
             // ---- stage 1: conv1 + bias, gate with U ----
             mbar_wait_sleep(barC1, (uint32_t)i & 1u);
@@ -436,10 +435,12 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
                     if (a.vec32) ldg8_stream(up + c0, u0, u1);
                     else { u0 = ldg4_stream(up + c0); u1 = ldg4_stream(up + c0 + 4); }
                 }
+                float x[8];
                 tmem_ld8(tX + c0, v);
+                tmem_ld8(tX + NT + c0, x);
                 const float uv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = (v[e] + sBias[128 + c0 + e]) * uv[e];
+                for (int e = 0; e < 8; ++e) o[e] = ((v[e] + x[e]) + sBias[128 + c0 + e]) * uv[e];
                 if (a.chain == 2) restage(c0, o);
                 else store_y(c0, o);
             }
@@ -458,14 +459,19 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
                         if (a.vec32) ldg8_stream(rp + c0, r0, r1);
                         else { r0 = ldg4_stream(rp + c0); r1 = ldg4_stream(rp + c0 + 4); }
                     }
+                    float x[8];
                     tmem_ld8(tX + c0, v);
+                    tmem_ld8(tX + NT + c0, x);
                     const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = v[e] + sBias[256 + c0 + e] + rv[e];
+                    for (int e = 0; e < 8; ++e) o[e] = (v[e] + x[e]) + sBias[256 + c0 + e] + rv[e];
                     store_y(c0, o);
                 }
             }
-            tc_fence_before();   // X / A(tmem) of this tile are fully consumed before the next tile's stage 0 signals barE1
+            // the chain's X (= this buffer) and the A operand are fully consumed: the buffer may take tile i+2's accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accEmpty(buf));
         }
     }
     tc_fence_before();
@@ -477,7 +483,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
     }
 }
 
-// weight [Co][C][taps] -> Bp[chunk][tap][hi|lo][4 planes][NT][8]   (one N tile)
+// weight [Co][C][taps] -> Bp[chunk][tap][4 planes][hi NT rows | lo NT rows][8]   (one N tile)
 __global__ void ps_pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ bp, int Co, int C, int taps, int NT)
 {
     const i64 total = (i64)(C / PS_KC) * taps * PS_KC * NT;
@@ -491,9 +497,9 @@ __global__ void ps_pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16
         const float v = n < Co ? w[((i64)n * C + c) * taps + tap] : 0.f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        const i64 slot = ((i64)ch * taps + tap) * (2 * PS_KC * NT);
-        bp[slot + ((i64)p * NT + n) * 8 + e] = hi;
-        bp[slot + (i64)PS_KC * NT + ((i64)p * NT + n) * 8 + e] = lo;
+        const i64 slot = ((i64)ch * taps + tap) * (2 * PS_KC * NT);   // plane p = 2 NT rows of 8 channels: hi rows, then lo rows
+        bp[slot + ((i64)p * 2 * NT + n) * 8 + e] = hi;
+        bp[slot + ((i64)p * 2 * NT + NT + n) * 8 + e] = lo;
     }
 }
 
