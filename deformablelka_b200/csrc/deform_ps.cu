@@ -43,7 +43,8 @@ constexpr int PS_SA = 3, PS_SB = 3, PS_SP = 4;
 constexpr int PS_LBO = 2048 + 32;          // A plane (8 channels x 128 rows) stride, padded to spread banks
 constexpr int PS_APLANE = (PS_KC / 8) * PS_LBO;
 constexpr int PS_ASLOT = 2 * PS_APLANE;    // hi + lo
-constexpr int PS_PREC = 32;                // parameter record: {base|flags, wx0, base|flags, wx1} + float4 (d, h) weight products
+constexpr int PS_PSIDE = 128 * 16 + 64;    // parameter stage: [128 rows x 16 B, low-w side] [+64 B bank shift] [128 x 16 B, high-w side]
+constexpr int PS_PSTAGE = 2 * PS_PSIDE;    // record = one 16-byte {offset|flags, wx, ld, lh} per row and w-side (ps_make_params)
 constexpr int PS_GROUPS = 2;               // gather warp groups on alternate K steps
 constexpr int PS_GW = 8;                   // warps per gather group
 constexpr int PS_PARAM_WARPS = 4, PS_EPI_WARPS = 4;
@@ -100,39 +101,37 @@ __device__ __forceinline__ void ps_tile_coords(const DeformPsArgs &a, int tile, 
 __device__ __forceinline__ void ps_make_params(const ConvGeo &g, const PsRow &ri, int ii, int jj, int kk, float od, float oh, float ow,
                                                uint8_t *rec)
 {
-    // record: word0 = byte offset of the (d0, h0) pair | bit 0: the h1 row differs (+ W*128) | bit 1: the d1 plane differs;
-    // wx0 / wx1 = w-interpolation weight of the pair's low / high side; p = the four (d, h) weight products.  A gather lane reads
-    // 8 B ({word0, wx of its side}) + 16 B (p) and forms its 4 corner weights as p * wx -- the same products, in the same order,
-    // as the reference's hd*hh*hw (cuh:67-68).
+    // record (32 B per row, one 16-byte half per w-side): {word0, wx, ld, lh} with
+    //   word0 = byte offset of the (d0, h0) line pair (multiple of 128) | bit 0: the h1 row differs | bit 1: the d1 plane differs |
+    //           bits 2..5: the reference keeps the d-low / d-high / h-low / h-high corner (index inside the volume, cuh:43-65),
+    //   wx = w-interpolation weight of this side of the pair, ld / lh = fractional parts along d / h.
+    // A gather lane reads ONE 16-byte word and forms its 4 corner weights (hd|ld)*(hh|lh)*wx exactly as the reference orders the
+    // products (cuh:67-68).  An invalid sample has wx = 0 on both sides.
     uint32_t word0 = 0u;
-    float wx0 = 0.f, wx1 = 0.f;
-    float4 pp = f4zero();
+    float wx0 = 0.f, wx1 = 0.f, ld = 0.f, lh = 0.f;
     if (ri.m >= 0) {
         const float pd = sample_pos(ri.d, g.sd, g.pd, ii, g.dd, od);
         const float ph = sample_pos(ri.h, g.sh, g.ph, jj, g.dh, oh);
         const float pw = sample_pos(ri.w, g.sw, g.pw, kk, g.dw, ow);
         const Sample3 s = make_sample3(pd, ph, pw, g.D, g.H, g.W);
         if (s.mask & 1) {
-            const float ld = s.l[0], lh = s.l[1], lw = s.l[2], hd = 1.f - ld, hh = 1.f - lh, hw = 1.f - lw;
+            ld = s.l[0]; lh = s.l[1];
+            const float lw = s.l[2], hw = 1.f - lw;
             const int d0 = max(s.lo[0], 0), d1 = min(s.lo[0] + 1, g.D - 1);
             const int h0 = max(s.lo[1], 0), h1 = min(s.lo[1] + 1, g.H - 1);
             const int xb = min(max(s.lo[2], 0), g.W - 2);
-            // per-axis factors, zero where the reference drops the corner (low index < 0 / high index > dim - 1)
-            const float fd0 = s.lo[0] >= 0 ? hd : 0.f, fd1 = s.lo[0] + 1 <= g.D - 1 ? ld : 0.f;
-            const float fh0 = s.lo[1] >= 0 ? hh : 0.f, fh1 = s.lo[1] + 1 <= g.H - 1 ? lh : 0.f;
             const float fxl = s.lo[2] >= 0 ? hw : 0.f, fxh = s.lo[2] + 1 <= g.W - 1 ? lw : 0.f;   // corner at lo / at lo + 1
             // side 0 reads voxel xb, side 1 voxel xb + 1
             wx0 = (xb == s.lo[2] ? fxl : 0.f) + (xb == s.lo[2] + 1 ? fxh : 0.f);
             wx1 = (xb + 1 == s.lo[2] ? fxl : 0.f) + (xb + 1 == s.lo[2] + 1 ? fxh : 0.f);
             const uint32_t sH = (uint32_t)g.W * 128u, sD = (uint32_t)g.H * sH;
-            word0 = ((uint32_t)d0 * sD + (uint32_t)h0 * sH + (uint32_t)xb * 128u) | (h1 != h0 ? 1u : 0u) | (d1 != d0 ? 2u : 0u);
-            pp = make_float4(fd0 * fh0, fd0 * fh1, fd1 * fh0, fd1 * fh1);   // (d, h) products first: cuh:67-68
+            word0 = ((uint32_t)d0 * sD + (uint32_t)h0 * sH + (uint32_t)xb * 128u) | (h1 != h0 ? 1u : 0u) | (d1 != d0 ? 2u : 0u) |
+                    (s.lo[0] >= 0 ? 4u : 0u) | (s.lo[0] + 1 <= g.D - 1 ? 8u : 0u) | (s.lo[1] >= 0 ? 16u : 0u) |
+                    (s.lo[1] + 1 <= g.H - 1 ? 32u : 0u);
         }
     }
-    // structure of arrays inside a stage: [128 x {word0, wx0, word0, wx1}] then [128 x p] -- both 16-byte stores are then
-    // bank-conflict free across the warp's 32 rows
-    *reinterpret_cast<uint4 *>(rec) = make_uint4(word0, __float_as_uint(wx0), word0, __float_as_uint(wx1));
-    *reinterpret_cast<float4 *>(rec + 128 * 16) = pp;
+    *reinterpret_cast<uint4 *>(rec) = make_uint4(word0, __float_as_uint(wx0), __float_as_uint(ld), __float_as_uint(lh));
+    *reinterpret_cast<uint4 *>(rec + PS_PSIDE) = make_uint4(word0, __float_as_uint(wx1), __float_as_uint(ld), __float_as_uint(lh));
 }
 
 __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const DeformPsArgs a)
@@ -144,8 +143,8 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
     const uint32_t acc_stride = NT > 96 ? 256u : 192u;
     uint8_t *sA = smem;
     uint8_t *sB = sA + PS_SA * PS_ASLOT;
-    uint8_t *sPrm = sB + PS_SB * B_SLOT;                                    // [SP][128][48 B]
-    PsRow *sRow = reinterpret_cast<PsRow *>(sPrm + PS_SP * 128 * PS_PREC);  // [2][128]
+    uint8_t *sPrm = sB + PS_SB * B_SLOT;                                    // [SP][PS_PSTAGE]
+    PsRow *sRow = reinterpret_cast<PsRow *>(sPrm + PS_SP * PS_PSTAGE);      // [2][128]
     float *sBias = reinterpret_cast<float *>(sRow + 2 * 128);               // [3][128]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sBias + 3 * 128);
     constexpr int NBARS = 2 * PS_SA + 2 * PS_SB + 2 * PS_SP + 4 + 4;
@@ -305,7 +304,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
                 }
                 const int ps = gp % PS_SP;
                 mbar_wait(emptyP(ps), ((gp / PS_SP) & 1) ^ 1);
-                ps_make_params(g, ri, ii, jj, kk, od, oh, ow, sPrm + ps * 128 * PS_PREC + r * 16);
+                ps_make_params(g, ri, ii, jj, kk, od, oh, ow, sPrm + ps * PS_PSTAGE + r * 16);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(fullP(ps));
                 od = nod; oh = noh; ow = now;
@@ -340,12 +339,12 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int row = row0 + u * 32;
-                const uint8_t *rec = sPrm + ps * 128 * PS_PREC + row * 16;
-                const uint2 ow = *reinterpret_cast<const uint2 *>(rec + side * 8);     // {base | flags, wx of this side}
-                const float4 pp = *reinterpret_cast<const float4 *>(rec + 128 * 16);
-                const uint32_t o00 = ow.x & ~3u, dh = (ow.x & 1u) ? sHb : 0u, dd = (ow.x & 2u) ? sDb : 0u;
-                const float wx = __uint_as_float(ow.y);
-                const float4 w = make_float4(pp.x * wx, pp.y * wx, pp.z * wx, pp.w * wx);
+                const uint4 rc = *reinterpret_cast<const uint4 *>(sPrm + ps * PS_PSTAGE + side * PS_PSIDE + row * 16);   // {word0, wx, ld, lh}
+                const uint32_t o00 = rc.x & ~127u, dh = (rc.x & 1u) ? sHb : 0u, dd = (rc.x & 2u) ? sDb : 0u;
+                const float wx = __uint_as_float(rc.y), fl_d = __uint_as_float(rc.z), fl_h = __uint_as_float(rc.w);
+                const float fd0 = (rc.x & 4u) ? 1.f - fl_d : 0.f, fd1 = (rc.x & 8u) ? fl_d : 0.f;
+                const float fh0 = (rc.x & 16u) ? 1.f - fl_h : 0.f, fh1 = (rc.x & 32u) ? fl_h : 0.f;
+                const float4 w = make_float4((fd0 * fh0) * wx, (fd0 * fh1) * wx, (fd1 * fh0) * wx, (fd1 * fh1) * wx);
                 float4 a0, b0, a1, b1, a2, b2, a3, b3;
                 ldg8(base + o00, a0, b0); ldg8(base + (o00 + dh), a1, b1); ldg8(base + (o00 + dd), a2, b2); ldg8(base + (o00 + dd + dh), a3, b3);
                 if (u == 3) {
@@ -505,7 +504,7 @@ __global__ void ps_pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16
 
 size_t ps_smem_bytes(int NT)
 {
-    return (size_t)PS_SA * PS_ASLOT + (size_t)PS_SB * 2 * (PS_KC / 8) * NT * 16 + (size_t)PS_SP * 128 * PS_PREC + 2 * 128 * sizeof(PsRow) +
+    return (size_t)PS_SA * PS_ASLOT + (size_t)PS_SB * 2 * (PS_KC / 8) * NT * 16 + (size_t)PS_SP * PS_PSTAGE + 2 * 128 * sizeof(PsRow) +
            3 * 128 * sizeof(float) + (2 * PS_SA + 2 * PS_SB + 2 * PS_SP + 8) * 8 + 16 + 128;
 }
 
