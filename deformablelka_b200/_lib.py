@@ -131,8 +131,8 @@ def _load() -> ctypes.CDLL:
         getattr(lib, name).argtypes = [c_void_p]
     lib.dlka_host_pipe_join.restype = c_int
     lib.dlka_host_pipe_join.argtypes = [c_void_p, c_void_p]
-    lib.dlka_host_pipe_slot_done.restype = c_int
-    lib.dlka_host_pipe_slot_done.argtypes = [c_void_p, c_int]
+    lib.dlka_host_pipe_completed.restype = ctypes.c_longlong
+    lib.dlka_host_pipe_completed.argtypes = [c_void_p]
     lib.dlka_host_numa_node.restype = c_int
     lib.dlka_host_numa_node.argtypes = [c_int]
     lib.dlka_host_bind_thread.restype = c_int

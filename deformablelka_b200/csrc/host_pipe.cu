@@ -25,7 +25,8 @@
 struct dlkaHostPipe {
     int depth = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    unsigned long long step = 0;
+    unsigned long long step = 0;        // steps submitted
+    unsigned long long completed = 0;   // lower bound of the steps whose last D2H copy has finished (advanced by polling)
     // per slot: "sample b landed" / "sample b computed" events, "slot inputs consumed", "slot outputs copied back"
     std::vector<std::vector<cudaEvent_t>> ev_in, ev_comp;
     std::vector<cudaEvent_t> ev_consumed, ev_out;
@@ -230,6 +231,7 @@ int dlka_host_pipe_wait(dlkaHostPipe *p)
     if (!p) return DLKA_ERR_INVALID_ARGUMENT;
     DLKA_CUDA_TRY(cudaStreamSynchronize(p->s_in));
     DLKA_CUDA_TRY(cudaStreamSynchronize(p->s_out));
+    p->completed = p->step;
     return DLKA_OK;
 }
 
@@ -295,15 +297,22 @@ int dlka_host_pipe_join(dlkaHostPipe *p, void *stream)
     return DLKA_OK;
 }
 
-// 1 when slot `slot`'s last D2H copy has completed (its host / device buffers may be released), 0 while in flight
-int dlka_host_pipe_slot_done(dlkaHostPipe *p, int slot)
+// Non-blocking: a lower bound of the number of submitted steps whose last D2H copy has finished (the host tensors of those steps
+// may be released).  Steps finish in submission order (one output stream); a slot's event is re-recorded when the slot is reused,
+// so the count only advances over slots whose CURRENT event has completed -- conservative, never ahead of the truth.
+long long dlka_host_pipe_completed(dlkaHostPipe *p)
 {
-    if (!p || slot < 0 || slot >= p->depth) return DLKA_ERR_INVALID_ARGUMENT;
-    if (!p->used[slot]) return 1;
-    const cudaError_t e = cudaEventQuery(p->ev_out[slot]);
-    if (e == cudaSuccess) return 1;
-    if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
-    return dlka::record_cuda_error(e, "cudaEventQuery");
+    if (!p) return DLKA_ERR_INVALID_ARGUMENT;
+    while (p->completed < p->step) {
+        const int s = (int)(p->completed % p->depth);
+        const cudaError_t e = cudaEventQuery(p->ev_out[s]);
+        if (e == cudaErrorNotReady) { cudaGetLastError(); break; }
+        if (e != cudaSuccess) return dlka::record_cuda_error(e, "cudaEventQuery");
+        // ev_out[s] now belongs to the newest step that used slot s: that step and every earlier one are done
+        unsigned long long newest = p->step - 1 - ((p->step - 1 - p->completed) % p->depth);   // newest step index with slot s
+        p->completed = newest + 1;
+    }
+    return (long long)p->completed;
 }
 
 }  // extern "C"

@@ -408,9 +408,9 @@ class HostPipe:
     """Streaming host-buffer pipeline (dlka_host_pipe_*): keeps `depth` steps in flight so that the H2D copy of the next
     step and the D2H copy of the previous one overlap the compute of the current step.
 
-    Lifetime rules enforced here: every step's host tensors and contiguous parameter copies are held in a per-slot list
-    until that slot is reused (by then the library has ordered the new step after the old one's copies) or until wait();
-    the device staging buffer is never regrown while steps are in flight."""
+    Lifetime rules enforced here (without ever blocking the host in submit): every step's host tensors and contiguous
+    parameter copies are held until the library reports that step's last D2H copy as finished (dlka_host_pipe_completed,
+    polled non-blocking) or until wait(); the device staging buffer is never regrown while steps are in flight."""
 
     def __init__(self, device, depth: int = 2):
         self.device = torch.device(device)
@@ -419,8 +419,16 @@ class HostPipe:
         with torch.cuda.device(self.device):
             check(lib.dlka_host_pipe_create(ctypes.byref(self._h), depth), "dlka_host_pipe_create")
         self._scratch = None
-        self._keep = [None] * depth
+        self._inflight = []     # [(step index, references)]
         self._step = 0
+
+    def _release_finished(self) -> None:
+        if not self._inflight:
+            return
+        done = int(lib.dlka_host_pipe_completed(self._h))
+        if done < 0:
+            check(done, "dlka_host_pipe_completed")
+        self._inflight = [(i, r) for i, r in self._inflight if i >= done]
 
     def submit(self, params: dict, x_host: torch.Tensor, y_host: torch.Tensor, B, C, H, W, D, math=None) -> None:
         assert x_host.device.type == "cpu" and y_host.device.type == "cpu" and x_host.is_contiguous() and y_host.is_contiguous()
@@ -430,25 +438,15 @@ class HostPipe:
             self.wait()                               # copies on the library's private streams may still use the old buffer
             self._scratch = None
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
-        slot = self._step % self.depth
-        if self._keep[slot] is not None:
-            # the slot's previous step must have finished its D2H copy before its host tensors may be dropped
-            with torch.cuda.device(self.device):
-                while True:
-                    done = lib.dlka_host_pipe_slot_done(self._h, slot)
-                    if done < 0:
-                        check(done, "dlka_host_pipe_slot_done")
-                    if done:
-                        break
-                    torch.cuda.current_stream(self.device).synchronize()
-                    check(lib.dlka_host_pipe_wait(self._h), "dlka_host_pipe_wait")
+        with torch.cuda.device(self.device):
+            self._release_finished()
         s, keep = _params_struct(Block3dParams, params)
         ws = Workspace.get(self.device, lib.dlka_lka_attention3d_deform_workspace_bytes(1, C, H, W, D))
         with torch.cuda.device(self.device):
             st = lib.dlka_lka_attention3d_deform_forward_host_async(
                 self._h, ctypes.byref(s), x_host.data_ptr(), y_host.data_ptr(), B, C, H, W, D, _math(math),
                 self._scratch.data_ptr(), self._scratch.numel(), ws.data_ptr(), ws.numel(), stream_ptr(self.device))
-        self._keep[slot] = [keep, x_host, y_host, ws]
+        self._inflight.append((self._step, [keep, x_host, y_host, ws]))
         check(st, "dlka_lka_attention3d_deform_forward_host_async")
         self._step += 1
 
@@ -461,7 +459,7 @@ class HostPipe:
         with torch.cuda.device(self.device):
             torch.cuda.current_stream(self.device).synchronize()
             check(lib.dlka_host_pipe_wait(self._h), "dlka_host_pipe_wait")
-        self._keep = [None] * self.depth
+        self._inflight = []
 
     def __del__(self):
         try:

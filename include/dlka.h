@@ -227,8 +227,9 @@ DLKA_API int dlka_lka_attention3d_deform_forward_host_async(dlkaHostPipe *pipe, 
                                                    const float *x_host, float *y_host, int B, int C, int D1, int D2,
                                                    int D3, int math, void *dev_scratch, size_t dev_scratch_bytes,
                                                    void *workspace, size_t workspace_bytes, void *stream);
-/* 1 when slot `slot` (= step index % depth) has finished its last D2H copy (its buffers may be released), 0 while in flight */
-DLKA_API int dlka_host_pipe_slot_done(dlkaHostPipe *pipe, int slot);
+/* non-blocking lower bound of the number of submitted steps whose last D2H copy has finished (their host buffers may be
+ * released); negative = dlkaStatus */
+DLKA_API long long dlka_host_pipe_completed(dlkaHostPipe *pipe);
 
 /* Host-side placement for the `_host` entries (the reference's only multi-GPU mode is nn.DataParallel out of un-placed
  * host tensors, 2D/trainer_MaxViT_deform_LKA.py:60-66; at 805 MB per direction per step the copy rate is the end-to-end rate).
