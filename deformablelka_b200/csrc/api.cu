@@ -107,6 +107,11 @@ int contraction(IgemmArgs a, const float *w, int math, float *wscratch, cudaStre
     const ConvGeo &g = a.geo;
     if (math == DLKA_MATH_BF16X3 && a.mode == IGEMM_CONV && conv_tiled_supported(a)) return conv_tiled(a, w, wscratch, st);
     if (math == DLKA_MATH_BF16X3 && a.mode == IGEMM_DEFORM && deform3d_tc_supported(a)) return deform3d_tc(a, w, wscratch, nullptr, st);
+    // large-M 1x1 projections: the persistent streaming kernel (HBM-bound; at least two 128-row tiles per SM)
+    if (math == DLKA_MATH_BF16X3 && a.mode == IGEMM_DENSE && a.M >= 2 * 148 * 128 && dense_stream_supported(a)) {
+        DLKA_TRY(deform3d_ps_pack(w, wscratch, g.Co, g.C, 1, st));
+        return dense_stream(a, wscratch, st);
+    }
     if (math == DLKA_MATH_BF16X3 && tc_supported(a)) {
         DLKA_TRY(tc_pack_weight(w, wscratch, g.Co, g.C, g.K, st));
         return igemm_tc(a, wscratch, st);

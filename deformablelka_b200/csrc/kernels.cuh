@@ -41,9 +41,10 @@ int igemm_simt(const IgemmArgs &a, cudaStream_t st);
 
 // tensor-core (tcgen05, bf16 hi/lo split) variant -- mma_tc.cu
 bool tc_supported(const IgemmArgs &a);
-// persistent pipelined variant for the single-K-step, single-N-tile 1x1 projections (dense_persist.cu); same packed weights
-bool dense_persist_supported(const IgemmArgs &a);
-int dense_persist(const IgemmArgs &a, const void *w_packed, cudaStream_t st);
+// persistent streaming variant for the HBM-bound 1x1 projections (dense_stream.cu): whole raw tiles in flight through
+// cp.async.bulk, weights resident in shared memory; weights packed with deform3d_ps_pack(w, bp, Co, C, 1)
+bool dense_stream_supported(const IgemmArgs &a);
+int dense_stream(const IgemmArgs &a, const void *w_packed, cudaStream_t st);
 int tc_kc(int C);
 int tc_nt(int Co);
 size_t tc_packed_weight_bytes(int Co, int C, int taps);

@@ -458,9 +458,6 @@ int igemm_tc(const IgemmArgs &g, const void *bp, cudaStream_t st)
 {
     if (!tc_supported(g)) return DLKA_ERR_UNSUPPORTED;
     if (g.M <= 0) return DLKA_OK;
-#ifdef DLKA_DENSE_PERSIST   // persistent pipelined variant (dense_persist.cu): correct, measured 0.77 vs 0.64 ms for proj_1 -- off
-    if (dense_persist_supported(g)) return dense_persist(g, bp, st);
-#endif
     TcArgs a;
     a.g = g;
     a.Bp = (const uint8_t *)bp;

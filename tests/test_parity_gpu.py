@@ -606,9 +606,10 @@ def test_deform_conv3d_backward_refuses_groups(dl):
 
 
 # ----------------------------------------------------------------------------- 1x1 projections at large M (generic kernel by
-# default; the persistent variant of dense_persist.cu when the library is built with -DDLKA_DENSE_PERSIST)
+# for M < 37888 rows, the persistent streaming kernel dense_stream.cu above that: both sizes are covered)
 @pytest.mark.parametrize("M,K,N,bias,add", [(20000, 96, 96, True, True), (19001, 64, 128, True, False), (40000, 32, 9, False, True),
-                                             (18944, 96, 81, True, False)])
+                                             (18944, 96, 81, True, False), (300001, 96, 96, True, True), (262144, 64, 64, True, False),
+                                             (150000, 32, 40, False, True), (37888, 96, 81, True, False)])
 def test_linear_tokens_large_m_vs_torch(dl, M, K, N, bias, add, math):
     """Many 128-row tiles per SM: ragged last tile, N not a multiple of 16, bias / residual epilogues."""
     torch.manual_seed(40)
