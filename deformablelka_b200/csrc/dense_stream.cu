@@ -27,8 +27,9 @@ constexpr int DS_KC = 32;                 // channels per operand chunk
 constexpr int DS_LBO = 2048 + 32;         // operand plane (8 channels x 128 rows) stride
 constexpr int DS_APLANE = (DS_KC / 8) * DS_LBO, DS_ASLOT = 2 * DS_APLANE;   // hi + lo of one chunk
 constexpr int DS_RS = 2, DS_OS = 3;       // raw-tile ring, operand-chunk ring
-constexpr int DS_CONV_WARPS = 8, DS_EPI_WARPS = 8;   // epilogue: two warps per TMEM lane quadrant, half of the columns each
-constexpr int DS_THREADS = (4 + DS_CONV_WARPS + DS_EPI_WARPS) * 32;   // 640
+constexpr int DS_CONV_WARPS = 8, DS_EPI_WARPS = 16;   // epilogue: four warps per TMEM lane quadrant, a quarter of the columns each
+constexpr int DS_EPI_SPLIT = DS_EPI_WARPS / 4;        // (the exact-erf GELU of proj_1 is a long dependent chain: ncu showed the epilogue pacing the kernel)
+constexpr int DS_THREADS = (4 + DS_CONV_WARPS + DS_EPI_WARPS) * 32;   // 896
 
 struct DenseStreamArgs {
     const float *X;      // [M][K] contiguous rows
@@ -159,9 +160,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dense_stream_kernel(const Dense
             if (lane == 0) mbar_arrive(rawEmpty(rs));   // this warp has read its share of the raw tile
         }
     } else if (warp >= 4 + DS_CONV_WARPS) {
-        // =============================================== epilogue: two threads per accumulator row (column halves) ===============================================
-        const int q = warp & 3, row = q * 32 + lane, half = (warp - 4 - DS_CONV_WARPS) >> 2;
-        const int nchunk8 = NT / 8, c_begin = half * ((nchunk8 + 1) / 2) * 8, c_end = half ? NT : ((nchunk8 + 1) / 2) * 8;
+        // =============================================== epilogue: DS_EPI_SPLIT threads per accumulator row (column groups) ===============================================
+        const int q = warp & 3, row = q * 32 + lane, grp = (warp - 4 - DS_CONV_WARPS) >> 2;
+        const int per = ((NT / 8 + DS_EPI_SPLIT - 1) / DS_EPI_SPLIT) * 8;                  // columns per group (multiple of 8)
+        const int c_begin = grp * per < NT ? grp * per : NT, c_end = c_begin + per < NT ? c_begin + per : NT;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const bool vec_y = (a.ldY & 3) == 0;
         for (i64 i = 0; i < ntl; ++i) {
