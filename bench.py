@@ -303,30 +303,50 @@ def main():
     dom_avg_ms = dom_ms / max(dom_n, 1)
     launches_per_step = {k: v[0] / args.steps for k, v in prof.items()}
     total_prof_ms = sum(v[1] for v in prof.values())
-    # tensor-bound roofline on the dominant kernel when it is a contraction kernel, else HBM-bound
+    # Roofline of the dominant kernel.  The contract's two bounds (tensor FLOP/s, HBM bytes/s) are reported for it, and -- for the
+    # deformable kernel, where neither binds -- the bound that does: the SM's L1TEX data pipe (one 128-byte wavefront per cycle and
+    # SM for global lines, shared-memory accesses, shuffles and UMMA operand reads alike).  Its algorithmic work is
+    # the trilinear gather: 8 corners x 27 taps x C/32 lines of 128 bytes per voxel, every one of which must cross that pipe.
     per_launch_flop = {
         "igemm_simt_deform": 2 * 27 * C * C * vox, "igemm_simt_conv": 2 * 27 * C * 81 * vox,
         "tc_deform": 2 * 27 * C * C * vox, "tc_conv": 2 * 27 * C * 81 * vox, "tc_conv_tiled": 2 * 27 * C * 81 * vox,
         "tc_deform3d": 2 * 27 * C * C * vox, "tc_deform3d_chain": (2 * 27 * C * C + 2 * 2 * C * C) * vox,
+        "tc_dense": 2 * C * C * vox,
     }
+    per_launch_hbm = {   # compulsory bytes of each kernel: what it must read and write once
+        "tc_deform3d_chain": (4 * C * 4 + 81 * 4) * vox,   # a (gather source), u (gate), x (residual) in, y out, offsets in
+        "tc_conv_tiled": (C * 4 + 81 * 4) * vox, "tc_dense": 2 * C * 4 * vox,
+        "dwconv3d_smem_k5": 2 * C * 4 * vox, "dwconv3d_smem_k7d3": 2 * C * 4 * vox,
+    }
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    share = dom_ms / total_prof_ms if total_prof_ms else None
+    tensor = None
     if dom_name in per_launch_flop:
         ach = per_launch_flop[dom_name] / (dom_avg_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": dom_name, "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops"], "traffic": traffic.get(dom_name), "peak_source": pk["source"] + " bf16 burst",
-                "avg_launch_ms": dom_avg_ms, "share_of_step": dom_ms / total_prof_ms if total_prof_ms else None}
-        if dom_name.startswith("tc_deform3d"):
-            # what actually binds this kernel: the trilinear gather through the SM's L1 data path, 1.84 cycles
-            # per 128-byte line measured by tools/l1_probe.cu; reported beside the contract's tensor roofline
-            lines = vox * 27 * 8 * (C // 32)
-            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-            floor_ms = lines * 1.84 / (148 * sm_mhz * 1e6) * 1e3
-            roof["onchip_gather"] = {"lines_128B": lines, "cycles_per_line_measured": 1.84, "floor_ms": floor_ms,
-                                     "frac_of_floor": floor_ms / dom_avg_ms}
+        tensor = {"achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                  "peak_source": pk["source"] + " bf16 burst"}
+    hbm_bytes = per_launch_hbm.get(dom_name, HBM_BYTES_PER_VOXEL * vox)
+    ach_hbm = hbm_bytes / (dom_avg_ms * 1e-3) / 1e9
+    hbm = {"achieved": ach_hbm, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_hbm / pk["hbm_gbs"], "peak_source": pk["source"],
+           "algorithmic_bytes": hbm_bytes}
+    if dom_name and dom_name.startswith("tc_deform3d"):
+        lines = vox * 27 * 8 * (C // 32)
+        peak_l1 = 148 * 128 * sm_mhz * 1e6 / 1e9          # GB/s: 128 bytes per clock and SM at the SM clock seen during the run
+        ach_l1 = lines * 128 / (dom_avg_ms * 1e-3) / 1e9
+        roof = {"bound": "l1tex_data_pipe", "kernel": dom_name, "achieved": ach_l1, "peak": peak_l1, "unit": "GB/s",
+                "frac": ach_l1 / peak_l1, "traffic": traffic.get(dom_name), "avg_launch_ms": dom_avg_ms, "share_of_step": share,
+                "peak_source": f"148 SMs x 128 B/clk x {sm_mhz:.0f} MHz (L1TEX data pipe, one wavefront per cycle; ncu: "
+                               "l1tex__data_pipe_lsu_wavefronts + l1tex__data_pipe_tc_wavefronts ~ elapsed cycles)",
+                "algorithmic_bytes": lines * 128, "gather_lines_128B": lines,
+                "note": "the gather alone is 1024 of the ~2000 wavefronts of a K step (profiles/r02_deform_ps_l1tex.txt); "
+                        "tensor and hbm are the contract's bounds for the same kernel and do not bind",
+                "tensor": tensor, "hbm": hbm}
+    elif tensor is not None and dom_name != "tc_dense":
+        roof = dict(tensor, bound="tensor", kernel=dom_name, traffic=traffic.get(dom_name), avg_launch_ms=dom_avg_ms, share_of_step=share,
+                    hbm=hbm)
     else:
-        ach = HBM_BYTES_PER_VOXEL * vox / (dom_avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": traffic.get(dom_name), "peak_source": pk["source"],
-                "avg_launch_ms": dom_avg_ms, "share_of_step": dom_ms / total_prof_ms if total_prof_ms else None}
+        roof = dict(hbm, bound="hbm", kernel=dom_name, traffic=traffic.get(dom_name), avg_launch_ms=dom_avg_ms, share_of_step=share,
+                    tensor=tensor)
     roof["traffic_source"] = traffic_note
     out = {
         "metric": METRIC, "value": value, "unit": "GVoxel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
