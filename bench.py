@@ -99,6 +99,88 @@ def make_block(C, device, seed=1234):
     return m.to(device).eval()
 
 
+C4_BLOCKS = ((32, 32, 6), (64, 16, 6), (128, 8, 6), (256, 4, 3))   # (C, cube edge, instances) of the 3D net at batch 2 (SURVEY 3.4)
+C2_BLOCKS = ((384, 14), (192, 28), (96, 56))                          # (C, H = W) of the 2D net's decoder blocks at batch 24 (SURVEY 3.3)
+
+
+def _time_call(fn, iters=20, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def other_configs(dl, dev):
+    """BASELINE.json configs[1..3] (and the block shapes of configs[3] / [4]) as ms per call of the block / operator that the
+    reference network runs at that shape: CUDA events, 5 warm-ups, 20 timed calls, inputs resident, seeded random parameters."""
+    out = {}
+    with torch.no_grad():
+        for C, hw in C2_BLOCKS:
+            torch.manual_seed(1234)
+            m = dl.deformable_LKA_Attention(C).to(dev).eval()
+            x = torch.randn(24, C, hw, hw, device=dev)
+            out[f"c2_block2d_24x{C}x{hw}x{hw}_ms"] = _time_call(lambda: m(x))
+        torch.manual_seed(1234)
+        B, C, D, H, W = 2, 64, 32, 64, 64
+        x = torch.randn(B, C, D, H, W, device=dev); w = torch.randn(C, C, 3, 3, 3, device=dev) * 0.05
+        b = torch.randn(C, device=dev); off = torch.randn(B, 81, D, H, W, device=dev)
+        out["c3_deform_conv3d_2x64x32x64x64_ms"] = _time_call(lambda: dl.ops.deform_conv3d_forward(x, w, b, off, 3, 1, 1, 1, 1, 1, 64))
+        del x, off
+        for C, s, _ in C4_BLOCKS:
+            m = make_block(C, dev)
+            x = torch.randn(2, s * s * s, C, device=dev)
+            out[f"c4_block3d_2x{C}x{s}x{s}x{s}_ms"] = _time_call(lambda: m(x, 2, C, s, s, s))
+    return out
+
+
+def run_c4net(args, dl, dev, world, rank):
+    """--config c4net: one step = the 21 D-LKA attention blocks of the 3D D-LKA Net forward (SURVEY 3.4) at per-rank batch 2
+    (BASELINE configs[3]; under torchrun with 8 ranks = configs[4], global batch 16, batch-sharded, no collective)."""
+    from deformablelka_b200.dist import max_over_ranks
+    blocks = []
+    with torch.no_grad():
+        for C, s, n in C4_BLOCKS:
+            m = make_block(C, dev)
+            x = torch.randn(2, s * s * s, C, device=dev)
+            blocks.append((m, x, C, s, n))
+
+        def step():
+            for m, x, C, s, n in blocks:
+                for _ in range(n):
+                    m(x, 2, C, s, s, s)
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+        n0 = dl.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+        launches = dl.launch_count() - n0
+    if rank == 0:
+        print(json.dumps({
+            "metric": "3D D-LKA Net, D-LKA block path fwd (21 blocks), patches/s @ batch 2 per GPU", "value": 2 * world / (ms * 1e-3),
+            "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3]/[4]: LKA_Attention3d_deform at the 21 block shapes of the 3D net, 64x128x128 patches",
+                       "blocks": [list(b) for b in C4_BLOCKS], "math": args.math, "parallelism": f"dp{world}"},
+            "gpu_launches": int(launches)}))
+
+
 def cpu_threads():
     """One software thread per PHYSICAL core, capped at 64: the torch intra-op pool and the C oracle's OpenMP team share the
     same libgomp, and with every hyper-thread in both the sample time swung 4.6x between two boxes (VERDICT r1 weak #6)."""
@@ -182,6 +264,8 @@ def main():
     ap.add_argument("--math", default=os.environ.get("DLKA_MATH", "bf16x3"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--config", default="headline", choices=["headline", "c4net"], help="c4net: BASELINE configs[3] / [4] (block path)")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--no-profile-pass", action="store_true", help="skip the per-kernel event pass (tools/measure_traffic.py)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -203,6 +287,11 @@ def main():
     # host side of the e2e path: this rank's thread on the GPU's NUMA node, pinned buffers placed there (ops.pinned_empty)
     numa_node = dl.ops.bind_host_thread(dev) if os.environ.get("DLKA_HOST_NUMA", "local") != "off" else -1
 
+    if args.config == "c4net":
+        run_c4net(args, dl, dev, world, rank)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     B, C, D1, D2, D3 = (SHAPE[k] for k in ("B", "C", "D1", "D2", "D3"))
     N = D1 * D2 * D3
     vox = B * N
@@ -281,6 +370,11 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    others = None
+    if world == 1 and not args.no_other_configs:
+        del x, y
+        torch.cuda.empty_cache()
+        others = other_configs(dl, dev)
 
     pk = peaks()
     # DRAM traffic per launch: measured by tools/measure_traffic.py (ncu) and used only if it was measured on THESE sources
@@ -367,6 +461,8 @@ def main():
     }
     if e2e is not None:
         out["e2e"] = e2e
+    if others is not None:
+        out["other_configs"] = others
     if world == 1 and not args.no_cpu_baseline:
         threads = cpu_threads()
         v, t, sample = cpu_reference_sample(C, threads)

@@ -81,6 +81,10 @@ def _load() -> ctypes.CDLL:
     lib.dlka_deform_conv2d_workspace_bytes.argtypes = [I] * 15
     lib.dlka_deform_conv2d_forward.restype = c_int
     lib.dlka_deform_conv2d_forward.argtypes = [V] * 6 + [I] * 16 + [V, c_size_t, V]
+    lib.dlka_deform_conv2d_backward_workspace_bytes.restype = c_size_t
+    lib.dlka_deform_conv2d_backward_workspace_bytes.argtypes = [I] * 16
+    lib.dlka_deform_conv2d_backward.restype = c_int
+    lib.dlka_deform_conv2d_backward.argtypes = [V] * 10 + [I] * 15 + [V, c_size_t, V]
     lib.dlka_deform_conv2d_sample_indices.restype = c_int
     lib.dlka_deform_conv2d_sample_indices.argtypes = [V] * 3 + [I] * 12 + [V]
     lib.dlka_deform_conv_pack3d_workspace_bytes.restype = c_size_t

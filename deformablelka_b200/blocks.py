@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .deformable_LKA import _block2d_params, _refuse_autograd, deformable_LKA_Attention
+from .deformable_LKA import _block2d_params, deformable_LKA_Attention
 from .lka3d import LKA_Attention3d_deform, _block3d_params, needs_autograd
 
 
@@ -66,8 +66,21 @@ class deformableLKABlock(nn.Module):
         self.layer_scale_1 = nn.Parameter(layer_scale_init_value * torch.ones((dim)), requires_grad=True)
         self.layer_scale_2 = nn.Parameter(layer_scale_init_value * torch.ones((dim)), requires_grad=True)
 
+    def forward_autograd(self, x, H, W):
+        """Training / gradient path: MaxViT_deform_LKA.py:165-189 composed from this module's own sub-modules."""
+        B, N, C = x.shape
+        v = x.permute(0, 2, 1).reshape(B, C, H, W)
+        y = self.attn(self.norm1(v.permute(0, 2, 3, 1)).permute(0, 3, 1, 2))
+        v = v + self.layer_scale_1.unsqueeze(-1).unsqueeze(-1) * self.drop_path(y)
+        y = self.norm2(v.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        m = self.mlp
+        y = m.fc2(m.drop(m.act(m.dwconv.dwconv(m.fc1(y)))))
+        v = v + self.layer_scale_2.unsqueeze(-1).unsqueeze(-1) * self.drop_path(m.drop(y))
+        return v.reshape(B, C, N).permute(0, 2, 1)
+
     def forward(self, x, H, W):
-        _refuse_autograd(self, x, "deformableLKABlock")
+        if needs_autograd(self, x):
+            return self.forward_autograd(x, H, W)
         blk = {
             "norm1_weight": self.norm1.weight, "norm1_bias": self.norm1.bias, "layer_scale_1": self.layer_scale_1,
             "norm2_weight": self.norm2.weight, "norm2_bias": self.norm2.bias, "layer_scale_2": self.layer_scale_2,
@@ -155,7 +168,7 @@ class MyDecoderLayer(nn.Module):
             return self.layer_up(x1)
         b, h, w, c = x2.shape
         grad = needs_autograd(self, x1, x2)
-        if grad:   # the two deformableLKABlocks below refuse (2D operator has no backward); the linear parts are stock layers
+        if grad:   # every sub-module takes its differentiable path
             cat_linear_x = self.x1_linear(x1) + x2.reshape(b, -1, c)
         else:
             cat_linear_x = ops.linear_tokens_forward(x1, self.x1_linear.weight, self.x1_linear.bias, add=x2.reshape(b, -1, c))

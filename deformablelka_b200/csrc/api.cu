@@ -653,6 +653,64 @@ int dlka_deform_conv2d_forward(const float *input, const float *weight, const fl
     return run_deform_op(g, input, weight, bias, offset, mask, output, math, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// ---- backward of the 2D operator (row N2, 2D half): what torchvision's deform_conv2d autograd returns ----
+namespace {
+struct Deform2dBwdPlan {
+    float *x_cl, *off_cl, *mask_cl, *gout_cl, *gx_cl, *goff_cl, *gmask_cl;
+};
+bool plan_deform2d_bwd(Arena &ar, const ConvGeo &g, bool has_mask, Deform2dBwdPlan &p)
+{
+    const size_t Vi = (size_t)g.B * g.H * g.W, M = (size_t)g.B * g.Ho * g.Wo;
+    p.x_cl = ar.take<float>(Vi * g.C);
+    p.gx_cl = ar.take<float>(Vi * g.C);
+    p.off_cl = ar.take<float>(M * g.dg * 2 * g.K);
+    p.goff_cl = ar.take<float>(M * g.dg * 2 * g.K);
+    p.mask_cl = has_mask ? ar.take<float>(M * g.dg * g.K) : nullptr;
+    p.gmask_cl = has_mask ? ar.take<float>(M * g.dg * g.K) : nullptr;
+    p.gout_cl = ar.take<float>(M * g.Co);
+    return ar.ok();
+}
+}  // namespace
+
+size_t dlka_deform_conv2d_backward_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int sh, int sw, int ph, int pw,
+                                                   int dilh, int dilw, int n_weight_grps, int n_offset_grps, int has_mask)
+{
+    ConvGeo g = make_geo(B, C, 1, H, W, Co, 1, kh, kw, 1, sh, sw, 0, ph, pw, 1, dilh, dilw, n_weight_grps, n_offset_grps, 2);
+    if (bad_geo(g)) return 0;
+    Arena ar(nullptr, 0);
+    Deform2dBwdPlan p;
+    plan_deform2d_bwd(ar, g, has_mask != 0, p);
+    return ar.off + 256;
+}
+
+int dlka_deform_conv2d_backward(const float *input, const float *weight, const float *offset, const float *mask,
+                                const float *grad_output, float *grad_input, float *grad_weight, float *grad_offset, float *grad_mask,
+                                float *grad_bias, int B, int C, int H, int W, int Co, int kh, int kw, int sh, int sw, int ph, int pw,
+                                int dilh, int dilw, int n_weight_grps, int n_offset_grps, void *workspace, size_t workspace_bytes,
+                                void *stream)
+{
+    if (!input || !weight || !offset || !grad_output || !grad_input || !grad_weight || !grad_offset) return DLKA_ERR_INVALID_ARGUMENT;
+    if ((mask == nullptr) != (grad_mask == nullptr)) return DLKA_ERR_INVALID_ARGUMENT;
+    if (n_weight_grps <= 0 || n_offset_grps <= 0) return DLKA_ERR_INVALID_ARGUMENT;
+    ConvGeo g = make_geo(B, C, 1, H, W, Co, 1, kh, kw, 1, sh, sw, 0, ph, pw, 1, dilh, dilw, n_weight_grps, n_offset_grps, 2);
+    if (bad_geo(g)) return DLKA_ERR_INVALID_ARGUMENT;
+    DLKA_TRY(check_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ar(workspace, workspace_bytes);
+    Deform2dBwdPlan p;
+    if (!plan_deform2d_bwd(ar, g, mask != nullptr, p)) return DLKA_ERR_WORKSPACE;
+    const i64 Vi = (i64)g.H * g.W, Vo = (i64)g.Ho * g.Wo;
+    DLKA_TRY(transpose_cs_to_sc(input, p.x_cl, g.B, g.C, Vi, st));
+    DLKA_TRY(transpose_cs_to_sc(offset, p.off_cl, g.B, g.dg * 2 * g.K, Vo, st));
+    if (mask) DLKA_TRY(transpose_cs_to_sc(mask, p.mask_cl, g.B, g.dg * g.K, Vo, st));
+    DLKA_TRY(transpose_cs_to_sc(grad_output, p.gout_cl, g.B, g.Co, Vo, st));
+    DLKA_TRY(deform2d_backward_cl(g, p.x_cl, weight, p.off_cl, p.mask_cl, p.gout_cl, p.gx_cl, grad_weight, p.goff_cl, p.gmask_cl, grad_bias, st));
+    DLKA_TRY(transpose_sc_to_cs(p.gx_cl, grad_input, g.B, g.C, Vi, st));
+    DLKA_TRY(transpose_sc_to_cs(p.goff_cl, grad_offset, g.B, g.dg * 2 * g.K, Vo, st));
+    if (mask) DLKA_TRY(transpose_sc_to_cs(p.gmask_cl, grad_mask, g.B, g.dg * g.K, Vo, st));
+    return DLKA_OK;
+}
+
 int dlka_deform_conv2d_sample_indices(const float *offset, int32_t *low, int32_t *mask, int B, int H, int W, int kh, int kw, int sh,
                                       int sw, int ph, int pw, int dilh, int dilw, int n_offset_grps, void *stream)
 {

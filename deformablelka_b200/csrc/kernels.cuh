@@ -131,6 +131,10 @@ int deform3d_backward_cl(const ConvGeo &g, const float *x, const float *off, con
                          float *gw, float *gb, float *wt, float *gwt, float *colbuf, float *colT, float *gchunk, float *gchunkT,
                          float *partial /* [Mc/512 + 1][K*C*Co] split-K partial products */, float *wscratch, int math, cudaStream_t st);
 
+// ---------------- backward of the 2D deformable conv (deform2d_bwd.cu), channels-last, every forward configuration ----------------
+int deform2d_backward_cl(const ConvGeo &g, const float *x, const float *w, const float *off, const float *mask, const float *gout,
+                         float *gx, float *gw, float *goff, float *gmask, float *gb, cudaStream_t st);
+
 // dense 3x3x3 conv C->C (stride 1, pad 1) on channels-last tokens with folded per-channel scale/shift and
 // LeakyReLU (+ residual): the two convolutions of UnetResBlock (row N3).  SIMT fp32 fallback when math != bf16x3.
 int conv3_bn_act_cl(const float *x, const float *w, const float *scale, const float *shift, int act, float slope, const float *E,

@@ -20,13 +20,29 @@ from . import ops
 from .lka3d import needs_autograd
 
 
-def _refuse_autograd(module, x, what):
-    """The fused 2D entries have no backward: refuse instead of returning a tensor that is cut off from the graph."""
-    if needs_autograd(module, x):
-        raise RuntimeError(
-            f"{what}: the fused forward is inference-only and a gradient is required (grad mode is on and the input or a "
-            "parameter requires grad). Wrap the call in torch.no_grad() / call .requires_grad_(False) for inference; "
-            "training through the 2D deformable operator is not implemented in deformablelka_b200")
+class DeformConv2dFunction(torch.autograd.Function):
+    """Autograd bridge of the 2D operator: library forward (dlka_deform_conv2d_forward) and library backward
+    (dlka_deform_conv2d_backward) -- the gradients torch.ops.torchvision.deform_conv2d's autograd returns."""
+
+    @staticmethod
+    def forward(ctx, input, offset, weight, bias, mask, stride, padding, dilation):
+        ctx.cfg = (stride, padding, dilation)
+        ctx.save_for_backward(input, offset, weight, bias, mask)
+        return ops.deform_conv2d(input, offset, weight, bias, stride, padding, dilation, mask)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        input, offset, weight, bias, mask = ctx.saved_tensors
+        stride, padding, dilation = ctx.cfg
+        gi, go, gw, gm, gb = ops.deform_conv2d_backward(input, offset, weight, mask, grad_output, stride, padding, dilation,
+                                                        need_bias_grad=bias is not None)
+        return gi, go, gw, gb, gm, None, None, None
+
+
+def deform_conv2d_autograd(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1), mask=None):
+    """``ops.deform_conv2d`` that autograd can differentiate (used by the modules below when a gradient can be asked for)."""
+    return DeformConv2dFunction.apply(input, offset, weight, bias, mask, _pair(stride), _pair(padding), _pair(dilation))
 
 
 class DeformConv2d(nn.Module):
@@ -56,9 +72,8 @@ class DeformConv2d(nn.Module):
             nn.init.uniform_(self.bias, -bound, bound)
 
     def forward(self, input, offset, mask=None):
-        _refuse_autograd(self, input, "DeformConv2d")
-        if offset.requires_grad and torch.is_grad_enabled():
-            raise RuntimeError("DeformConv2d: offset requires grad, but the 2D deformable operator has no backward here")
+        if needs_autograd(self, input, offset, mask):
+            return deform_conv2d_autograd(input, offset, self.weight, self.bias, self.stride, self.padding, self.dilation, mask)
         return ops.deform_conv2d(input, offset, self.weight, self.bias, self.stride, self.padding, self.dilation, mask)
 
 
@@ -73,7 +88,11 @@ class DeformConv(nn.Module):
                                         padding=padding, groups=groups, stride=stride, dilation=dilation, bias=False)
 
     def forward(self, x):
-        _refuse_autograd(self, x, "DeformConv")
+        if needs_autograd(self, x):
+            # training: the reference's own two steps (deformable_LKA.py:27-30) -- stock offset_net, differentiable operator
+            with torch.backends.cudnn.flags(allow_tf32=False):   # offsets are sampling positions: keep them fp32
+                offsets = self.offset_net(x)
+            return self.deform_conv(x, offsets)
         return ops.deform_conv_pack2d(x, self.offset_net.weight, self.offset_net.bias, self.deform_conv.weight,
                                       self.deform_conv.bias, self.deform_conv.stride, self.deform_conv.padding,
                                       self.deform_conv.dilation)
@@ -102,8 +121,9 @@ class deformable_LKA(nn.Module):
         self.conv1 = nn.Conv2d(dim, dim, 1)
 
     def forward(self, x):
-        # u * conv1(conv_spatial(conv0(x)))  in one library call (deformable_LKA.py:98-104)
-        _refuse_autograd(self, x, "deformable_LKA")
+        if needs_autograd(self, x):   # differentiable composition (deformable_LKA.py:98-104)
+            return x * self.conv1(self.conv_spatial(self.conv0(x)))
+        # u * conv1(conv_spatial(conv0(x)))  in one library call
         return ops.deformable_lka2d_forward(_block2d_params(self), x)
 
 
@@ -116,6 +136,7 @@ class deformable_LKA_Attention(nn.Module):
         self.proj_2 = nn.Conv2d(d_model, d_model, 1)
 
     def forward(self, x):
-        # proj_1 -> GELU -> gating unit -> proj_2 -> + shortcut (deformable_LKA.py:133-140)
-        _refuse_autograd(self, x, "deformable_LKA_Attention")
+        if needs_autograd(self, x):   # differentiable composition (deformable_LKA.py:133-140)
+            return self.proj_2(self.spatial_gating_unit(self.activation(self.proj_1(x)))) + x
+        # proj_1 -> GELU -> gating unit -> proj_2 -> + shortcut in one library call
         return ops.deformable_lka_attention2d_forward(_block2d_params(self.spatial_gating_unit, self), x)

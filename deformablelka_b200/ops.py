@@ -135,6 +135,36 @@ def deform_conv2d(input: torch.Tensor, offset: torch.Tensor, weight: torch.Tenso
     return out
 
 
+def deform_conv2d_backward(input, offset, weight, mask, grad_output, stride=(1, 1), padding=(0, 0), dilation=(1, 1),
+                           need_bias_grad: bool = False):
+    """Gradients of ``torchvision.ops.deform_conv2d`` (row N2, 2D half): returns (grad_input, grad_offset, grad_weight,
+    grad_mask or None, grad_bias or None) -- what autograd through torch.ops.torchvision.deform_conv2d returns."""
+    if not input.is_cuda:
+        raise RuntimeError("Not implemented on the CPU (deformablelka_b200 is CUDA-only)")
+    sh, sw = _pair(stride); ph, pw = _pair(padding); dh, dw = _pair(dilation)
+    B, C, H, W = input.shape
+    Co, Cg, kh, kw = weight.shape
+    n_off = offset.shape[1] // (2 * kh * kw)
+    n_wg = C // Cg
+    Ho, Wo = _out_extent(H, ph, dh, kh, sh), _out_extent(W, pw, dw, kw, sw)
+    if tuple(grad_output.shape) != (B, Co, Ho, Wo):
+        raise RuntimeError(f"grad_output shape {tuple(grad_output.shape)} does not match {(B, Co, Ho, Wo)}")
+    input = input.contiguous(); offset = offset.contiguous(); weight = weight.contiguous(); grad_output = grad_output.contiguous()
+    mask = None if mask is None else mask.contiguous()
+    gi, go, gw = torch.empty_like(input), torch.empty_like(offset), torch.empty_like(weight)
+    gm = None if mask is None else torch.empty_like(mask)
+    gb = torch.empty(Co, dtype=torch.float32, device=input.device) if need_bias_grad else None
+    ws = Workspace.get(input.device, lib.dlka_deform_conv2d_backward_workspace_bytes(
+        B, C, H, W, Co, kh, kw, sh, sw, ph, pw, dh, dw, n_wg, n_off, 0 if mask is None else 1))
+    with torch.cuda.device(input.device):
+        st = lib.dlka_deform_conv2d_backward(
+            dptr(input, "input"), dptr(weight, "weight"), dptr(offset, "offset"), dptr(mask, "mask"), dptr(grad_output, "grad_output"),
+            dptr(gi), dptr(gw), dptr(go), dptr(gm), dptr(gb), B, C, H, W, Co, kh, kw, sh, sw, ph, pw, dh, dw, n_wg, n_off,
+            ws.data_ptr(), ws.numel(), stream_ptr(input.device))
+    check(st, "dlka_deform_conv2d_backward")
+    return gi, go, gw, gm, gb
+
+
 def deform_conv2d_sample_indices(offset, in_size, kernel_size, stride=1, padding=0, dilation=1, n_offset_grps=1):
     H, W = in_size
     kh, kw = _pair(kernel_size); sh, sw = _pair(stride); ph, pw = _pair(padding); dh, dw = _pair(dilation)

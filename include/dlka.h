@@ -147,6 +147,18 @@ DLKA_API int dlka_deform_conv2d_forward(const float *input, const float *weight,
                                int sh, int sw, int ph, int pw, int dilh, int dilw,
                                int n_weight_grps, int n_offset_grps, int math,
                                void *workspace, size_t workspace_bytes, void *stream);
+/* Backward of the 2D operator: the gradients torchvision's autograd returns for deform_conv2d
+ * (torchvision/ops/deform_conv.py:92-107; published kernels deformable_col2im / deformable_col2im_coord + the weight GEMM):
+ * grad_input [B,C,H,W], grad_weight [Co,C/g,kh,kw], grad_offset like offset, grad_mask like mask (both NULL without a mask),
+ * grad_bias [Co] or NULL.  Every forward configuration (weight groups incl. depthwise, offset groups, DCNv2 mask); fp32.   */
+DLKA_API size_t dlka_deform_conv2d_backward_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw,
+                                                   int sh, int sw, int ph, int pw, int dilh, int dilw,
+                                                   int n_weight_grps, int n_offset_grps, int has_mask);
+DLKA_API int dlka_deform_conv2d_backward(const float *input, const float *weight, const float *offset, const float *mask,
+                                const float *grad_output, float *grad_input, float *grad_weight, float *grad_offset,
+                                float *grad_mask, float *grad_bias, int B, int C, int H, int W, int Co, int kh, int kw,
+                                int sh, int sw, int ph, int pw, int dilh, int dilw, int n_weight_grps, int n_offset_grps,
+                                void *workspace, size_t workspace_bytes, void *stream);
 DLKA_API int dlka_deform_conv2d_sample_indices(const float *offset, int32_t *low, int32_t *mask,
                                       int B, int H, int W, int kh, int kw, int sh, int sw,
                                       int ph, int pw, int dilh, int dilw, int n_offset_grps, void *stream);

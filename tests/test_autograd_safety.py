@@ -123,26 +123,69 @@ def test_patch_expand_grad_path_matches_oracle_cpu(cpu_operator, oracle):
         assert m.expand.weight.grad is not None
 
 
-def test_fused_2d_entries_refuse_when_grad_is_required():
+@pytest.fixture
+def cpu_operator2d(monkeypatch):
+    """Stand-in for the CUDA-only 2D operator (forward and backward) built on torchvision's CPU op: routing tests only."""
+    import torchvision
     import deformablelka_b200 as dl
-    m = dl.deformable_LKA_Attention(8)
-    blk = dl.deformableLKABlock(8)
-    x = torch.randn(1, 8, 5, 5)
+
+    def fwd(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1), mask=None, math=None):
+        return torchvision.ops.deform_conv2d(input, offset, weight, bias, stride, padding, dilation, mask)
+
+    def bwd(input, offset, weight, mask, grad_output, stride=(1, 1), padding=(0, 0), dilation=(1, 1), need_bias_grad=False):
+        with torch.enable_grad():
+            x, o, w = (t.detach().clone().requires_grad_() for t in (input, offset, weight))
+            m = None if mask is None else mask.detach().clone().requires_grad_()
+            b = torch.zeros(weight.shape[0], requires_grad=True) if need_bias_grad else None
+            torchvision.ops.deform_conv2d(x, o, w, b, stride, padding, dilation, m).backward(grad_output)
+        return x.grad, o.grad, w.grad, None if m is None else m.grad, None if b is None else b.grad
+
+    monkeypatch.setattr(dl.ops, "deform_conv2d", fwd)
+    monkeypatch.setattr(dl.ops, "deform_conv2d_backward", bwd)
+
+    def fused(*a, **k):
+        raise AssertionError("the fused (non-differentiable) entry was taken although a gradient is required")
+
+    for name in ("deformable_lka2d_forward", "deformable_lka_attention2d_forward", "deformable_lka_block2d_forward",
+                 "deform_conv_pack2d", "linear_tokens_forward", "patch_expand2d_forward"):
+        monkeypatch.setattr(dl.ops, name, fused)
     with mock.patch.object(torch.Tensor, "is_cuda", new_callable=mock.PropertyMock, return_value=True):
-        for call in (lambda: m(x), lambda: m.spatial_gating_unit(x), lambda: m.spatial_gating_unit.conv0(x),
-                     lambda: blk(torch.randn(1, 25, 8), 5, 5)):
-            with pytest.raises(RuntimeError, match="gradient is required"):
-                call()
-        m.requires_grad_(False)
-        with pytest.raises(RuntimeError, match="gradient is required"):   # the input still asks for one
-            m(x.clone().requires_grad_())
+        yield dl
+
+
+def test_block2d_routes_to_differentiable_path_cpu(cpu_operator2d, oracle):
+    """deformable_LKA_Attention / deformableLKABlock / MyDecoderLayer with grad required: composed from stock layers around the
+    differentiable 2D operator; gradients equal autograd through the oracle's modules (torchvision's own autograd)."""
+    dl = cpu_operator2d
+    torch.manual_seed(4)
+    C, H, W = 8, 7, 6
+    m, om = dl.deformableLKABlock(C), oracle.deformableLKABlock(C)
+    with torch.no_grad():
+        m.layer_scale_1.uniform_(0.2, 1.0); m.layer_scale_2.uniform_(0.2, 1.0)
+    om.load_state_dict(m.state_dict())
+    x = torch.randn(2, H * W, C, requires_grad=True)
+    xo = x.detach().clone().requires_grad_()
+    y, yo = m(x, H, W), om(xo, H, W)
+    assert y.grad_fn is not None and rel_err(y, yo) < 1e-5
+    y.square().sum().backward(); yo.square().sum().backward()
+    assert rel_err(x.grad, xo.grad) < 1e-4
+    for (n, p), (_, po) in zip(m.named_parameters(), om.named_parameters()):
+        assert p.grad is not None, n
+        assert rel_err(p.grad, po.grad) < 1e-4, n
+    # the decoder stage: every sub-module on its differentiable path
+    d, od = dl.MyDecoderLayer((H, W), [C] * 5, 1, "mix_skip", is_last=True), oracle.MyDecoderLayer((H, W), [C] * 5, 1, "mix_skip", is_last=True)
+    od.load_state_dict(d.state_dict())
+    x1, x2 = torch.randn(1, H * W, C, requires_grad=True), torch.randn(1, H, W, C)
+    out, oout = d(x1, x2), od(x1.detach(), x2)
+    assert out.grad_fn is not None and rel_err(out, oout) < 1e-5
+    out.sum().backward()
+    assert all(p.grad is not None for p in d.parameters())
     # CPU tensors are refused either way (no CPU path)
-    with pytest.raises(RuntimeError, match="CPU"):
-        dl.deformable_LKA_Attention(8)(x)
-    with torch.no_grad(), pytest.raises(RuntimeError, match="CPU"):
-        dl.deformable_LKA_Attention(8)(x)
-    with pytest.raises(RuntimeError, match="CPU"):
-        dl.PatchExpand((2, 2), 16)(torch.randn(1, 4, 16))
+    with mock.patch.object(torch.Tensor, "is_cuda", new_callable=mock.PropertyMock, return_value=False):
+        with pytest.raises(RuntimeError, match="CPU"):
+            dl.deformable_LKA_Attention(8)(torch.randn(1, 8, 5, 5))
+        with pytest.raises(RuntimeError, match="CPU"):
+            dl.PatchExpand((2, 2), 16)(torch.randn(1, 4, 16))
 
 
 # ------------------------------------------------------------------------------------------------ GPU
@@ -178,11 +221,71 @@ def test_attention3d_backward_on_gpu_vs_oracle(oracle, acdc):
 
 
 @pytest.mark.gpu
-def test_fused_2d_refuses_on_gpu():
+@pytest.mark.parametrize("C,Co,wg,og,k,stride,pad,dil,use_mask,use_bias", [
+    (16, 16, 16, 1, (5, 5), 1, 2, 1, False, False),       # depthwise, as conv0 of the 2D block (register-accumulated weight gradient)
+    (16, 16, 16, 1, (7, 7), 1, 9, 3, False, False),       # depthwise dilated, as conv_spatial
+    (40, 40, 40, 1, (3, 3), 1, 1, 1, False, True),        # depthwise 3x3, channels not a multiple of 32
+    (8, 8, 1, 1, (3, 3), 1, 1, 1, False, True),           # dense
+    (16, 8, 2, 2, (3, 5), (1, 2), (2, 3), (2, 1), True, True),   # weight groups + offset groups + mask + stride / dilation
+    (64, 64, 64, 2, (3, 3), 2, 1, 1, True, False),        # depthwise + 2 offset groups of 32 channels (warp-uniform reduction) + mask
+])
+def test_deform_conv2d_backward_vs_torchvision_autograd(C, Co, wg, og, k, stride, pad, dil, use_mask, use_bias):
+    import torchvision
     import deformablelka_b200 as dl
-    m = dl.deformable_LKA_Attention(8).to("cuda:0")
-    x = torch.randn(1, 8, 6, 6, device="cuda:0")
-    with pytest.raises(RuntimeError, match="gradient is required"):
-        m(x)
+    from oracle import oracle as o
+    torch.manual_seed(5)
+    B, H, W = 2, 13, 11
+    kh, kw = k
+    sh, sw = o._pair(stride); ph, pw = o._pair(pad); dh, dw = o._pair(dil)
+    Ho, Wo = o.out_extent(H, ph, dh, kh, sh), o.out_extent(W, pw, dw, kw, sw)
+    x = torch.randn(B, C, H, W, requires_grad=True)
+    w = (torch.randn(Co, C // wg, kh, kw) * 0.3).requires_grad_()
+    b = torch.randn(Co, requires_grad=True) if use_bias else None
+    off = (torch.randn(B, og * 2 * kh * kw, Ho, Wo) * 2).requires_grad_()
+    mask = torch.rand(B, og * kh * kw, Ho, Wo, requires_grad=True) if use_mask else None
+    gout = torch.randn(B, Co, Ho, Wo)
+    torchvision.ops.deform_conv2d(x, off, w, b, stride, pad, dil, mask).backward(gout)
+    dev = "cuda:0"
+    xg, wg_, og_ = (t.detach().to(dev).requires_grad_() for t in (x, w, off))
+    bg = None if b is None else b.detach().to(dev).requires_grad_()
+    mg = None if mask is None else mask.detach().to(dev).requires_grad_()
+    from deformablelka_b200.deformable_LKA import deform_conv2d_autograd
+    y = deform_conv2d_autograd(xg, og_, wg_, bg, stride, pad, dil, mg)
+    y.backward(gout.to(dev))
+    pairs = [("grad_input", xg.grad, x.grad), ("grad_weight", wg_.grad, w.grad), ("grad_offset", og_.grad, off.grad)]
+    if use_bias:
+        pairs.append(("grad_bias", bg.grad, b.grad))
+    if use_mask:
+        pairs.append(("grad_mask", mg.grad, mask.grad))
+    for name, got, want in pairs:
+        assert got.shape == want.shape, name
+        assert rel_err(got, want) < TOL, name
+
+
+@pytest.mark.gpu
+def test_block2d_backward_on_gpu_vs_oracle(oracle):
+    import deformablelka_b200 as dl
+    torch.manual_seed(6)
+    C, H, W = 32, 12, 10
+    m = dl.deformable_LKA_Attention(C)
+    om = oracle.deformable_LKA_Attention(C)
+    om.load_state_dict(m.state_dict())
+    x = torch.randn(2, C, H, W)
+    xo = x.clone().requires_grad_()
+    om(xo).square().sum().backward()
+    m = m.to("cuda:0")
+    xg = x.to("cuda:0").requires_grad_()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = m(xg)
+        assert y.grad_fn is not None
+        y.square().sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
     with torch.no_grad():
-        assert m(x).shape == x.shape
+        assert rel_err(m(xg.detach()), om(x)) < TOL      # the fused inference call computes the same function
+    assert rel_err(xg.grad, xo.grad) < TOL
+    for (n, p), (_, po) in zip(m.named_parameters(), om.named_parameters()):
+        assert p.grad is not None, n
+        assert rel_err(p.grad, po.grad) < 2e-3, n
