@@ -342,13 +342,14 @@ def main():
         # end-to-end through the module API with host buffers: pinned H2D of the step input, D2H of the result
         e2e = None
         if not args.no_e2e:
-            xh = dl.ops.pinned_empty((B, N, C), dev)
+            wc = os.environ.get("DLKA_HOST_WC", "0") == "1"     # write-combined input buffer (the host only writes it)
+            xh = dl.ops.pinned_empty((B, N, C), dev, write_combined=wc)
             yh = dl.ops.pinned_empty((B, N, C), dev)
-            xh.normal_(generator=torch.Generator().manual_seed(4321 + rank))
+            xh.copy_(torch.randn(B, N, C, generator=torch.Generator().manual_seed(4321 + rank)))   # writes only (a write-combined buffer must not be read)
             # streaming serving loop through the public module API: every step copies its input from pinned host memory
             # and its result back to pinned host memory; the pipeline keeps 2 steps in flight (H2D of step k+1 and D2H of
             # step k-1 overlap the compute of step k).
-            pipe = m.host_pipe(depth=2)
+            pipe = m.host_pipe(depth=int(os.environ.get("DLKA_PIPE_DEPTH", "2")))
             ksteps = max(4, args.steps)
             for _ in range(3):
                 m.submit_host(pipe, xh, yh, B, C, D1, D2, D3)

@@ -100,6 +100,14 @@ def _load() -> ctypes.CDLL:
         getattr(lib, name + "_workspace_bytes").argtypes = [I] * 5
         getattr(lib, name + "_forward").restype = c_int
         getattr(lib, name + "_forward").argtypes = [POINTER(Block3dParams), V, V] + [I] * 6 + [V, c_size_t, V]
+    lib.dlka_lka_attention3d_deform_packed_bytes.restype = c_size_t
+    lib.dlka_lka_attention3d_deform_packed_bytes.argtypes = [I]
+    lib.dlka_lka_attention3d_deform_forward_packed.restype = c_int
+    lib.dlka_lka_attention3d_deform_forward_packed.argtypes = [POINTER(Block3dParams), V, V] + [I] * 6 + [V, c_size_t, I, V, c_size_t, V]
+    lib.dlka_deformable_lka_attention2d_packed_bytes.restype = c_size_t
+    lib.dlka_deformable_lka_attention2d_packed_bytes.argtypes = [I]
+    lib.dlka_deformable_lka_attention2d_forward_packed.restype = c_int
+    lib.dlka_deformable_lka_attention2d_forward_packed.argtypes = [POINTER(Block2dParams), V, V] + [I] * 5 + [V, c_size_t, I, V, c_size_t, V]
     lib.dlka_lka_attention3d_deform_forward_host.restype = c_int
     lib.dlka_lka_attention3d_deform_forward_host.argtypes = (
         [POINTER(Block3dParams), V, V] + [I] * 6 + [V, c_size_t, V, c_size_t, V])

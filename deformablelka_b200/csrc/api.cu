@@ -17,6 +17,11 @@ static std::atomic<uint64_t> g_launches{0};
 
 void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+static thread_local bool g_pack_skip = false;
+bool pack_skipped() { return g_pack_skip; }
+PackSkipScope::PackSkipScope(bool skip) : prev(g_pack_skip) { g_pack_skip = skip; }
+PackSkipScope::~PackSkipScope() { g_pack_skip = prev; }
+
 // ---- optional per-kernel event timing ---------------------------------------------------
 struct ProfRec {
     const char *name;
@@ -204,8 +209,10 @@ struct Block3dPlan {
     int np_c, np_off;
 };
 
-bool plan_block3d(Arena &ar, int B, int C, int D1, int D2, int D3, Block3dPlan &p)
+// wpk: arena of the packed weights (the caller's persistent buffer of *_forward_packed), or null = scratch in the workspace
+bool plan_block3d(Arena &ar, int B, int C, int D1, int D2, int D3, Block3dPlan &p, Arena *wpk = nullptr)
 {
+    Arena &wa = wpk ? *wpk : ar;
     const size_t M = (size_t)B * D1 * D2 * D3;
     p.np_c = p.np_off = 0;
     p.t1 = ar.take<float>(M * C);
@@ -215,14 +222,14 @@ bool plan_block3d(Arena &ar, int B, int C, int D1, int D2, int D3, Block3dPlan &
         const size_t brick = deform3d_ps_offset_floats(B, D1, D2, D3, 81);
         p.off = ar.take<float>(M * OFF3D_LD > brick ? M * OFF3D_LD : brick);
     }
-    p.wp_proj1 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
-    p.wp_conv1 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
-    p.wp_proj2 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
-    p.wp_off = ar.take<float>(contraction_scratch_floats(81, C, 27, 1));
-    p.wp_dcn = ar.take<float>(contraction_scratch_floats(C, C, 27, 1));
-    p.wp_dw5 = ar.take<float>((size_t)125 * C);
-    p.wp_dw7 = ar.take<float>((size_t)343 * C);
-    return ar.ok();
+    p.wp_proj1 = wa.take<float>(contraction_scratch_floats(C, C, 1, 1));
+    p.wp_conv1 = wa.take<float>(contraction_scratch_floats(C, C, 1, 1));
+    p.wp_proj2 = wa.take<float>(contraction_scratch_floats(C, C, 1, 1));
+    p.wp_off = wa.take<float>(contraction_scratch_floats(81, C, 27, 1));
+    p.wp_dcn = wa.take<float>(contraction_scratch_floats(C, C, 27, 1));
+    p.wp_dw5 = wa.take<float>((size_t)125 * C);
+    p.wp_dw7 = wa.take<float>((size_t)343 * C);
+    return ar.ok() && wa.ok();
 }
 
 // packed depthwise weights live in fixed workspace slots sized for 5^3 and 7^3 taps
@@ -333,8 +340,9 @@ struct Block2dPlan {
     int np_c, np_off0, np_off1;
 };
 
-bool plan_block2d(Arena &ar, int B, int C, int H, int W, Block2dPlan &p)
+bool plan_block2d(Arena &ar, int B, int C, int H, int W, Block2dPlan &p, Arena *wpk = nullptr)
 {
+    Arena &wa = wpk ? *wpk : ar;
     const size_t M = (size_t)B * H * W;
     p.np_c = p.np_off0 = p.np_off1 = 0;
     p.x_cl = ar.take<float>(M * C);
@@ -342,14 +350,14 @@ bool plan_block2d(Arena &ar, int B, int C, int H, int W, Block2dPlan &p)
     p.t2 = ar.take<float>(M * C);
     p.t3 = ar.take<float>(M * C);
     p.off = ar.take<float>(M * 98);
-    p.wp_proj1 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
-    p.wp_conv1 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
-    p.wp_proj2 = ar.take<float>(contraction_scratch_floats(C, C, 1, 1));
-    p.wp_off0 = ar.take<float>(contraction_scratch_floats(50, C, 25, 1));
-    p.wp_off1 = ar.take<float>(contraction_scratch_floats(98, C, 49, 1));
-    p.wp_dw0 = ar.take<float>((size_t)25 * C);
-    p.wp_dw1 = ar.take<float>((size_t)49 * C);
-    return ar.ok();
+    p.wp_proj1 = wa.take<float>(contraction_scratch_floats(C, C, 1, 1));
+    p.wp_conv1 = wa.take<float>(contraction_scratch_floats(C, C, 1, 1));
+    p.wp_proj2 = wa.take<float>(contraction_scratch_floats(C, C, 1, 1));
+    p.wp_off0 = wa.take<float>(contraction_scratch_floats(50, C, 25, 1));
+    p.wp_off1 = wa.take<float>(contraction_scratch_floats(98, C, 49, 1));
+    p.wp_dw0 = wa.take<float>((size_t)25 * C);
+    p.wp_dw1 = wa.take<float>((size_t)49 * C);
+    return ar.ok() && wa.ok();
 }
 
 // u channels-last -> u * conv1(conv_spatial(conv0(u))) into p.t2
@@ -862,17 +870,19 @@ size_t dlka_lka_attention3d_deform_workspace_bytes(int B, int C, int D1, int D2,
     return dlka_lka3d_deform_workspace_bytes(B, C, D1, D2, D3);
 }
 
-int dlka_lka_attention3d_deform_forward(const dlkaBlock3dParams *params, const float *x, float *y, int B, int C, int D1, int D2,
-                                        int D3, int math, void *workspace, size_t workspace_bytes, void *stream)
+namespace {
+int attention3d_impl(const dlkaBlock3dParams *params, const float *x, float *y, int B, int C, int D1, int D2, int D3, int math,
+                     void *packed, size_t packed_bytes, int packed_valid, void *workspace, size_t workspace_bytes, void *stream)
 {
     if (null_params3d(params, true) || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
     if (B <= 0 || C <= 0 || D1 <= 0 || D2 <= 0 || D3 <= 0) return DLKA_ERR_INVALID_ARGUMENT;
     if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
     DLKA_TRY(check_device());
     cudaStream_t st = (cudaStream_t)stream;
-    Arena ar(workspace, workspace_bytes);
+    Arena ar(workspace, workspace_bytes), pk(packed, packed_bytes);
     Block3dPlan p;
-    if (!plan_block3d(ar, B, C, D1, D2, D3, p)) return DLKA_ERR_WORKSPACE;
+    if (!plan_block3d(ar, B, C, D1, D2, D3, p, packed ? &pk : nullptr)) return DLKA_ERR_WORKSPACE;
+    PackSkipScope skip(packed != nullptr && packed_valid != 0);
     const i64 M = (i64)B * D1 * D2 * D3;
     // tokens [B,N,C] are already channels-last over the Conv3d volume (transformerblock.py:665)
     IgemmArgs a1 = dense_args(x, C, M, C, C, nullptr, 0, params->proj_1_bias, EPI_GELU, nullptr, 0, p.t1, C);
@@ -883,6 +893,30 @@ int dlka_lka_attention3d_deform_forward(const dlkaBlock3dParams *params, const f
     IgemmArgs a2 = dense_args(p.t3, C, M, C, C, nullptr, 0, params->proj_2_bias, EPI_ADD, x, C, y, C);
     DLKA_TRY(contraction(a2, params->proj_2_weight, math, p.wp_proj2, st));
     return DLKA_OK;
+}
+}  // namespace
+
+int dlka_lka_attention3d_deform_forward(const dlkaBlock3dParams *params, const float *x, float *y, int B, int C, int D1, int D2,
+                                        int D3, int math, void *workspace, size_t workspace_bytes, void *stream)
+{
+    return attention3d_impl(params, x, y, B, C, D1, D2, D3, math, nullptr, 0, 0, workspace, workspace_bytes, stream);
+}
+
+size_t dlka_lka_attention3d_deform_packed_bytes(int C)
+{
+    if (C <= 0) return 0;
+    Arena ar(nullptr, 0), pk(nullptr, 0);
+    Block3dPlan p;
+    plan_block3d(ar, 1, C, 1, 1, 1, p, &pk);
+    return pk.off + 256;
+}
+
+int dlka_lka_attention3d_deform_forward_packed(const dlkaBlock3dParams *params, const float *x, float *y, int B, int C, int D1,
+                                               int D2, int D3, int math, void *packed, size_t packed_bytes, int packed_valid,
+                                               void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!packed) return DLKA_ERR_INVALID_ARGUMENT;
+    return attention3d_impl(params, x, y, B, C, D1, D2, D3, math, packed, packed_bytes, packed_valid, workspace, workspace_bytes, stream);
 }
 
 int dlka_lka_attention3d_deform_forward_host(const dlkaBlock3dParams *params, const float *x_host, float *y_host, int B, int C,
@@ -979,21 +1013,47 @@ size_t dlka_deformable_lka_attention2d_workspace_bytes(int B, int C, int H, int 
     return dlka_deformable_lka2d_workspace_bytes(B, C, H, W);
 }
 
-int dlka_deformable_lka_attention2d_forward(const dlkaBlock2dParams *params, const float *x, float *y, int B, int C, int H, int W,
-                                            int math, void *workspace, size_t workspace_bytes, void *stream)
+namespace {
+int attention2d_impl(const dlkaBlock2dParams *params, const float *x, float *y, int B, int C, int H, int W, int math, void *packed,
+                     size_t packed_bytes, int packed_valid, void *workspace, size_t workspace_bytes, void *stream)
 {
     if (null_params2d(params, true) || !x || !y) return DLKA_ERR_INVALID_ARGUMENT;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return DLKA_ERR_INVALID_ARGUMENT;
     if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
     DLKA_TRY(check_device());
     cudaStream_t st = (cudaStream_t)stream;
-    Arena ar(workspace, workspace_bytes);
+    Arena ar(workspace, workspace_bytes), pk(packed, packed_bytes);
     Block2dPlan p;
-    if (!plan_block2d(ar, B, C, H, W, p)) return DLKA_ERR_WORKSPACE;
+    if (!plan_block2d(ar, B, C, H, W, p, packed ? &pk : nullptr)) return DLKA_ERR_WORKSPACE;
+    PackSkipScope skip(packed != nullptr && packed_valid != 0);
     DLKA_TRY(transpose_cs_to_sc(x, p.x_cl, B, C, (i64)H * W, st));
     DLKA_TRY(attention2d_cl_planned(*params, p.x_cl, p.t3, p, B, C, H, W, math, st));
     DLKA_TRY(transpose_sc_to_cs(p.t3, y, B, C, (i64)H * W, st));
     return DLKA_OK;
+}
+}  // namespace
+
+int dlka_deformable_lka_attention2d_forward(const dlkaBlock2dParams *params, const float *x, float *y, int B, int C, int H, int W,
+                                            int math, void *workspace, size_t workspace_bytes, void *stream)
+{
+    return attention2d_impl(params, x, y, B, C, H, W, math, nullptr, 0, 0, workspace, workspace_bytes, stream);
+}
+
+size_t dlka_deformable_lka_attention2d_packed_bytes(int C)
+{
+    if (C <= 0) return 0;
+    Arena ar(nullptr, 0), pk(nullptr, 0);
+    Block2dPlan p;
+    plan_block2d(ar, 1, C, 1, 1, p, &pk);
+    return pk.off + 256;
+}
+
+int dlka_deformable_lka_attention2d_forward_packed(const dlkaBlock2dParams *params, const float *x, float *y, int B, int C, int H,
+                                                   int W, int math, void *packed, size_t packed_bytes, int packed_valid,
+                                                   void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!packed) return DLKA_ERR_INVALID_ARGUMENT;
+    return attention2d_impl(params, x, y, B, C, H, W, math, packed, packed_bytes, packed_valid, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -86,6 +86,17 @@ struct SmemOptIn {
     }
 };
 
+// Prepacked weights (dlka_*_forward_packed): while a PackSkipScope is alive on this HOST thread, the weight-packing launchers
+// (tc_pack_weight, pack_weight, pack_dw, deform3d_ps_pack, the packers inside conv_tiled_ex / deform3d_tc, pack_dw9) return
+// without launching -- the caller has promised that the packed buffers already hold these weights.  Host-side, per thread,
+// scoped to one entry-point call: no device state.
+bool pack_skipped();
+struct PackSkipScope {
+    bool prev;
+    explicit PackSkipScope(bool skip);
+    ~PackSkipScope();
+};
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline i64 cdiv(i64 a, i64 b) { return (a + b - 1) / b; }
 

@@ -375,7 +375,7 @@ int conv_tiled_ex(const IgemmArgs &g, const float *w, const float *wscale, int a
     a.act = act; a.slope = slope; a.E = E; a.ldE = ldE;
     const ConvGeo &geo = g.geo;
     const int n_tiles = (int)cdiv(geo.Co, a.NT);
-    {
+    if (!pack_skipped()) {
         const i64 total = (i64)n_tiles * (geo.C / CT_KCH) * geo.K * 16 * a.NT;
         const int blocks = (int)(cdiv(total, 256) < 148 * 8 ? cdiv(total, 256) : 148 * 8);
         DLKA_LAUNCH("pack_weight_ct", st,

@@ -533,6 +533,7 @@ size_t deform3d_ps_packed_bytes(int Co, int C, int taps) { return (size_t)2 * C 
 
 int deform3d_ps_pack(const float *w, void *bp, int Co, int C, int taps, cudaStream_t st)
 {
+    if (pack_skipped()) return DLKA_OK;   // prepacked weights: see PackSkipScope
     const int NT = tc_nt(Co);
     const i64 total = (i64)taps * C * NT;
     const int blocks = (int)(cdiv(total, 256) < 148 * 8 ? cdiv(total, 256) : 148 * 8);

@@ -702,7 +702,7 @@ int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, const DeformChain
         a.W1p = (const uint8_t *)chain->W1p; a.b1 = chain->b1; a.U = chain->U; a.ldU = chain->ldU;
         a.W2p = (const uint8_t *)chain->W2p; a.b2 = chain->b2; a.R = chain->R; a.ldR = chain->ldR;
     }
-    {
+    if (!pack_skipped()) {
         const i64 total = (i64)n_tiles * g.K * g.C * a.NT;
         const int blocks = (int)(cdiv(total, 256) < 148 * 8 ? cdiv(total, 256) : 148 * 8);
         DLKA_LAUNCH("pack_weight_df", st,

@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(256) deform_dwconv_cl_kernel(const float *__re
 
 int pack_dw(const float *w, float *wp, int C, int taps, cudaStream_t st)
 {
+    if (pack_skipped()) return DLKA_OK;   // prepacked weights: see PackSkipScope
     DLKA_LAUNCH("pack_dw_weight", st, pack_dw_weight_kernel<<<(int)cdiv((i64)C * taps, 256), 256, 0, st>>>(w, wp, C, taps));
     return DLKA_OK;
 }

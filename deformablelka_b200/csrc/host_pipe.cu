@@ -153,8 +153,30 @@ int dlka_host_bind_thread(int device)
 // with mbind BEFORE first touch, touched, and registered with cudaHostRegister (portable).  Free with dlka_host_free.
 int dlka_host_alloc(void **ptr, size_t bytes, int device, int policy)
 {
+    // policy | 16: WRITE-COMBINED input buffer (cudaHostAllocWriteCombined: the DMA reads of the H2D copy do not snoop the CPU
+    // caches; the host must only WRITE such a buffer -- CPU reads from it are uncached and very slow)
+    const bool wc = (policy & 16) != 0;
+    policy &= 15;
     if (!ptr || bytes == 0 || policy < 0 || policy > 2) return DLKA_ERR_INVALID_ARGUMENT;
     *ptr = nullptr;
+    if (wc) {
+        // the driver allocates the pages from the calling thread's memory policy: bind it for the duration of the call
+        const int node = device_numa_node(device), nodes = numa_node_count();
+        unsigned long mask[1] = {policy == 1 && node >= 0 ? 1ul << node : (nodes >= 64 ? ~0ul : (1ul << (nodes > 0 ? nodes : 1)) - 1)};
+        if (policy == 1 && node >= 0) syscall(SYS_set_mempolicy, MPOL_BIND, mask, 64ul);
+        else if (policy == 2 && nodes > 1) syscall(SYS_set_mempolicy, MPOL_INTERLEAVE, mask, 64ul);
+        void *q = nullptr;
+        const cudaError_t e = cudaHostAlloc(&q, bytes, cudaHostAllocWriteCombined | cudaHostAllocPortable);
+        if (policy == 1 && node >= 0) { unsigned long pm[1] = {1ul << node}; syscall(SYS_set_mempolicy, MPOL_PREFERRED, pm, 64ul); }
+        else syscall(SYS_set_mempolicy, MPOL_DEFAULT, nullptr, 0ul);
+        if (e != cudaSuccess) return dlka::record_cuda_error(e, "cudaHostAlloc");
+        {
+            std::lock_guard<std::mutex> lk(g_alloc_mu);
+            g_allocs[q] = 0;   // length 0 marks a cudaHostAlloc block
+        }
+        *ptr = q;
+        return DLKA_OK;
+    }
     const size_t len = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
     void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
     if (p == MAP_FAILED) {
@@ -194,6 +216,10 @@ int dlka_host_free(void *ptr)
         if (it == g_allocs.end()) return DLKA_ERR_INVALID_ARGUMENT;
         len = it->second;
         g_allocs.erase(it);
+    }
+    if (len == 0) {   // cudaHostAlloc (write-combined) block
+        const cudaError_t e = cudaFreeHost(ptr);
+        return e == cudaSuccess ? DLKA_OK : dlka::record_cuda_error(e, "cudaFreeHost");
     }
     const cudaError_t e = cudaHostUnregister(ptr);
     munmap(ptr, len);

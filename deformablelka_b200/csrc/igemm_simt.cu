@@ -186,6 +186,7 @@ int igemm_simt_npad(int n_per_group)
 
 int pack_weight(const float *w, float *wp, int Co, int Cg, int taps, int groups, int Npad, cudaStream_t st)
 {
+    if (pack_skipped()) return DLKA_OK;   // prepacked weights: see PackSkipScope
     const i64 total = (i64)groups * taps * Cg * Npad;
     const int blocks = (int)(cdiv(total, 256) < 1184 ? cdiv(total, 256) : 1184);
     DLKA_LAUNCH("pack_weight", st, pack_weight_kernel<<<blocks, 256, 0, st>>>(w, wp, Co, Cg, taps, groups, Npad));

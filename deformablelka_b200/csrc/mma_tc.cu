@@ -445,6 +445,7 @@ size_t tc_packed_weight_bytes(int Co, int C, int taps)
 
 int tc_pack_weight(const float *w, void *bp, int Co, int C, int taps, cudaStream_t st)
 {
+    if (pack_skipped()) return DLKA_OK;   // prepacked weights: see PackSkipScope
     const int KC = tc_kc(C), NT = tc_nt(Co), n_tiles = (int)cdiv(Co, NT);
     if (KC == 0) return DLKA_ERR_UNSUPPORTED;
     const i64 total = (i64)n_tiles * taps * C * NT;

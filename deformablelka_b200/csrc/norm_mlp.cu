@@ -204,7 +204,7 @@ int dwconv2d3_cl(const float *x, const float *w, const float *bias, float *y, in
                  cudaStream_t st)
 {
     if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
-    DLKA_LAUNCH("pack_dw9", st, pack_dw9_kernel<<<(int)cdiv(9 * C, 256), 256, 0, st>>>(w, w_packed, C));
+    if (!pack_skipped()) DLKA_LAUNCH("pack_dw9", st, pack_dw9_kernel<<<(int)cdiv(9 * C, 256), 256, 0, st>>>(w, w_packed, C));
     const i64 total = (i64)B * H * W * (C / 4);
     if (total <= 0) return DLKA_OK;
     const int blocks = (int)(cdiv(total, 256) < 148 * 16 ? cdiv(total, 256) : 148 * 16);

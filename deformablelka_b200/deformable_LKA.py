@@ -139,4 +139,5 @@ class deformable_LKA_Attention(nn.Module):
         if needs_autograd(self, x):   # differentiable composition (deformable_LKA.py:133-140)
             return self.proj_2(self.spatial_gating_unit(self.activation(self.proj_1(x)))) + x
         # proj_1 -> GELU -> gating unit -> proj_2 -> + shortcut in one library call
-        return ops.deformable_lka_attention2d_forward(_block2d_params(self.spatial_gating_unit, self), x)
+        return ops.deformable_lka_attention2d_forward(_block2d_params(self.spatial_gating_unit, self), x,
+                                                      cache=self.__dict__.setdefault("_dlka_pack_cache", {}))

@@ -74,7 +74,9 @@ class LKA_Attention3d_deform(nn.Module):
             v = x.permute(0, 2, 1).reshape(B, C, H, W, D)
             t = self.proj_2(self.spatial_gating_unit(self.activation(self.proj_1(v)))) + v
             return t.reshape(B, C, H * W * D).permute(0, 2, 1)
-        return ops.lka_attention3d_deform_forward(_block3d_params(self.spatial_gating_unit, self), x, B, C, H, W, D)
+        # inference: one library call; the packed weights persist in a per-module cache and are re-packed only when a parameter changes
+        return ops.lka_attention3d_deform_forward(_block3d_params(self.spatial_gating_unit, self), x, B, C, H, W, D,
+                                                  cache=self.__dict__.setdefault("_dlka_pack_cache", {}))
 
     def host_pipe(self, depth: int = 2):
         """A streaming pipeline for `submit_host` (keeps `depth` steps in flight; see ops.HostPipe)."""

@@ -280,15 +280,42 @@ def lka3d_deform_forward(params: dict, x: torch.Tensor, math=None) -> torch.Tens
     return y
 
 
+def _pack_signature(params: dict):
+    """Identity of the parameter VALUES as far as the host can see it: storage pointer + in-place version counter of every tensor."""
+    return tuple((k, t.data_ptr(), t._version) for k, t in sorted(params.items()) if torch.is_tensor(t))
+
+
+def _packed_slot(cache, key, params, nbytes, device):
+    """(buffer, valid) of the prepacked weights for this (module, shape): valid when the buffer was filled from the same
+    parameter values (dlka_*_forward_packed).  `cache` is a plain dict owned by the module."""
+    sig = _pack_signature(params)
+    ent = cache.get(key)
+    if ent is None or ent[0].numel() < nbytes or ent[0].device != device:
+        ent = [torch.empty(nbytes, dtype=torch.uint8, device=device), None]
+        cache[key] = ent
+    return ent, sig
+
+
 def lka_attention3d_deform_forward(params: dict, x: torch.Tensor, B: int, C: int, H: int, W: int, D: int,
-                                   math=None) -> torch.Tensor:
-    """LKA_Attention3d_deform.forward on tokens [B, N, C], N = H*W*D (transformerblock.py:664-673)."""
+                                   math=None, cache: Optional[dict] = None) -> torch.Tensor:
+    """LKA_Attention3d_deform.forward on tokens [B, N, C], N = H*W*D (transformerblock.py:664-673).
+    cache: a dict owned by the calling module -> the packed weights are kept there and re-packed only when a parameter changed."""
     if x.dim() != 3 or x.shape[0] != B or x.shape[1] != H * W * D or x.shape[2] != C:
         raise RuntimeError(f"expected tokens of shape {(B, H * W * D, C)}, got {tuple(x.shape)}")
     x = x.contiguous()
     y = torch.empty_like(x)
     s, keep = _params_struct(Block3dParams, params)
     ws = Workspace.get(x.device, lib.dlka_lka_attention3d_deform_workspace_bytes(B, C, H, W, D))
+    if cache is not None and all(t.is_contiguous() for t in params.values() if torch.is_tensor(t)):
+        mm = _math(math)
+        ent, sig = _packed_slot(cache, ("attn3d", B, C, H, W, D, mm), params, lib.dlka_lka_attention3d_deform_packed_bytes(C), x.device)
+        with torch.cuda.device(x.device):
+            st = lib.dlka_lka_attention3d_deform_forward_packed(
+                ctypes.byref(s), dptr(x, "x"), dptr(y), B, C, H, W, D, mm, ent[0].data_ptr(), ent[0].numel(),
+                1 if ent[1] == sig else 0, ws.data_ptr(), ws.numel(), stream_ptr(x.device))
+        check(st, "dlka_lka_attention3d_deform_forward_packed")
+        ent[1] = sig
+        return y
     with torch.cuda.device(x.device):
         st = lib.dlka_lka_attention3d_deform_forward(ctypes.byref(s), dptr(x, "x"), dptr(y), B, C, H, W, D, _math(math),
                                                      ws.data_ptr(), ws.numel(), stream_ptr(x.device))
@@ -416,8 +443,9 @@ def bind_host_thread(device) -> int:
     return int(lib.dlka_host_bind_thread(device.index if device.index is not None else torch.cuda.current_device()))
 
 
-def pinned_empty(shape, device, policy=None) -> torch.Tensor:
+def pinned_empty(shape, device, policy=None, write_combined: bool = False) -> torch.Tensor:
     """A page-locked fp32 host tensor placed for `device` (dlka_host_alloc: mbind before first touch + cudaHostRegister).
+    write_combined=True: an INPUT buffer the host only writes (cudaHostAllocWriteCombined; CPU reads from it are very slow).
     The memory is released when the tensor (and every view of it) is garbage-collected."""
     import weakref
     device = torch.device(device)
@@ -427,7 +455,8 @@ def pinned_empty(shape, device, policy=None) -> torch.Tensor:
         n *= int(d)
     ptr = ctypes.c_void_p()
     with torch.cuda.device(idx):
-        check(lib.dlka_host_alloc(ctypes.byref(ptr), max(n, 1) * 4, idx, host_numa_policy(policy)), "dlka_host_alloc")
+        check(lib.dlka_host_alloc(ctypes.byref(ptr), max(n, 1) * 4, idx, host_numa_policy(policy) | (16 if write_combined else 0)),
+              "dlka_host_alloc")
     buf = (ctypes.c_float * max(n, 1)).from_address(ptr.value)
     t = torch.frombuffer(buf, dtype=torch.float32, count=n).view(*shape)
     weakref.finalize(buf, lib.dlka_host_free, ptr)   # `buf` is kept alive by the tensor's storage
@@ -530,8 +559,8 @@ def deformable_lka2d_forward(params: dict, x: torch.Tensor, math=None) -> torch.
     return y
 
 
-def deformable_lka_attention2d_forward(params: dict, x: torch.Tensor, math=None) -> torch.Tensor:
-    """deformable_LKA_Attention.forward on NCHW input (deformable_LKA.py:133-140)."""
+def deformable_lka_attention2d_forward(params: dict, x: torch.Tensor, math=None, cache: Optional[dict] = None) -> torch.Tensor:
+    """deformable_LKA_Attention.forward on NCHW input (deformable_LKA.py:133-140); `cache` as in lka_attention3d_deform_forward."""
     if x.dim() != 4:
         raise RuntimeError("expected a 4-D NCHW tensor")
     x = x.contiguous()
@@ -539,6 +568,16 @@ def deformable_lka_attention2d_forward(params: dict, x: torch.Tensor, math=None)
     y = torch.empty_like(x)
     s, keep = _params_struct(Block2dParams, params)
     ws = Workspace.get(x.device, lib.dlka_deformable_lka_attention2d_workspace_bytes(B, C, H, W))
+    if cache is not None and all(t.is_contiguous() for t in params.values() if torch.is_tensor(t)):
+        mm = _math(math)
+        ent, sig = _packed_slot(cache, ("attn2d", B, C, H, W, mm), params, lib.dlka_deformable_lka_attention2d_packed_bytes(C), x.device)
+        with torch.cuda.device(x.device):
+            st = lib.dlka_deformable_lka_attention2d_forward_packed(
+                ctypes.byref(s), dptr(x, "x"), dptr(y), B, C, H, W, mm, ent[0].data_ptr(), ent[0].numel(),
+                1 if ent[1] == sig else 0, ws.data_ptr(), ws.numel(), stream_ptr(x.device))
+        check(st, "dlka_deformable_lka_attention2d_forward_packed")
+        ent[1] = sig
+        return y
     with torch.cuda.device(x.device):
         st = lib.dlka_deformable_lka_attention2d_forward(ctypes.byref(s), dptr(x, "x"), dptr(y), B, C, H, W, _math(math),
                                                          ws.data_ptr(), ws.numel(), stream_ptr(x.device))

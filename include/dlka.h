@@ -218,6 +218,17 @@ DLKA_API size_t dlka_lka_attention3d_deform_workspace_bytes(int B, int C, int D1
 DLKA_API int dlka_lka_attention3d_deform_forward(const dlkaBlock3dParams *params, const float *x, float *y,
                                         int B, int C, int D1, int D2, int D3, int math,
                                         void *workspace, size_t workspace_bytes, void *stream);
+/* Prepacked weights.  The reference keeps its weights in the layout its GEMM consumes (deform_conv_cuda.cu:85,111-117); here the
+ * packed bf16 hi/lo operand tiles of a block live in a caller-owned buffer of *_packed_bytes(C) bytes that persists across
+ * calls.  packed_valid = 0: pack the weights of `params` into `packed`, then run;  packed_valid = 1: the caller asserts that
+ * `packed` was filled by an earlier call with the SAME parameter values, shape (B, C, D1, D2, D3), math and device -- no packing
+ * kernel is launched.  (The Python host keeps one buffer per module and shape, keyed on the parameters' data pointers and
+ * version counters: ops.lka_attention3d_deform_forward(..., cache=).)                                                      */
+DLKA_API size_t dlka_lka_attention3d_deform_packed_bytes(int C);
+DLKA_API int dlka_lka_attention3d_deform_forward_packed(const dlkaBlock3dParams *params, const float *x, float *y,
+                                               int B, int C, int D1, int D2, int D3, int math,
+                                               void *packed, size_t packed_bytes, int packed_valid,
+                                               void *workspace, size_t workspace_bytes, void *stream);
 /* Same call with HOST buffers (x_host, y_host pinned or pageable): H2D, compute, D2H on `stream`,
  * then stream-synchronised.  `params` still holds device pointers; `dev_scratch` must hold
  * 2*B*N*C floats in addition to the workspace (x and y staging).                               */
@@ -274,6 +285,12 @@ DLKA_API int dlka_deformable_lka2d_forward(const dlkaBlock2dParams *params, cons
                                   int B, int C, int H, int W, int math,
                                   void *workspace, size_t workspace_bytes, void *stream);
 DLKA_API size_t dlka_deformable_lka_attention2d_workspace_bytes(int B, int C, int H, int W);
+/* prepacked-weights variant: see dlka_lka_attention3d_deform_forward_packed */
+DLKA_API size_t dlka_deformable_lka_attention2d_packed_bytes(int C);
+DLKA_API int dlka_deformable_lka_attention2d_forward_packed(const dlkaBlock2dParams *params, const float *x, float *y,
+                                                   int B, int C, int H, int W, int math,
+                                                   void *packed, size_t packed_bytes, int packed_valid,
+                                                   void *workspace, size_t workspace_bytes, void *stream);
 DLKA_API int dlka_deformable_lka_attention2d_forward(const dlkaBlock2dParams *params, const float *x, float *y,
                                             int B, int C, int H, int W, int math,
                                             void *workspace, size_t workspace_bytes, void *stream);
