@@ -203,8 +203,9 @@ int run_deform_op(const ConvGeo &g, const float *input, const float *weight, con
 
 // ---- 3D block ---------------------------------------------------------------------------
 constexpr int OFF3D_LD = 84;  // row stride of the [M][81] offset buffer (16-byte aligned rows)
+constexpr size_t SPLIT3D_ROWS = 2048;   // volumes up to this many voxels run the C > 96 deformable conv K-split over channel chunks
 struct Block3dPlan {
-    float *t1, *t2, *t3, *off;
+    float *t1, *t2, *t3, *off, *split;
     float *wp_proj1, *wp_off, *wp_dcn, *wp_conv1, *wp_proj2, *wp_dw5, *wp_dw7;
     int np_c, np_off;
 };
@@ -222,6 +223,8 @@ bool plan_block3d(Arena &ar, int B, int C, int D1, int D2, int D3, Block3dPlan &
         const size_t brick = deform3d_ps_offset_floats(B, D1, D2, D3, 81);
         p.off = ar.take<float>(M * OFF3D_LD > brick ? M * OFF3D_LD : brick);
     }
+    // K-split partial sums of the deformable conv on small volumes (<= SPLIT3D_ROWS rows, one slice per 32-channel chunk)
+    p.split = (M <= SPLIT3D_ROWS && C % 32 == 0 && C / 32 >= 2) ? ar.take<float>(M * C * (size_t)(C / 32)) : nullptr;
     p.wp_proj1 = wa.take<float>(contraction_scratch_floats(C, C, 1, 1));
     p.wp_conv1 = wa.take<float>(contraction_scratch_floats(C, C, 1, 1));
     p.wp_proj2 = wa.take<float>(contraction_scratch_floats(C, C, 1, 1));
@@ -316,7 +319,16 @@ int run_lka3d_core(const dlkaBlock3dParams &P, const float *u, Block3dPlan &p, i
         }
         return fuse_proj2 ? 1 : DLKA_OK;  // 1: the whole tail (proj_2 + shortcut) is already in y_final
     }
-    DLKA_TRY(contraction(ad, P.deform_weight, math, p.wp_dcn, st));
+    if (math == DLKA_MATH_BF16X3 && p.split && deform3d_tc_supported(ad)) {
+        // small volume, C > 96 (the deep stages of the 3D net: 128 x 8^3, 256 x 4^3): a handful of 128-row tiles with a K loop of
+        // 27 * C/32 steps each -- one slice per channel chunk fills 4 .. 16x more SMs; the slices are summed by reduce_partials
+        IgemmArgs as = ad;
+        as.Y = p.split; as.ksplit_steps = 1; as.ysplit_stride = M * C;
+        DLKA_TRY(deform3d_tc(as, P.deform_weight, p.wp_dcn, nullptr, st));
+        DLKA_TRY(reduce_partials(p.split, p.t2, M * C, C / 32, st));
+    } else {
+        DLKA_TRY(contraction(ad, P.deform_weight, math, p.wp_dcn, st));
+    }
     // conv1 (1x1x1) then gate with u
     IgemmArgs a1 = dense_args(p.t2, C, M, C, C, nullptr, 0, P.conv1_bias, EPI_MUL, u, C, p.t3, C);
     DLKA_TRY(contraction(a1, P.conv1_weight, math, p.wp_conv1, st));

@@ -198,6 +198,14 @@ int grid_for(i64 total, int threads) { return (int)(cdiv(total, threads) < 148 *
 
 }  // namespace
 
+// out = sum_z partial[z] (n elements per slice): reduction of K-split partial products
+int reduce_partials(const float *partial, float *out, i64 n, int nsplit, cudaStream_t st)
+{
+    if (n <= 0) return DLKA_OK;
+    DLKA_LAUNCH("reduce_partials", st, bwd_reduce_partials_kernel<<<grid_for(n, 256), 256, 0, st>>>(partial, out, n, nsplit, 0));
+    return DLKA_OK;
+}
+
 int deform3d_bwd_chunk_rows(i64 M) { return (int)(M < 8192 ? cdiv(M, 64) * 64 : 8192); }
 
 // all pointers channels-last; gin / gwt zero-initialised by the caller; workspace pieces supplied by the caller (api.cu)

@@ -104,6 +104,8 @@ struct DeformTcArgs {
     const float *b2;
     const float *R;
     int ldR;
+    int chunk_split;      // > 0: grid.z slices of `chunk_split` channel chunks each; slice z writes its partial sum to Y + z * ysplit
+    i64 ysplit;           // (bias only in slice 0); the host reduces the slices
     long long *trace;     // optional debug timeline (clock64 stamps of CTA `trace_cta`), see tools/df_trace.py
     int trace_cta;
 };
@@ -222,7 +224,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     const int th = bid % a.tiles_h; bid /= a.tiles_h;
     const int td = bid % a.tiles_d;
     const int b = bid / a.tiles_d;
-    const int nchunks = g.C / DF_KC, K = g.K, KS = nchunks * K;
+    const int nchunks = a.chunk_split > 0 ? a.chunk_split : g.C / DF_KC, K = g.K, KS = nchunks * K;
+    const int chunk0 = a.chunk_split > 0 ? (int)blockIdx.z * a.chunk_split : 0;   // first channel chunk of this K slice
     const int tc_need = a.chain ? 2 * NT : NT;
     const uint32_t tmem_cols = tc_need <= 32 ? 32u : tc_need <= 64 ? 64u : tc_need <= 128 ? 128u : 256u;
     const int CP = g.C / 8;                               // chain: 16-byte K chunks per row
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
         for (int i = tid - 256; i < 3 * 128; i += DF_GATHER_WARPS * 32) {
             const int st = i >> 7, n = n_tile * NT + (i & 127);
             const float *src = st == 0 ? a.bias : st == 1 ? a.b1 : a.b2;
-            sBias[i] = (src && (i & 127) < NT && n < g.Co && (st == 0 || st <= a.chain)) ? __ldg(src + n) : 0.f;
+            sBias[i] = (src && (i & 127) < NT && n < g.Co && (st == 0 || st <= a.chain) && chunk0 == 0) ? __ldg(src + n) : 0.f;
         }
     }
     if (warp >= 4 && warp < 8) {  // brick row decode
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                 }
                 if (last) {
                     if (live) {
-                        float *yp = a.Y + (i64)ro.m * a.ldY + nb;
+                        float *yp = a.Y + (i64)blockIdx.z * a.ysplit + (i64)ro.m * a.ldY + nb;
                         if (vec_y && nb + 7 < g.Co) {
                             *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);
                             *reinterpret_cast<float4 *>(yp + 4) = make_float4(o[4], o[5], o[6], o[7]);
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     } else if (warp == 1) {
         // ===================== weight loader =====================
         if (elect_one()) {
-            const uint8_t *src = a.Bp + (i64)n_tile * KS * B_SLOT;
+            const uint8_t *src = a.Bp + ((i64)n_tile * (g.C / DF_KC) + chunk0) * K * B_SLOT;
             for (int ks = 0; ks < KS; ++ks) {
                 const int bs = ks % DF_SB;
                 mbar_wait(emptyB(bs), ((ks / DF_SB) & 1) ^ 1);
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             const int cg = gt & 7;
             const float *Xb = a.X + (i64)b * a.vol_c + cg * 4;
             for (int ks = grp; ks < KS; ks += DF_GROUPS) {
-                const int chunk = ks / K;
+                const int chunk = chunk0 + ks / K;
                 const int as = ks % DF_SA, ps = ks % DF_SP;
                 const uint32_t phA = ((ks / DF_SA) & 1) ^ 1, phP = (ks / DF_SP) & 1;   // emptyA starts "free", fullP "not ready"
                 mbar_wait(fullP(ps), phP);
@@ -696,6 +699,7 @@ int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, const DeformChain
     a.tiles_d = (int)cdiv(g.Do, DF_BD); a.tiles_h = (int)cdiv(g.Ho, DF_BH); a.tiles_w = (int)cdiv(g.Wo, DF_BW);
     a.vol_c = (i64)g.D * g.H * g.W * g.C;
     a.trace = g_df_trace; a.trace_cta = g_df_trace_cta;
+    a.chunk_split = 0; a.ysplit = 0;
     a.chain = 0; a.W1p = a.W2p = nullptr; a.b1 = a.b2 = a.U = a.R = nullptr; a.ldU = a.ldR = 0;
     if (chain && chain->stages) {
         a.chain = chain->stages;
@@ -715,6 +719,11 @@ int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, const DeformChain
     static SmemOptIn optin;   // per launch site (= per kernel instantiation), per device
     DLKA_TRY(optin.ensure(deform3d_tc_kernel, smem));
     dim3 grid((unsigned)((i64)g.B * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)n_tiles);
+    if (ga.ksplit_steps > 0 && !a.chain && !DF_REGION) {   // K split over channel chunks (small volumes: a few tiles, a long K loop)
+        a.chunk_split = ga.ksplit_steps;
+        a.ysplit = ga.ysplit_stride;
+        grid.z = (unsigned)((g.C / DF_KC) / a.chunk_split);
+    }
     CUtensorMap tmapX;
     memset(&tmapX, 0, sizeof(tmapX));
     if (DF_REGION && !make_tmap_cl5(&tmapX, a.X, g.B, g.C, g.D, g.H, g.W, DF_KC, DF_RW, DF_RH, DF_RD, 1)) return DLKA_ERR_CUDA;

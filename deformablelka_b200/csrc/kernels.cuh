@@ -126,6 +126,7 @@ int dense_cl(const float *x, int ldX, i64 M, int Ci, int Co, const float *w, con
 size_t dense_scratch_floats(int Co, int Ci);
 
 // ---------------- backward of the 3D deformable conv (deform_bwd.cu), channels-last, groups = dg = 1 ----------------
+int reduce_partials(const float *partial, float *out, i64 n, int nsplit, cudaStream_t st);   // out = sum_z partial[z]
 int deform3d_bwd_chunk_rows(i64 M);   // rows per streamed chunk (multiple of 64)
 int deform3d_backward_cl(const ConvGeo &g, const float *x, const float *off, const float *w, const float *gout, float *gin, float *goff,
                          float *gw, float *gb, float *wt, float *gwt, float *colbuf, float *colT, float *gchunk, float *gchunkT,

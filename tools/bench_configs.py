@@ -29,6 +29,20 @@ def timeit(fn, iters=20, warm=3):
     return a.elapsed_time(b) / iters
 
 
+def breakdown(fn, iters=10):
+    """per-kernel device time (us per call) from the library's event profiler"""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    dl._lib.profile_enable(True)
+    for _ in range(iters):
+        fn()
+    torch.cuda.synchronize()
+    prof = dl._lib.profile_summary()
+    dl._lib.profile_enable(False)
+    return {k: round(v[1] / iters * 1e3, 1) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+
+
 def main():
     math = os.environ.get("DLKA_MATH", "bf16x3")
     os.environ["DLKA_MATH"] = math
@@ -41,7 +55,7 @@ def main():
             x = torch.randn(B, C, hw, hw, device=dev)
             ms = timeit(lambda: m(x))
             out.append({"config": "C2" if hw != 224 else "C1-shape", "op": "deformable_LKA_Attention", "shape": [B, C, hw, hw], "ms": ms,
-                        "Mpx_per_s": B * hw * hw / ms / 1e3, "math": math})
+                        "Mpx_per_s": B * hw * hw / ms / 1e3, "math": math, "kernels_us": breakdown(lambda: m(x))})
         B, C, D, H, W = 2, 64, 32, 64, 64
         x = torch.randn(B, C, D, H, W, device=dev); w = torch.randn(C, C, 3, 3, 3, device=dev) * 0.05
         b = torch.randn(C, device=dev); off = torch.randn(B, 81, D, H, W, device=dev)
@@ -56,7 +70,7 @@ def main():
             x = torch.randn(2, s * s * s, C, device=dev)
             ms = timeit(lambda: m(x, 2, C, s, s, s))
             out.append({"config": "C4", "op": "LKA_Attention3d_deform", "shape": [2, C, s, s, s], "ms": ms,
-                        "GVoxel_per_s": 2 * s ** 3 / ms / 1e6, "math": math})
+                        "GVoxel_per_s": 2 * s ** 3 / ms / 1e6, "math": math, "kernels_us": breakdown(lambda: m(x, 2, C, s, s, s))})
     for o in out:
         print(json.dumps(o))
 
