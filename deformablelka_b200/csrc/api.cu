@@ -203,9 +203,11 @@ int run_deform_op(const ConvGeo &g, const float *input, const float *weight, con
 
 // ---- 3D block ---------------------------------------------------------------------------
 constexpr int OFF3D_LD = 84;  // row stride of the [M][81] offset buffer (16-byte aligned rows)
+constexpr size_t SPLIT_SCRATCH_CAP = (size_t)4 << 20;   // floats: upper bound of a K-split scratch buffer
 constexpr size_t SPLIT3D_ROWS = 2048;   // volumes up to this many voxels run the C > 96 deformable conv K-split over channel chunks
 struct Block3dPlan {
-    float *t1, *t2, *t3, *off, *split;
+    float *t1, *t2, *t3, *off, *split, *off_split;
+    i64 off_split_floats;
     float *wp_proj1, *wp_off, *wp_dcn, *wp_conv1, *wp_proj2, *wp_dw5, *wp_dw7;
     int np_c, np_off;
 };
@@ -221,7 +223,11 @@ bool plan_block3d(Arena &ar, int B, int C, int D1, int D2, int D3, Block3dPlan &
     p.t3 = ar.take<float>(M * C);
     {   // offsets: [M][84] rows (round-1 kernels) or brick-major bricks x 81 x 128 (deform_ps.cu); ragged volumes pad the bricks
         const size_t brick = deform3d_ps_offset_floats(B, D1, D2, D3, 81);
-        p.off = ar.take<float>(M * OFF3D_LD > brick ? M * OFF3D_LD : brick);
+        const size_t offsz = M * OFF3D_LD > brick ? M * OFF3D_LD : brick;
+        p.off = ar.take<float>(offsz);
+        // K-split scratch of the offset conv on small volumes (conv_tiled_ex decides whether it splits)
+        p.off_split_floats = M <= 16384 ? (i64)(16 * offsz < SPLIT_SCRATCH_CAP ? 16 * offsz : SPLIT_SCRATCH_CAP) : 0;
+        p.off_split = p.off_split_floats ? ar.take<float>((size_t)p.off_split_floats) : nullptr;
     }
     // K-split partial sums of the deformable conv on small volumes (<= SPLIT3D_ROWS rows, one slice per 32-channel chunk)
     p.split = (M <= SPLIT3D_ROWS && C % 32 == 0 && C / 32 >= 2) ? ar.take<float>(M * C * (size_t)(C / 32)) : nullptr;
@@ -265,6 +271,7 @@ int run_lka3d_core(const dlkaBlock3dParams &P, const float *u, Block3dPlan &p, i
     ad.ldOff = OFF3D_LD;
     IgemmArgs ao = conv_args(IGEMM_CONV, go, p.t3, nullptr, nullptr, nullptr, 0, P.conv_offset_bias, EPI_NONE, nullptr, 0, p.off,
                              OFF3D_LD);
+    ao.split_scratch = p.off_split; ao.split_scratch_floats = p.off_split_floats;
     // persistent deformable kernel (deform_ps.cu): the large-kernel stencil writes its output CHUNK-MAJOR
     // ([C/32][B][D][H][W][32]), which the offset conv and the deformable gather then read -- no extra pass over the tensor
     const i64 xch = (i64)B * D1 * D2 * D3 * 32;
@@ -272,9 +279,7 @@ int run_lka3d_core(const dlkaBlock3dParams &P, const float *u, Block3dPlan &p, i
     ao_cm.xch = xch;
     ao_cm.ybrick = 1;
     const bool use_ps = math == DLKA_MATH_BF16X3 && deform_ps_enabled() && deform3d_ps_supported(ad, fuse_proj2 ? 2 : 1) &&
-                        dwconv_smem_supported(C, G.conv_spatial_k[0], G.conv_spatial_k[1], G.conv_spatial_k[2], G.conv_spatial_dil[0],
-                                              G.conv_spatial_dil[1], G.conv_spatial_dil[2]) &&
-                        conv_tiled_supported(ao_cm);
+                        conv_tiled_supported(ao_cm);   // (both stencil kernels can write chunk-major when C % 32 == 0)
     DLKA_TRY(dwconv_cl(p.t2, P.conv_spatial_weight, P.conv_spatial_bias, p.t3, B, C, D1, D2, D3, G.conv_spatial_k[0],
                        G.conv_spatial_k[1], G.conv_spatial_k[2], G.conv_spatial_dil[0], G.conv_spatial_dil[1], p.wp_dw7, st, use_ps));
     if (use_ps) {
@@ -347,7 +352,8 @@ bool null_params3d(const dlkaBlock3dParams *P, bool attention)
 
 // ---- 2D block ---------------------------------------------------------------------------
 struct Block2dPlan {
-    float *x_cl, *t1, *t2, *t3, *off;
+    float *x_cl, *t1, *t2, *t3, *off, *off_split;
+    i64 off_split_floats;
     float *wp_proj1, *wp_off0, *wp_off1, *wp_conv1, *wp_proj2, *wp_dw0, *wp_dw1;
     int np_c, np_off0, np_off1;
 };
@@ -362,6 +368,8 @@ bool plan_block2d(Arena &ar, int B, int C, int H, int W, Block2dPlan &p, Arena *
     p.t2 = ar.take<float>(M * C);
     p.t3 = ar.take<float>(M * C);
     p.off = ar.take<float>(M * 98);
+    p.off_split_floats = M <= 32768 ? (i64)(8 * M * 98 < SPLIT_SCRATCH_CAP ? 8 * M * 98 : SPLIT_SCRATCH_CAP) : 0;
+    p.off_split = p.off_split_floats ? ar.take<float>((size_t)p.off_split_floats) : nullptr;
     p.wp_proj1 = wa.take<float>(contraction_scratch_floats(C, C, 1, 1));
     p.wp_conv1 = wa.take<float>(contraction_scratch_floats(C, C, 1, 1));
     p.wp_proj2 = wa.take<float>(contraction_scratch_floats(C, C, 1, 1));
@@ -380,6 +388,7 @@ int run_lka2d_core(const dlkaBlock2dParams &P, const float *u, Block2dPlan &p, i
     // conv0: offset_net Conv2d(C->50, k5, pad 2) + depthwise deformable k5 (deformable_LKA.py:93)
     ConvGeo g0 = make_geo(B, C, 1, H, W, 50, 1, 5, 5, 1, 1, 1, 0, 2, 2, 1, 1, 1, 1, 1, 2);
     IgemmArgs a0 = conv_args(IGEMM_CONV, g0, u, nullptr, nullptr, nullptr, 0, P.conv0_offset_bias, EPI_NONE, nullptr, 0, p.off, 50);
+    a0.split_scratch = p.off_split; a0.split_scratch_floats = p.off_split_floats;
     DLKA_TRY(contraction(a0, P.conv0_offset_weight, math, p.wp_off0, st));
     ConvGeo d0 = make_geo(B, C, 1, H, W, C, 1, 5, 5, 1, 1, 1, 0, 2, 2, 1, 1, 1, C, 1, 2);
     DLKA_TRY(deform_dwconv_cl(u, p.off, nullptr, P.conv0_deform_weight, nullptr, p.t2, d0, p.wp_dw0, st));
@@ -387,6 +396,7 @@ int run_lka2d_core(const dlkaBlock2dParams &P, const float *u, Block2dPlan &p, i
     ConvGeo g1 = make_geo(B, C, 1, H, W, 98, 1, 7, 7, 1, 1, 1, 0, 9, 9, 1, 3, 3, 1, 1, 2);
     IgemmArgs a1 = conv_args(IGEMM_CONV, g1, p.t2, nullptr, nullptr, nullptr, 0, P.conv_spatial_offset_bias, EPI_NONE, nullptr, 0,
                              p.off, 98);
+    a1.split_scratch = p.off_split; a1.split_scratch_floats = p.off_split_floats;
     DLKA_TRY(contraction(a1, P.conv_spatial_offset_weight, math, p.wp_off1, st));
     ConvGeo d1 = make_geo(B, C, 1, H, W, C, 1, 7, 7, 1, 1, 1, 0, 9, 9, 1, 3, 3, C, 1, 2);
     DLKA_TRY(deform_dwconv_cl(p.t2, p.off, nullptr, P.conv_spatial_deform_weight, nullptr, p.t3, d1, p.wp_dw1, st));

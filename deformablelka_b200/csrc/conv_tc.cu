@@ -57,6 +57,8 @@ struct ConvTileArgs {
     int RD, RH, RW;      // region extent (voxels)
     int tiles_d, tiles_h, tiles_w;  // CTA grid decomposition
     int lbo;             // plane stride in bytes = RV*16 + pad
+    int csplit;          // > 0: grid.z slices of `csplit` K chunks; slice z writes to Y + z * ysplit (bias in slice 0 only)
+    i64 ysplit;
 };
 
 template <int MT>
@@ -91,7 +93,8 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
     const int b = bid / a.tiles_d;
     const bool is3d = g.ndim == 3;
     const int d0 = is3d ? td * MT : 0, h0 = is3d ? th * 16 : th * 16 * MT, w0 = tw * 8;
-    const int nchunks = g.C / CT_KCH, K = g.K;
+    const int nchunks_all = g.C / CT_KCH, K = g.K;
+    const int nchunks = a.csplit > 0 ? a.csplit : nchunks_all, chunk0 = a.csplit > 0 ? (int)blockIdx.z * a.csplit : 0;
     const uint32_t tmem_cols = (MT * NT <= 32) ? 32u : (MT * NT <= 64) ? 64u : (MT * NT <= 128) ? 128u : (MT * NT <= 256) ? 256u : 512u;
 
     if (tid == 0) {
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
         // ===================== weight loader =====================
         if (elect_one()) {
             const int total = nchunks * K;
-            const uint8_t *src = a.Bp + (i64)n_tile * total * B_SLOT;
+            const uint8_t *src = a.Bp + ((i64)n_tile * nchunks_all + chunk0) * K * B_SLOT;
             for (int bi = 0; bi < total; ++bi) {
                 const int bs = bi % CT_SB;
                 mbar_wait(emptyB(bs), ((bi / CT_SB) & 1) ^ 1);
@@ -170,7 +173,8 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
             const int rb = c & 1;
             mbar_wait(emptyR(rb), ((c >> 1) & 1) ^ 1);
             uint8_t *buf = sR + rb * R_BUF;
-            const float *Xc = a.xch ? Xb + (i64)(c >> 1) * a.xch + (c & 1) * CT_KCH : Xb + c * CT_KCH;
+            const int cg = chunk0 + c;   // global K chunk
+            const float *Xc = a.xch ? Xb + (i64)(cg >> 1) * a.xch + (cg & 1) * CT_KCH : Xb + cg * CT_KCH;
             for (int u0 = ptid; u0 < units; u0 += 4 * NPT) {
                 float4 v[4];
                 int vox[4];
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int ne = n + e < g.Co ? n + e : g.Co - 1;
-                        o[e] = v[j4 * 4 + e] + (a.bias ? __ldg(a.bias + ne) : 0.f);
+                        o[e] = v[j4 * 4 + e] + ((a.bias && chunk0 == 0) ? __ldg(a.bias + ne) : 0.f);
                     }
                     if (a.act) {
                         if (a.act == 2) {
@@ -242,13 +246,14 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
 #pragma unroll
                         for (int e = 0; e < 4; ++e) o[e] = o[e] > 0.f ? o[e] : a.slope * o[e];
                     }
+                    float *Ys = a.Y + (i64)blockIdx.z * a.ysplit;
                     if (a.ybrick) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            if (n + e < g.Co) a.Y[ybase + (i64)(n + e) * 128] = o[e];
+                            if (n + e < g.Co) Ys[ybase + (i64)(n + e) * 128] = o[e];
                         continue;
                     }
-                    float *yp = a.Y + m * (i64)a.ldY + n;
+                    float *yp = Ys + m * (i64)a.ldY + n;
                     if (vec_y && n + 3 < a.ldY) {
                         *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);  // pad columns hold junk-free bias values
                     } else {
@@ -309,7 +314,7 @@ bool ct_plan(const IgemmArgs &g, ConvTileArgs &a)
     if (g.ybrick && geo.ndim != 3) return false;
     a.ybrick = g.ybrick; a.bt_d = (int)cdiv(geo.Do, 4); a.bt_h = (int)cdiv(geo.Ho, 4); a.bt_w = (int)cdiv(geo.Wo, 8);
     a.g = geo; a.X = g.X; a.xch = g.xch; a.bias = g.bias; a.Y = g.Y; a.ldY = g.ldY;
-    a.act = 0; a.slope = 0.f; a.E = nullptr; a.ldE = 0;
+    a.act = 0; a.slope = 0.f; a.E = nullptr; a.ldE = 0; a.csplit = 0; a.ysplit = 0;
     a.NT = tc_nt(geo.Co);
     const bool is3d = geo.ndim == 3;
     for (int mt = DLKA_CT_MTMAX; mt >= 1; mt >>= 1) {
@@ -334,7 +339,7 @@ bool ct_plan(const IgemmArgs &g, ConvTileArgs &a)
 }
 
 template <int MT>
-int launch_ct(const ConvTileArgs &a, int n_tiles, cudaStream_t st)
+int launch_ct(const ConvTileArgs &a, int n_tiles, cudaStream_t st, int zsplit = 1)
 {
     const size_t smem = ct_smem_bytes(a);
     auto kern = conv_tiled_kernel<MT>;
@@ -342,7 +347,7 @@ int launch_ct(const ConvTileArgs &a, int n_tiles, cudaStream_t st)
     // host thread -- e.g. the autograd engine's -- lower the limit under a launch that needs more)
     static SmemOptIn optin;   // per launch site (= per kernel instantiation), per device
     DLKA_TRY(optin.ensure(kern, smem));
-    dim3 grid((unsigned)((i64)a.g.B * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)n_tiles);
+    dim3 grid((unsigned)((i64)a.g.B * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)n_tiles, (unsigned)zsplit);
     DLKA_LAUNCH("tc_conv_tiled", st, (kern<<<grid, (CT_CTRL_WARPS + CT_NPW) * 32, smem, st>>>(a)));
     return DLKA_OK;
 }
@@ -382,11 +387,26 @@ int conv_tiled_ex(const IgemmArgs &g, const float *w, const float *wscale, int a
                     pack_weight_ct_kernel<<<blocks, 256, 0, st>>>(w, wscale, (__nv_bfloat16 *)bp, geo.Co, geo.C, geo.K, a.NT, n_tiles));
     }
     a.Bp = (const uint8_t *)bp;
-    switch (a.MT) {
-    case 4: return launch_ct<4>(a, n_tiles, st);
-    case 2: return launch_ct<2>(a, n_tiles, st);
-    default: return launch_ct<1>(a, n_tiles, st);
+    // K split over channel chunks when the grid would leave most SMs idle behind a long K loop (the offset nets of the deep network
+    // stages: 24 x 14 x 14 pixels, 4^3 volumes): S slices write partial outputs, reduce_partials sums them into Y
+    int S = 1;
+    const i64 blocks = (i64)geo.B * a.tiles_d * a.tiles_h * a.tiles_w * n_tiles;
+    const int nch = geo.C / CT_KCH;
+    const i64 ybuf = a.ybrick ? (i64)geo.B * a.bt_d * a.bt_h * a.bt_w * geo.Co * 128 : g.M * (i64)a.ldY;
+    if (act == 0 && g.split_scratch && blocks < 100 && nch >= 4) {
+        for (int s = 2; s <= nch; ++s)
+            if (nch % s == 0 && blocks * s <= 296 && (i64)s * ybuf <= g.split_scratch_floats) S = s;
     }
+    float *Yfinal = a.Y;
+    if (S > 1) { a.csplit = nch / S; a.ysplit = ybuf; a.Y = g.split_scratch; }
+    int rc;
+    switch (a.MT) {
+    case 4: rc = launch_ct<4>(a, n_tiles, st, S); break;
+    case 2: rc = launch_ct<2>(a, n_tiles, st, S); break;
+    default: rc = launch_ct<1>(a, n_tiles, st, S); break;
+    }
+    if (rc != DLKA_OK || S == 1) return rc;
+    return reduce_partials(g.split_scratch, Yfinal, ybuf, S, st);
 }
 
 }  // namespace dlka

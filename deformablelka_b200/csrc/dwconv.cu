@@ -79,14 +79,18 @@ __global__ void __launch_bounds__(256) dwconv3d_cl_kernel(const float *__restric
 // stencil shapes / channel counts the shared-memory kernel has no instance for.
 __global__ void __launch_bounds__(256) dwconv3d_generic_kernel(const float *__restrict__ x, const float *__restrict__ wp,
                                                                const float *__restrict__ bias, float *__restrict__ y, int B, int C,
-                                                               int D, int H, int W, int kd, int kh, int kw, int dd, int dh, int dw)
+                                                               int D, int H, int W, int kd, int kh, int kw, int dd, int dh, int dw, i64 ych,
+                                                               int yldv)
 {
+    // output element (voxel, channel c) at y + (c / 32) * ych + voxel * yldv + c % 32: channels-last (ych = 32, yldv = C) or the
+    // chunk-major gather layout of deform_ps.cu (ych = voxels * 32, yldv = 32)
     const int C4 = C / 4;
     const i64 total = (i64)B * D * H * W * C4;
     const int pd = dd * (kd - 1) / 2, ph = dh * (kh - 1) / 2, pw = dw * (kw - 1) / 2;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4) * 4;
         i64 v = i / C4;
+        const i64 voxel = v;
         const int w = (int)(v % W); v /= W;
         const int h = (int)(v % H); v /= H;
         const int d = (int)(v % D);
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(256) dwconv3d_generic_kernel(const float *__re
                 }
             }
         }
-        *reinterpret_cast<float4 *>(y + i * 4) = acc;
+        *reinterpret_cast<float4 *>(y + (i64)(c >> 5) * ych + voxel * yldv + (c & 31)) = acc;
     }
 }
 
@@ -188,19 +192,26 @@ int dwconv_cl(const float *x, const float *w, const float *bias, float *y, int B
               int kh, int kw, int dd, int dil, float *w_packed, cudaStream_t st, bool chunk_major_out)
 {
     if (C % 4 != 0) return DLKA_ERR_UNSUPPORTED;
-    if (chunk_major_out && !dwconv_smem_supported(C, kd, kh, kw, dd, dil, dil)) return DLKA_ERR_UNSUPPORTED;
+    if (chunk_major_out && C % 32 != 0) return DLKA_ERR_UNSUPPORTED;
     if (kd < 1 || kh < 1 || kw < 1 || !(kd & 1) || !(kh & 1) || !(kw & 1) || dd < 1 || dil < 1) return DLKA_ERR_UNSUPPORTED;
     DLKA_TRY(pack_dw(w, w_packed, C, kd * kh * kw, st));
-    if (dwconv_smem_supported(C, kd, kh, kw, dd, dil, dil)) return dwconv_smem(x, w_packed, bias, y, B, C, D, H, W, kd, kh, dd, dil, st, chunk_major_out);
-    if (C / 4 <= 256 && kh == kw && dd == dil && (kd == kh || kd == 1)) {
+    const i64 voxels = (i64)B * D * H * W;
+    // small volumes (the deep stages of the 3D nets, 4^3 .. 32^3): the plane-streaming kernel's cost is set by its tile shape, not by
+    // the volume (measured ~140 us for 7^3-dil-3 and ~34 us for 5^3 on ANY volume below one wave of tiles), while the
+    // thread-per-voxel kernel scales with the voxel count
+    const bool small = voxels * C <= ((i64)1 << 20);
+    if (!small && dwconv_smem_supported(C, kd, kh, kw, dd, dil, dil)) return dwconv_smem(x, w_packed, bias, y, B, C, D, H, W, kd, kh, dd, dil, st, chunk_major_out);
+    if (!small && !chunk_major_out && C / 4 <= 256 && kh == kw && dd == dil && (kd == kh || kd == 1)) {
         if (kh == 5 && dil == 1) return launch_dw<5, 1, 4>(x, w_packed, bias, y, B, C, D, H, W, kd, st);
         if (kh == 7 && dil == 3) return launch_dw<7, 3, 4>(x, w_packed, bias, y, B, C, D, H, W, kd, st);
     }
-    const i64 total = (i64)B * D * H * W * (C / 4);
+    const i64 total = voxels * (C / 4);
     if (total <= 0) return DLKA_OK;
     const int blocks = (int)(cdiv(total, 256) < 148 * 32 ? cdiv(total, 256) : 148 * 32);
+    const i64 ych = chunk_major_out ? voxels * 32 : 32;
     DLKA_LAUNCH("dwconv3d_generic", st,
-                dwconv3d_generic_kernel<<<blocks, 256, 0, st>>>(x, w_packed, bias, y, B, C, D, H, W, kd, kh, kw, dd, dil, dil));
+                dwconv3d_generic_kernel<<<blocks, 256, 0, st>>>(x, w_packed, bias, y, B, C, D, H, W, kd, kh, kw, dd, dil, dil, ych,
+                                                                 chunk_major_out ? 32 : C));
     return DLKA_OK;
 }
 

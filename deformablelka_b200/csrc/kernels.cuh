@@ -33,6 +33,10 @@ struct IgemmArgs {
     // Y + z * ysplit_stride (bias / epilogue operand applied by slice 0 only); 0 = no split
     int ksplit_steps;
     i64 ysplit_stride;
+    // conv_tiled: optional scratch for K-split partial outputs (small problems: few CTAs, long K loop); the split and the
+    // reduction happen inside conv_tiled_ex when the scratch is large enough
+    float *split_scratch;
+    i64 split_scratch_floats;
 };
 
 int igemm_simt_npad(int n_per_group);
