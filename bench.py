@@ -139,6 +139,31 @@ def other_configs(dl, dev):
     return out
 
 
+def gpu_reference_leg(dl, dev):
+    """Informational: the reference's OWN CUDA extension (3D/dcn D3D, compiled unmodified apart from the two-token torch-2 patch
+    by oracle/build_ref.py into oracle/_ref/) against this library's operator, same GPU, same tensors, BASELINE configs[2]
+    (2,64,32,64,64), k=3: forward and backward, ms per call.  None when oracle/_ref was not built."""
+    try:
+        from oracle import build_ref
+        d3d = build_ref.load_d3d()
+    except Exception as e:   # noqa: BLE001 -- informational leg, never fails the bench
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    if d3d is None:
+        return {"unavailable": "oracle/_ref/D3D*.so not built"}
+    torch.manual_seed(1234)
+    B, C, D, H, W = 2, 64, 32, 64, 64
+    x = torch.randn(B, C, D, H, W, device=dev); w = torch.randn(C, C, 3, 3, 3, device=dev) * 0.05
+    b = torch.randn(C, device=dev); off = torch.randn(B, 81, D, H, W, device=dev); go = torch.randn(B, C, D, H, W, device=dev)
+    geo = (3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 64)
+    out = {"shape": [B, C, D, H, W], "what": "deform_conv3d k=3 s=1 p=1 g=1 dg=1 im2col_step=64"}
+    with torch.no_grad():
+        out["reference_d3d_forward_ms"] = _time_call(lambda: d3d.deform_conv_forward(x, w, b, off, *geo))
+        out["ours_forward_ms"] = _time_call(lambda: dl.ops.deform_conv3d_forward(x, w, b, off, 3, 1, 1, 1, 1, 1, 64))
+        out["reference_d3d_backward_ms"] = _time_call(lambda: d3d.deform_conv_backward(x, w, b, off, go, *geo))
+        out["ours_backward_ms"] = _time_call(lambda: dl.ops.deform_conv3d_backward(x, w, b, off, go, 3, 1, 1, 1, 1, 1, 64))
+    return out
+
+
 def run_c4net(args, dl, dev, world, rank):
     """--config c4net: one step = the 21 D-LKA attention blocks of the 3D D-LKA Net forward at per-rank batch 2
     (BASELINE configs[3]; under torchrun with 8 ranks = configs[4], global batch 16, batch-sharded, no collective)."""
@@ -376,6 +401,7 @@ def main():
         del x, y
         torch.cuda.empty_cache()
         others = other_configs(dl, dev)
+        others["gpu_reference"] = gpu_reference_leg(dl, dev)
 
     pk = peaks()
     # DRAM traffic per launch: measured by tools/measure_traffic.py (ncu) and used only if it was measured on THESE sources

@@ -505,13 +505,6 @@ const char *dlka_status_string(int status)
 const char *dlka_last_cuda_error(void) { return g_last_cuda_error; }
 uint64_t dlka_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-/* debug: clock64 timeline of one CTA of the deformable-conv kernel; buf = [6][1024][2] int64 on the device, or NULL */
-DLKA_API int dlka_debug_deform_trace(void *buf, int cta)
-{
-    deform3d_set_trace((long long *)buf, cta);
-    return DLKA_OK;
-}
-
 int dlka_profile_enable(int on)
 {
     g_profiling.store(on ? 1 : 0);
@@ -585,8 +578,8 @@ bool plan_deform_bwd(Arena &ar, const ConvGeo &g, DeformBwdPlan &p)
     p.Mc = deform3d_bwd_chunk_rows((i64)M);
     p.x_cl = ar.take<float>(g.B * Vi * g.C);
     p.gin_cl = ar.take<float>(g.B * Vi * g.C);
-    p.off_cl = ar.take<float>(M * 3 * g.K);
-    p.goff_cl = ar.take<float>(M * 3 * g.K);
+    p.off_cl = ar.take<float>(M * 3 * g.K * g.dg);
+    p.goff_cl = ar.take<float>(M * 3 * g.K * g.dg);
     p.gout_cl = ar.take<float>(M * g.Co);
     p.wt = ar.take<float>(KC * g.Co);
     p.gwt = ar.take<float>(KC * g.Co);
@@ -628,7 +621,8 @@ int dlka_deform_conv3d_backward(const float *input, const float *weight, const f
     if (bad_geo(g)) return DLKA_ERR_INVALID_ARGUMENT;
     const int step = B < im2col_step ? B : im2col_step;  // deform_conv_cuda.cu:176-178
     if (B % step != 0) return DLKA_ERR_INVALID_ARGUMENT;
-    if (group != 1 || deformable_group != 1 || C % 4 != 0) return DLKA_ERR_UNSUPPORTED;   // what the D-LKA block uses
+    if (C % group != 0 || Co % group != 0 || C % deformable_group != 0) return DLKA_ERR_INVALID_ARGUMENT;   // deform_conv_cuda.cu:160-166
+    if ((C / deformable_group) % 4 != 0) return DLKA_ERR_UNSUPPORTED;   // float4 channel vectors per deformable group
     DLKA_TRY(check_device());
     cudaStream_t st = (cudaStream_t)stream;
     Arena ar(workspace, workspace_bytes);
@@ -636,13 +630,13 @@ int dlka_deform_conv3d_backward(const float *input, const float *weight, const f
     if (!plan_deform_bwd(ar, g, p)) return DLKA_ERR_WORKSPACE;
     const i64 Vi = (i64)g.D * g.H * g.W, Vo = (i64)g.Do * g.Ho * g.Wo;
     DLKA_TRY(transpose_cs_to_sc(input, p.x_cl, g.B, g.C, Vi, st));
-    DLKA_TRY(transpose_cs_to_sc(offset, p.off_cl, g.B, 3 * g.K, Vo, st));
+    DLKA_TRY(transpose_cs_to_sc(offset, p.off_cl, g.B, 3 * g.K * g.dg, Vo, st));
     DLKA_TRY(transpose_cs_to_sc(grad_output, p.gout_cl, g.B, g.Co, Vo, st));
     DLKA_CUDA_TRY(cudaMemsetAsync(p.gin_cl, 0, (size_t)g.B * Vi * g.C * sizeof(float), st));
     DLKA_TRY(deform3d_backward_cl(g, p.x_cl, p.off_cl, weight, p.gout_cl, p.gin_cl, p.goff_cl, grad_weight, grad_bias, p.wt, p.gwt,
                                   p.colbuf, p.colT, p.gchunk, p.gchunkT, p.partial, p.wscratch, math, st));
     DLKA_TRY(transpose_sc_to_cs(p.gin_cl, grad_input, g.B, g.C, Vi, st));
-    DLKA_TRY(transpose_sc_to_cs(p.goff_cl, grad_offset, g.B, 3 * g.K, Vo, st));
+    DLKA_TRY(transpose_sc_to_cs(p.goff_cl, grad_offset, g.B, 3 * g.K * g.dg, Vo, st));
     return DLKA_OK;
 }
 

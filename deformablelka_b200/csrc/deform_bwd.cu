@@ -1,4 +1,6 @@
-// deform_bwd.cu -- backward of the 3D deformable convolution, groups = deformable groups = 1.
+// deform_bwd.cu -- backward of the 3D deformable convolution, any group / deformable_group.
+// (Weight groups run through the dense kernels as a block-diagonal [K*C][Co] matrix with explicit zeros: G times the flops of a
+// grouped GEMM, exact results; the D-LKA block itself only uses group = deformable_group = 1.)
 //
 // Replaces D3D.deform_conv_backward (3D/dcn/src/cuda/deform_conv_cuda.cu:128-285: at::mm -> columns, deformable_col2im_coord
 // -> grad_offset, deformable_col2im -> grad_input, deformable_im2col + at::addmm -> grad_weight, at::addmv -> grad_bias) with
@@ -19,27 +21,30 @@
 namespace dlka {
 namespace {
 
-// Wt[(tap*C + c)][co] = W[co][c][tap]      (W: [Co][C][K] as in the reference's state_dict)
-__global__ void bwd_pack_wt_kernel(const float *__restrict__ w, float *__restrict__ wt, int Co, int C, int K)
+// Wt[(tap*C + c)][co] = W[co][c - c0(co)][tap] when c lies in co's weight group, else 0
+// (W: [Co][C/G][K] as in the reference's state_dict; group of co = co / (Co/G), its input channels c0 .. c0 + C/G)
+__global__ void bwd_pack_wt_kernel(const float *__restrict__ w, float *__restrict__ wt, int Co, int C, int K, int G)
 {
     const i64 total = (i64)Co * C * K;
+    const int cpg = C / G, copg = Co / G;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
         const int co = (int)(i % Co);
         const int c = (int)((i / Co) % C);
         const int tap = (int)(i / ((i64)Co * C));
-        wt[i] = w[((i64)co * C + c) * K + tap];
+        wt[i] = (c / cpg == co / copg) ? w[((i64)co * cpg + c % cpg) * K + tap] : 0.f;
     }
 }
 
-// gW[co][c][tap] = gWt[(tap*C + c)][co]
-__global__ void bwd_unpack_gw_kernel(const float *__restrict__ gwt, float *__restrict__ gw, int Co, int C, int K)
+// gW[co][cl][tap] = gWt[(tap*C + c0(co) + cl)][co]   (the out-of-group entries of gWt are not gradients of anything)
+__global__ void bwd_unpack_gw_kernel(const float *__restrict__ gwt, float *__restrict__ gw, int Co, int C, int K, int G)
 {
-    const i64 total = (i64)Co * C * K;
+    const int cpg = C / G, copg = Co / G;
+    const i64 total = (i64)Co * cpg * K;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
         const int tap = (int)(i % K);
-        const int c = (int)((i / K) % C);
-        const int co = (int)(i / ((i64)K * C));
-        gw[i] = gwt[((i64)tap * C + c) * Co + co];
+        const int cl = (int)((i / K) % cpg);
+        const int co = (int)(i / ((i64)K * cpg));
+        gw[i] = gwt[((i64)tap * C + (co / copg) * cpg + cl) * Co + co];
     }
 }
 
@@ -89,8 +94,8 @@ __global__ void __launch_bounds__(256) bwd_scatter_kernel(const float *__restric
                                                           const float *__restrict__ off, float *__restrict__ gin,
                                                           float *__restrict__ goff, ConvGeo g, i64 m0, int Mc, i64 M)
 {
-    const int K = g.K, C = g.C;
-    const i64 total = (i64)Mc * K;                       // Mc: valid rows of this chunk
+    const int K = g.K, C = g.C, dg = g.dg, cpd = C / dg;   // cpd: channels per deformable group (share one sampling position)
+    const i64 total = (i64)Mc * K * dg;                  // Mc: valid rows of this chunk
     const int lg = threadIdx.x % LPG;
     const i64 ngroups = (i64)gridDim.x * (blockDim.x / LPG);
     // the loop condition is warp-uniform (index of the warp's first group), so the full-mask shuffles below are executed by
@@ -99,12 +104,14 @@ __global__ void __launch_bounds__(256) bwd_scatter_kernel(const float *__restric
     for (i64 i = (i64)blockIdx.x * (blockDim.x / LPG) + threadIdx.x / LPG; i - gw_ < total; i += ngroups) {
         const bool act = i < total;
         const i64 ic = act ? i : total - 1;
-        const int tap = (int)(ic % K);
-        const int r = (int)(ic / K);
+        const int dgi = (int)(ic % dg);
+        const int tap = (int)((ic / dg) % K);
+        const int r = (int)(ic / ((i64)dg * K));
         const i64 m = m0 + r;
         const BwdRow ro = decode_row(g, m);
         const int kk = tap % g.kw, jj = (tap / g.kw) % g.kh, ii = tap / (g.kw * g.kh);
-        const float *o = off + m * (3 * (i64)K) + 3 * tap;
+        const i64 oidx = m * (3 * (i64)K * dg) + 3 * ((i64)dgi * K + tap);   // offset channel = ((dgi * K + tap) * 3 + axis)
+        const float *o = off + oidx;
         const float pd = sample_pos(ro.d, g.sd, g.pd, ii, g.dd, __ldg(o));
         const float ph = sample_pos(ro.h, g.sh, g.ph, jj, g.dh, __ldg(o + 1));
         const float pw = sample_pos(ro.w, g.sw, g.pw, kk, g.dw, __ldg(o + 2));
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(256) bwd_scatter_kernel(const float *__restric
             const float ch[8] = {-hd * hw, -hd * lw, hd * hw, hd * lw, -ld * hw, -ld * lw, ld * hw, ld * lw};   // d weight / d p_h
             const float cw[8] = {-hd * hh, hd * hh, -hd * lh, hd * lh, -ld * hh, ld * hh, -ld * lh, ld * lh};   // d weight / d p_w
             const float *gc = gcol + (i64)r * K * C + (i64)tap * C;
-            for (int c = lg * 4; c < C; c += LPG * 4) {
+            for (int c = dgi * cpd + lg * 4; c < (dgi + 1) * cpd; c += LPG * 4) {
                 const float4 gv = *reinterpret_cast<const float4 *>(gc + c);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(256) bwd_scatter_kernel(const float *__restric
             gw += __shfl_xor_sync(0xffffffffu, gw, o2);
         }
         if (act && lg == 0) {
-            float *go = goff + m * (3 * (i64)K) + 3 * tap;
+            float *go = goff + oidx;
             go[0] = gd; go[1] = gh; go[2] = gw;
         }
     }
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(256) bwd_im2col_kernel(const float *__restrict
         if (m < M) {
             const BwdRow ro = decode_row(g, m);
             const int kk = tap % g.kw, jj = (tap / g.kw) % g.kh, ii = tap / (g.kw * g.kh);
-            const float *o = off + m * (3 * (i64)K) + 3 * tap;
+            const float *o = off + m * (3 * (i64)K * g.dg) + 3 * ((i64)(c / (C / g.dg)) * K + tap);
             const float pd = sample_pos(ro.d, g.sd, g.pd, ii, g.dd, o[0]);
             const float ph = sample_pos(ro.h, g.sh, g.ph, jj, g.dh, o[1]);
             const float pw = sample_pos(ro.w, g.sw, g.pw, kk, g.dw, o[2]);
@@ -217,7 +224,7 @@ int deform3d_backward_cl(const ConvGeo &g, const float *x, const float *off, con
     const i64 M = (i64)g.B * g.Do * g.Ho * g.Wo;
     if (M <= 0) return DLKA_OK;
     const int Mc = deform3d_bwd_chunk_rows(M);
-    DLKA_LAUNCH("bwd_pack_wt", st, bwd_pack_wt_kernel<<<grid_for((i64)Co * KC, 256), 256, 0, st>>>(w, wt, Co, C, K));
+    DLKA_LAUNCH("bwd_pack_wt", st, bwd_pack_wt_kernel<<<grid_for((i64)Co * KC, 256), 256, 0, st>>>(w, wt, Co, C, K, g.groups));
     DLKA_LAUNCH("bwd_bias", st, bwd_bias_kernel<<<Co, 256, 0, st>>>(gout, gb, M, Co));
     bool first = true;
     for (i64 m0 = 0; m0 < M; m0 += Mc) {
@@ -225,8 +232,9 @@ int deform3d_backward_cl(const ConvGeo &g, const float *x, const float *off, con
         // columns = W^T . grad_output (deform_conv_cuda.cu:226-230), for this chunk only
         DLKA_TRY(dense_cl(gout + m0 * Co, Co, rows, Co, KC, wt, nullptr, EPI_NONE, nullptr, 0, colbuf, KC, math, wscratch, st));
         {
-            const int lpg = C / 4 >= 32 ? 32 : C / 4 > 8 ? 16 : C / 4 > 4 ? 8 : 4;   // (C/4 = 24 -> 16 lanes, two passes)
-            const int blocks = grid_for(rows * K * lpg, 256);
+            const int v4 = C / g.dg / 4;   // float4 per (row, tap, deformable group)
+            const int lpg = v4 >= 32 ? 32 : v4 > 8 ? 16 : v4 > 4 ? 8 : 4;   // (24 -> 16 lanes, two passes)
+            const int blocks = grid_for(rows * K * g.dg * lpg, 256);
             if (lpg == 32) DLKA_LAUNCH("bwd_scatter", st, bwd_scatter_kernel<32><<<blocks, 256, 0, st>>>(colbuf, x, off, gin, goff, g, m0, (int)rows, M));
             else if (lpg == 16) DLKA_LAUNCH("bwd_scatter", st, bwd_scatter_kernel<16><<<blocks, 256, 0, st>>>(colbuf, x, off, gin, goff, g, m0, (int)rows, M));
             else if (lpg == 8) DLKA_LAUNCH("bwd_scatter", st, bwd_scatter_kernel<8><<<blocks, 256, 0, st>>>(colbuf, x, off, gin, goff, g, m0, (int)rows, M));
@@ -253,7 +261,7 @@ int deform3d_backward_cl(const ConvGeo &g, const float *x, const float *off, con
         }
         first = false;
     }
-    DLKA_LAUNCH("bwd_unpack_gw", st, bwd_unpack_gw_kernel<<<grid_for((i64)Co * KC, 256), 256, 0, st>>>(gwt, gw, Co, C, K));
+    DLKA_LAUNCH("bwd_unpack_gw", st, bwd_unpack_gw_kernel<<<grid_for((i64)Co * KC, 256), 256, 0, st>>>(gwt, gw, Co, C, K, g.groups));
     return DLKA_OK;
 }
 

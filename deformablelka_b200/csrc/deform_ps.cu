@@ -95,6 +95,19 @@ __device__ __forceinline__ void ps_tile_coords(const DeformPsArgs &a, int tile, 
     b = tile / a.tiles_d;
 }
 
+// brick row r (0..127 = 4 d x 4 h x 8 w) of a tile: pure arithmetic, so the parameter warps and the epilogue warps each derive
+// it themselves and no row table has to be handed between them through shared memory
+__device__ __forceinline__ PsRow ps_row(const DeformPsArgs &a, int tile, int r, int &b)
+{
+    int td, th, tw;
+    ps_tile_coords(a, tile, b, td, th, tw);
+    const ConvGeo &g = a.g;
+    PsRow ri;
+    ri.d = td * PS_BD + (r >> 5); ri.h = th * PS_BH + ((r >> 3) & 3); ri.w = tw * PS_BW + (r & 7);
+    ri.m = (ri.d < g.Do && ri.h < g.Ho && ri.w < g.Wo) ? (int)((((i64)b * g.Do + ri.d) * g.Ho + ri.h) * g.Wo + ri.w) : -1;
+    return ri;
+}
+
 // Sampling parameters of one (row, tap): the position / validity rules are the reference's (cuh:245-248, 30-65) through
 // make_sample3; corners are addressed as 4 (d, h) PAIRS of w-adjacent lines starting at xb = clamp(floor(pw), 0, W-2), and
 // the w-interpolation weights are attached to whichever side of the pair holds that corner's voxel.
@@ -144,8 +157,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
     uint8_t *sA = smem;
     uint8_t *sB = sA + PS_SA * PS_ASLOT;
     uint8_t *sPrm = sB + PS_SB * B_SLOT;                                    // [SP][PS_PSTAGE]
-    PsRow *sRow = reinterpret_cast<PsRow *>(sPrm + PS_SP * PS_PSTAGE);      // [2][128]
-    float *sBias = reinterpret_cast<float *>(sRow + 2 * 128);               // [3][128]
+    float *sBias = reinterpret_cast<float *>(sPrm + PS_SP * PS_PSTAGE);     // [3][128]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sBias + 3 * 128);
     constexpr int NBARS = 2 * PS_SA + 2 * PS_SB + 2 * PS_SP + 4 + 4;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
@@ -275,13 +287,8 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
         const int r = tid - 128;
         uint32_t gp = 0;
         for (int i = 0; i < ntl; ++i) {
-            int b, td, th, tw;
-            ps_tile_coords(a, (int)blockIdx.x + i * (int)gridDim.x, b, td, th, tw);
-            PsRow ri;
-            ri.d = td * PS_BD + (r >> 5); ri.h = th * PS_BH + ((r >> 3) & 3); ri.w = tw * PS_BW + (r & 7);
-            ri.m = (ri.d < g.Do && ri.h < g.Ho && ri.w < g.Wo) ? (int)((((i64)b * g.Do + ri.d) * g.Ho + ri.h) * g.Wo + ri.w) : -1;
-            if (i >= 2) mbar_wait(accEmpty(i & 1), (uint32_t)((i >> 1) - 1) & 1u);   // the epilogue of tile i-2 has read its row table
-            sRow[(i & 1) * 128 + r] = ri;
+            int b;
+            const PsRow ri = ps_row(a, (int)blockIdx.x + i * (int)gridDim.x, r, b);
             // offsets of this row: column c at offrow[c * cs] (coalesced across the warp for the brick-major and NCDHW layouts)
             const i64 cs = a.off_cs;
             const float *offrow = a.Off;
@@ -383,7 +390,8 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
             const int buf = i & 1;
             mbar_wait_sleep(accFull(buf), (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
-            const PsRow ro = sRow[buf * 128 + row];
+            int b_unused;
+            const PsRow ro = ps_row(a, (int)blockIdx.x + i * (int)gridDim.x, row, b_unused);
             const bool live = ro.m >= 0;
             const uint32_t tacc = tlane + (uint32_t)buf * acc_stride, tX = tacc;   // the chain's X lives in this tile's drained buffer
             float *yp = a.Y + (i64)(live ? ro.m : 0) * a.ldY;
@@ -504,7 +512,7 @@ __global__ void ps_pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16
 
 size_t ps_smem_bytes(int NT)
 {
-    return (size_t)PS_SA * PS_ASLOT + (size_t)PS_SB * 2 * (PS_KC / 8) * NT * 16 + (size_t)PS_SP * PS_PSTAGE + 2 * 128 * sizeof(PsRow) +
+    return (size_t)PS_SA * PS_ASLOT + (size_t)PS_SB * 2 * (PS_KC / 8) * NT * 16 + (size_t)PS_SP * PS_PSTAGE +
            3 * 128 * sizeof(float) + (2 * PS_SA + 2 * PS_SB + 2 * PS_SP + 8) * 8 + 16 + 128;
 }
 

@@ -13,10 +13,8 @@
 // (positions, clamped corner offsets, masked trilinear weights: 64 B per (row, tap)), warps 8-23 gather / blend / convert
 // producers that fill the UMMA A slots (two groups on alternate K steps); all 20 producer warps then run the fused
 // epilogue chain (+bias -> conv1 -> * u -> proj_2 -> + x on the accumulator tile).
-// -DDLKA_DF_REGION=1 builds the alternative gather path: brick + halo of a 32-channel chunk staged in shared memory by one
-// TMA tile copy, 8 gather warps with 168 registers (setmaxnreg), software-pipelined predicated shared / global corner
-// loads.  Correct (same tests) but measured slower (13.8 vs 12.3 ms): both paths end up bound by the SM's L1 / shared
-// data path, see DESIGN.md 4.  -DDF_TRACE-style clock64 stamps (deform3d_set_trace, tools/df_trace.py) show the pipeline.
+// (Round 1 also carried a TMA-staged shared-memory gather variant, measured slower, 13.8 vs 12.3 ms; removed in round 2 --
+// the persistent kernel deform_ps.cu supersedes both for C <= 96; this kernel serves C > 96 and the K-split small volumes.)
 #include <cuda_bf16.h>
 
 #include <cstring>
@@ -26,7 +24,6 @@
 
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
-#include "tma_host.cuh"
 
 namespace dlka {
 namespace {
@@ -34,52 +31,28 @@ namespace {
 using namespace ptx;
 
 constexpr int DF_KC = 32;                 // channels per K step (one 128-byte line per voxel)
-#ifndef DLKA_DF_REGION
-#define DLKA_DF_REGION 0   // 0: gather through L1 (LDG; 12.3 ms, default); 1: TMA-staged shared-memory region, 8 fat gather warps (13.8 ms)
-#endif
 #ifndef DLKA_DF_SA
-#if DLKA_DF_REGION
-#define DLKA_DF_SA 3
-#define DLKA_DF_SB 2
-#define DLKA_DF_SP 4
-#else
 #define DLKA_DF_SA 3
 #define DLKA_DF_SB 3
 #define DLKA_DF_SP 4
 #endif
-#endif
-constexpr bool DF_REGION = DLKA_DF_REGION != 0;
 constexpr int DF_SA = DLKA_DF_SA, DF_SB = DLKA_DF_SB, DF_SP = DLKA_DF_SP;
 constexpr int DF_LBO = 2048 + 32;         // A plane stride (bank-spread padding; see profiles/r01 notes)
 constexpr int DF_APLANE = (DF_KC / 8) * DF_LBO;
 constexpr int DF_ASLOT = 2 * DF_APLANE;
-#ifndef DLKA_DF_SETMAXNREG
-#define DLKA_DF_SETMAXNREG 1
-#endif
-#if DLKA_DF_REGION && DLKA_DF_SETMAXNREG
-#define DF_SETMAXNREG(dir, n) asm volatile("setmaxnreg." dir ".sync.aligned.u32 " n ";")
-#else
-#define DF_SETMAXNREG(dir, n)
-#endif
 constexpr int DF_PARAM_WARPS = 4;
-constexpr int DF_GATHER_WARPS = DF_REGION ? 8 : 16;   // region path: fewer, fatter warps (128 registers) so loads can be software-pipelined
+constexpr int DF_GATHER_WARPS = 16;
 constexpr int DF_THREADS = (4 + DF_PARAM_WARPS + DF_GATHER_WARPS) * 32;
 constexpr int DF_EPI_WARPS = DF_PARAM_WARPS + DF_GATHER_WARPS, DF_EWQ = DF_EPI_WARPS / 4;   // epilogue warps, per TMEM lane quadrant
 #ifndef DLKA_DF_GROUPS
-#define DLKA_DF_GROUPS 2   // L1 path: gather warp groups taking alternate K steps (1: all 16 warps on every K step)
+#define DLKA_DF_GROUPS 2   // gather warp groups taking alternate K steps (1: all 16 warps on every K step)
 #endif
-constexpr int DF_GROUPS = DF_REGION ? 1 : DLKA_DF_GROUPS;
+constexpr int DF_GROUPS = DLKA_DF_GROUPS;
 constexpr int DF_GW = DF_GATHER_WARPS / DF_GROUPS;   // warps per group
 constexpr int DF_GT = DF_GW * 32;                     // threads per group
-constexpr int DF_UNITS = 128 * 8 / DF_GT;             // L1 path: (row, float4) units per thread and K step
+constexpr int DF_UNITS = 128 * 8 / DF_GT;             // (row, float4) units per thread and K step
 static_assert(DF_GROUPS == 1 || DF_GROUPS == 2, "gather groups");
 constexpr int DF_BD = 4, DF_BH = 4, DF_BW = 8;  // brick
-// staged region = brick + halo: covers every corner of samples with |offset| <~ 1 (tap reach 1 + offset + 1);
-// samples that leave it take the guarded global path, so any offset stays correct.
-constexpr int DF_HALO = 2;
-constexpr int DF_RD = DF_BD + 2 * DF_HALO, DF_RH = DF_BH + 2 * DF_HALO, DF_RW = DF_BW + 2 * DF_HALO;
-constexpr int DF_RV = DF_RD * DF_RH * DF_RW;                       // 768 voxels x 128 B (32 fp32 channels)
-constexpr int DF_REGION_BYTES = DF_REGION ? DF_RV * 128 : 0;
 constexpr int DF_PSTRIDE = 5;                                      // int4 per parameter record (80 B: bank spread)
 
 struct DeformTcArgs {
@@ -106,16 +79,7 @@ struct DeformTcArgs {
     int ldR;
     int chunk_split;      // > 0: grid.z slices of `chunk_split` channel chunks each; slice z writes its partial sum to Y + z * ysplit
     i64 ysplit;           // (bias only in slice 0); the host reduces the slices
-    long long *trace;     // optional debug timeline (clock64 stamps of CTA `trace_cta`), see tools/df_trace.py
-    int trace_cta;
 };
-
-// trace layout: [role 0..5][ks][2] : 0 MMA (wait done, issued) 1 loader (slot free, issued) 2 param warp 4 (start, done)
-//               3 gather warp 8 (waits done, arrive) 4 gather warp 23 (waits done, arrive) 5 gather warp 8 (loads consumed, -)
-#define DF_TRACE(role, ks, ev)                                                                      \
-    do {                                                                                            \
-        if (a.trace && (int)blockIdx.x == a.trace_cta) a.trace[((role) * 1024 + (ks)) * 2 + (ev)] = clock64(); \
-    } while (0)
 
 struct DfRow {
     int b, d, h, w;
@@ -123,10 +87,9 @@ struct DfRow {
     int pad[3];
 };
 
-// 8 corner offsets + 8 masked weights.  Region mode: offsets are byte offsets into the staged region when all 8
-// (clamped) corners lie inside it, else global element offsets with bit 31 of o0.x set (guarded global path).
+// 8 corner element offsets (clamped) + 8 masked trilinear weights of one (row, tap)
 __device__ __forceinline__ void df_make_params(const DeformTcArgs &a, const DfRow &ri, int ii, int jj, int kk, float od, float oh,
-                                               float ow, int4 *prm, int rd0, int rh0, int rw0)
+                                               float ow, int4 *prm)
 {
     const ConvGeo &g = a.g;
     int4 o0 = make_int4(0, 0, 0, 0), o1 = o0;
@@ -141,22 +104,11 @@ __device__ __forceinline__ void df_make_params(const DeformTcArgs &a, const DfRo
             const int d0 = max(s.lo[0], 0), d1 = min(s.lo[0] + 1, g.D - 1);
             const int h0 = max(s.lo[1], 0), h1 = min(s.lo[1] + 1, g.H - 1);
             const int x0 = max(s.lo[2], 0), x1 = min(s.lo[2] + 1, g.W - 1);
-            const int zd0 = d0 - rd0, zd1 = d1 - rd0, zh0 = h0 - rh0, zh1 = h1 - rh0, zx0 = x0 - rw0, zx1 = x1 - rw0;
-            const bool inside = DF_REGION && zd0 >= 0 && zd1 < DF_RD && zh0 >= 0 && zh1 < DF_RH && zx0 >= 0 && zx1 < DF_RW;
-            if (inside) {   // region path: offsets in float4 (16-byte) units from the region base
-                const int sX = 8, sH = DF_RW * sX, sD = DF_RH * sH;
-                o0.x = zd0 * sD + zh0 * sH + zx0 * sX; o0.y = zd0 * sD + zh0 * sH + zx1 * sX;
-                o0.z = zd0 * sD + zh1 * sH + zx0 * sX; o0.w = zd0 * sD + zh1 * sH + zx1 * sX;
-                o1.x = zd1 * sD + zh0 * sH + zx0 * sX; o1.y = zd1 * sD + zh0 * sH + zx1 * sX;
-                o1.z = zd1 * sD + zh1 * sH + zx0 * sX; o1.w = zd1 * sD + zh1 * sH + zx1 * sX;
-            } else {        // global element offsets (L1 path), or float4 units with bit 31 of o0.x set (region path, corner outside)
-                const int sX = DF_REGION ? g.C / 4 : g.C, sH = g.W * sX, sD = g.H * sH;
-                o0.x = d0 * sD + h0 * sH + x0 * sX; o0.y = d0 * sD + h0 * sH + x1 * sX;
-                o0.z = d0 * sD + h1 * sH + x0 * sX; o0.w = d0 * sD + h1 * sH + x1 * sX;
-                o1.x = d1 * sD + h0 * sH + x0 * sX; o1.y = d1 * sD + h0 * sH + x1 * sX;
-                o1.z = d1 * sD + h1 * sH + x0 * sX; o1.w = d1 * sD + h1 * sH + x1 * sX;
-                if (DF_REGION) o0.x |= (int)0x80000000;
-            }
+            const int sX = g.C, sH = g.W * sX, sD = g.H * sH;
+            o0.x = d0 * sD + h0 * sH + x0 * sX; o0.y = d0 * sD + h0 * sH + x1 * sX;
+            o0.z = d0 * sD + h1 * sH + x0 * sX; o0.w = d0 * sD + h1 * sH + x1 * sX;
+            o1.x = d1 * sD + h0 * sH + x0 * sX; o1.y = d1 * sD + h0 * sH + x1 * sX;
+            o1.z = d1 * sD + h1 * sH + x0 * sX; o1.w = d1 * sD + h1 * sH + x1 * sX;
             w0.x = (s.mask & (1 << 1)) ? hd * hh * hw : 0.f; w0.y = (s.mask & (1 << 2)) ? hd * hh * lw : 0.f;
             w0.z = (s.mask & (1 << 3)) ? hd * lh * hw : 0.f; w0.w = (s.mask & (1 << 4)) ? hd * lh * lw : 0.f;
             w1.x = (s.mask & (1 << 5)) ? ld * hh * hw : 0.f; w1.y = (s.mask & (1 << 6)) ? ld * hh * lw : 0.f;
@@ -168,28 +120,7 @@ __device__ __forceinline__ void df_make_params(const DeformTcArgs &a, const DfRo
     *reinterpret_cast<float4 *>(prm + 3) = w1;
 }
 
-// predicated pair: shared-memory load when `in`, read-only global load otherwise (exactly one of them executes).
-// `off` is in float4 units from either base; the addresses are formed inside the block so they do not stay live.
-__device__ __forceinline__ float4 ld_region_or_global(uint32_t sbase, const float4 *gbase, int off, int in)
-{
-    float4 v;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b32 sa;\n\t"
-        ".reg .b64 ga;\n\t"
-        "setp.ne.b32 p, %7, 0;\n\t"
-        "mad.lo.u32 sa, %6, 16, %4;\n\t"
-        "mad.wide.s32 ga, %6, 16, %5;\n\t"
-        "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [sa];\n\t"
-        "@!p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [ga];\n\t"
-        "}\n"
-        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-        : "r"(sbase), "l"(gbase), "r"(off), "r"(in));
-    return v;
-}
-
-__global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const DeformTcArgs a, const __grid_constant__ CUtensorMap tmapX)
+__global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const DeformTcArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const ConvGeo &g = a.g;
@@ -200,11 +131,10 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     int4 *sPrm = reinterpret_cast<int4 *>(sB + DF_SB * B_SLOT);                 // [SP][128][PSTRIDE]
     DfRow *sRow = reinterpret_cast<DfRow *>(sPrm + DF_SP * 128 * DF_PSTRIDE);   // [128]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sRow + 128);
-    constexpr int NBARS = 2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6 + 2;
+    constexpr int NBARS = 2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
     float *sBias = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);                 // [3][128]: conv bias, conv1 bias, proj_2 bias (0 beyond Co)
-    uint8_t *sReg = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sBias + 3 * 128) + 127) & ~(uintptr_t)127);  // region
-    uint8_t *sChainW = DF_REGION ? sReg : sB;   // chain weights: the region is free once the main loop is done
+    uint8_t *sChainW = sB;   // chain weights reuse the weight ring once the main loop is done
     const uint32_t bar0 = smem_u32(bars);
     auto fullA = [&](int s) { return bar0 + 8u * s; };
     auto emptyA = [&](int s) { return bar0 + 8u * (DF_SA + s); };
@@ -212,12 +142,11 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     auto emptyB = [&](int s) { return bar0 + 8u * (2 * DF_SA + DF_SB + s); };
     auto fullP = [&](int s) { return bar0 + 8u * (2 * DF_SA + 2 * DF_SB + s); };
     auto emptyP = [&](int s) { return bar0 + 8u * (2 * DF_SA + 2 * DF_SB + DF_SP + s); };
-    const uint32_t accFull = bar0 + 8u * (NBARS - 9);
+    const uint32_t accFull = bar0 + 8u * (NBARS - 7);
     const uint32_t barW1 = accFull + 8, barE1 = accFull + 16, barC1 = accFull + 24, barW2 = accFull + 32, barE2 = accFull + 40,
-                   barC2 = accFull + 48, regFull = accFull + 56, regEmpty = accFull + 64;
+                   barC2 = accFull + 48;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 128) DF_TRACE(1, 0, 1);   // misc stamps (role 1, event 1): 0 entry, 1 setup done, 2 accFull, 3+2*stage waited, 4+2*stage done, 10 exit
     const int n_tile = blockIdx.y;
     int bid = blockIdx.x;
     const int tw = bid % a.tiles_w; bid /= a.tiles_w;
@@ -239,7 +168,6 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
         mbar_init(accFull, 1);
         mbar_init(barW1, 1); mbar_init(barE1, DF_EPI_WARPS); mbar_init(barC1, 1);
         mbar_init(barW2, 1); mbar_init(barE2, DF_EPI_WARPS); mbar_init(barC2, 1);
-        mbar_init(regFull, 1); mbar_init(regEmpty, DF_GATHER_WARPS);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -266,7 +194,6 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (tid == 128) DF_TRACE(1, 1, 1);
 
     auto epilogue = [&]() {
         // ===================== epilogue: all producer warps (parameter + gather) =====================
@@ -293,12 +220,10 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             }
         };
         mbar_wait(accFull, 0);
-        if (tid == 128) DF_TRACE(1, 2, 1);
         tc_fence_after();
         for (int stage = 0; stage <= a.chain; ++stage) {
             if (stage == 1) mbar_wait(barC1, 0);
             if (stage == 2) mbar_wait(barC2, 0);
-            if (tid == 128) DF_TRACE(1, 3 + 2 * stage, 1);
             if (stage) tc_fence_after();
             const bool last = stage == a.chain;
             const float *sb = sBias + stage * 128;
@@ -343,7 +268,6 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                     *reinterpret_cast<uint4 *>(sA + chainA_lo + boff) = make_uint4(lo0.x, lo0.y, lo1.x, lo1.y);
                 }
             }
-            if (tid == 128) DF_TRACE(1, 4 + 2 * stage, 1);
             if (!last) {
                 fence_proxy_async();
                 tc_fence_before();
@@ -356,11 +280,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
         }
     };
 
-    // Roles by warpgroup.  Region path: register reallocation per warpgroup (56 + 120 + 168 + 168 = 4 x 128, what the CTA was
-    // launched with) -- the control warps and the parameter producers hand registers to the two gather warpgroups, which
-    // keep two 8-load batches in flight.  setmaxnreg must dominate the role code for ptxas to honour the new budget.
+    // Roles by warpgroup
     if (warp < 4) {
-    DF_SETMAXNREG("dec", "56");
     if (warp == 0) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
@@ -368,9 +289,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             for (int ks = 0; ks < KS; ++ks) {
                 const int bs = ks % DF_SB, as = ks % DF_SA;
                 mbar_wait(fullB(bs), (ks / DF_SB) & 1);
-                DF_TRACE(0, ks, 0);
                 mbar_wait(fullA(as), (ks / DF_SA) & 1);
-                DF_TRACE(0, ks, 1);
                 tc_fence_after();
                 const uint32_t ahi = smem_u32(sA + as * DF_ASLOT), alo = ahi + DF_APLANE;
                 const uint32_t bhi = smem_u32(sB + bs * B_SLOT), blo = bhi + B_PLANE;
@@ -391,9 +310,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             // ---- fused 1x1 chain: A = epilogue-written rows in sA, B = whole weight matrix in sB ----
             for (int stage = 1; stage <= a.chain; ++stage) {
                 mbar_wait(stage == 1 ? barW1 : barW2, 0);
-                DF_TRACE(1, 20 + 3 * stage, 1);
                 mbar_wait(stage == 1 ? barE1 : barE2, 0);
-                DF_TRACE(1, 21 + 3 * stage, 1);
                 tc_fence_after();
                 const uint32_t ahi = smem_u32(sA), alo = ahi + chainA_lo, bhi = smem_u32(sChainW), blo = bhi + chainB_lo;
                 const uint32_t d_tmem = tmem_base + (stage == 1 ? (uint32_t)NT : 0u);
@@ -406,7 +323,6 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                     }
                 }
                 umma_commit(stage == 1 ? barC1 : barC2);
-                DF_TRACE(1, 22 + 3 * stage, 1);
             }
         }
     } else if (warp == 1) {
@@ -416,7 +332,6 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
             for (int ks = 0; ks < KS; ++ks) {
                 const int bs = ks % DF_SB;
                 mbar_wait(emptyB(bs), ((ks / DF_SB) & 1) ^ 1);
-                DF_TRACE(1, ks, 0);
                 mbar_arrive_expect_tx(fullB(bs), (uint32_t)B_SLOT);
                 bulk_g2s(smem_u32(sB + bs * B_SLOT), src + (i64)ks * B_SLOT, (uint32_t)B_SLOT, fullB(bs));
             }
@@ -432,18 +347,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                 }
             }
         }
-    } else if (DF_REGION && warp == 2) {
-        // ===================== region loader: brick + halo of one 32-channel chunk, ONE TMA tile copy =====================
-        if (elect_one()) {
-            for (int c = 0; c < nchunks; ++c) {
-                if (c > 0) mbar_wait(regEmpty, (c - 1) & 1);   // all 16 gather warps are done with the previous chunk
-                mbar_arrive_expect_tx(regFull, (uint32_t)DF_REGION_BYTES);
-                tma_load_5d(smem_u32(sReg), &tmapX, regFull, c * DF_KC, tw * DF_BW - DF_HALO, th * DF_BH - DF_HALO, td * DF_BD - DF_HALO, b);
-            }
-        }
     }
     } else if (warp < 8) {
-        DF_SETMAXNREG("dec", "120");
         // ===================== sample-parameter producers (one thread per brick row) =====================
         const int r = tid - 128;
         const DfRow ri = sRow[r];
@@ -464,12 +369,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
                 }
             }
             mbar_wait(emptyP(ps), ph);
-            if (warp == 4 && lane == 0) DF_TRACE(2, ks, 0);
-            df_make_params(a, ri, ii, jj, kk, od, oh, ow, sPrm + (ps * 128 + r) * DF_PSTRIDE, td * DF_BD - DF_HALO,
-                           th * DF_BH - DF_HALO, tw * DF_BW - DF_HALO);
+            df_make_params(a, ri, ii, jj, kk, od, oh, ow, sPrm + (ps * 128 + r) * DF_PSTRIDE);
             __syncwarp();
             if (lane == 0) mbar_arrive(fullP(ps));
-            if (warp == 4 && lane == 0) DF_TRACE(2, ks, 1);
             od = nod; oh = noh; ow = now;
             tap = ntap;
             if (++kk == g.kw) { kk = 0; if (++jj == g.kh) { jj = 0; if (++ii == g.kd) ii = 0; } }
@@ -477,157 +379,61 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform3d_tc_kernel(const Deform
         }
         epilogue();
     } else {
-        DF_SETMAXNREG("inc", "168");
         // ===================== gather / blend / convert producers =====================
         // DF_GROUPS == 2: the 16 warps form two groups that take alternate K steps, so one group's load phase overlaps
         // the other's blend/convert/store phase instead of all 16 warps moving in lock step.
         const int gt = tid - 256;                      // 0..511
         const int grp = (warp - 8) / DF_GW;
         const int ggt = gt - grp * DF_GT;              // thread within its group
-        if (!DF_REGION) {
-            // ---- L1 path: thread = (row, float4 cg of the 32-channel chunk); a warp instruction touches 4 lines ----
-            const int cg = gt & 7;
-            const float *Xb = a.X + (i64)b * a.vol_c + cg * 4;
-            for (int ks = grp; ks < KS; ks += DF_GROUPS) {
-                const int chunk = chunk0 + ks / K;
-                const int as = ks % DF_SA, ps = ks % DF_SP;
-                const uint32_t phA = ((ks / DF_SA) & 1) ^ 1, phP = (ks / DF_SP) & 1;   // emptyA starts "free", fullP "not ready"
-                mbar_wait(fullP(ps), phP);
-                if (warp == 8 && lane == 0) DF_TRACE(5, ks, 1);
-                mbar_wait(emptyA(as), phA);
-                if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 0);
-                uint8_t *slot = sA + as * DF_ASLOT;
-                const float *base = Xb + chunk * DF_KC;
+        // thread = (row, float4 cg of the 32-channel chunk); a warp instruction touches 4 lines ----
+        const int cg = gt & 7;
+        const float *Xb = a.X + (i64)b * a.vol_c + cg * 4;
+        for (int ks = grp; ks < KS; ks += DF_GROUPS) {
+            const int chunk = chunk0 + ks / K;
+            const int as = ks % DF_SA, ps = ks % DF_SP;
+            const uint32_t phA = ((ks / DF_SA) & 1) ^ 1, phP = (ks / DF_SP) & 1;   // emptyA starts "free", fullP "not ready"
+            mbar_wait(fullP(ps), phP);
+            mbar_wait(emptyA(as), phA);
+            uint8_t *slot = sA + as * DF_ASLOT;
+            const float *base = Xb + chunk * DF_KC;
 #pragma unroll
-                for (int u0 = 0; u0 < DF_UNITS; u0 += 2) {
-                    float4 acc[2];
+            for (int u0 = 0; u0 < DF_UNITS; u0 += 2) {
+                float4 acc[2];
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        const int row = (ggt >> 3) + (u0 + s) * (DF_GT / 8);
-                        const int4 *prm = sPrm + (ps * 128 + row) * DF_PSTRIDE;
-                        const int4 o0 = prm[0], o1 = prm[1];
-                        const float4 w0 = *reinterpret_cast<const float4 *>(prm + 2), w1 = *reinterpret_cast<const float4 *>(prm + 3);
-                        const float4 v0 = ldg4(base + o0.x), v1 = ldg4(base + o0.y), v2 = ldg4(base + o0.z), v3 = ldg4(base + o0.w);
-                        const float4 v4 = ldg4(base + o1.x), v5 = ldg4(base + o1.y), v6 = ldg4(base + o1.z), v7 = ldg4(base + o1.w);
-                        float4 r = f4zero();
-                        fma4(r, w0.x, v0); fma4(r, w0.y, v1); fma4(r, w0.z, v2); fma4(r, w0.w, v3);
-                        fma4(r, w1.x, v4); fma4(r, w1.y, v5); fma4(r, w1.z, v6); fma4(r, w1.w, v7);
-                        acc[s] = r;
-                    }
-                    if (u0 + 2 == DF_UNITS) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(emptyP(ps));    // parameters consumed
-                        if (warp == 8 && lane == 0) DF_TRACE(5, ks, 0);
-                    }
-#pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        const int row = (ggt >> 3) + (u0 + s) * (DF_GT / 8);
-                        uint2 hi, lo;
-                        split_bf16x4(acc[s], hi, lo);
-                        const int boff = (cg >> 1) * DF_LBO + row * 16 + (cg & 1) * 8;
-                        *reinterpret_cast<uint2 *>(slot + boff) = hi;
-                        *reinterpret_cast<uint2 *>(slot + DF_APLANE + boff) = lo;
-                    }
+                for (int s = 0; s < 2; ++s) {
+                    const int row = (ggt >> 3) + (u0 + s) * (DF_GT / 8);
+                    const int4 *prm = sPrm + (ps * 128 + row) * DF_PSTRIDE;
+                    const int4 o0 = prm[0], o1 = prm[1];
+                    const float4 w0 = *reinterpret_cast<const float4 *>(prm + 2), w1 = *reinterpret_cast<const float4 *>(prm + 3);
+                    const float4 v0 = ldg4(base + o0.x), v1 = ldg4(base + o0.y), v2 = ldg4(base + o0.z), v3 = ldg4(base + o0.w);
+                    const float4 v4 = ldg4(base + o1.x), v5 = ldg4(base + o1.y), v6 = ldg4(base + o1.z), v7 = ldg4(base + o1.w);
+                    float4 r = f4zero();
+                    fma4(r, w0.x, v0); fma4(r, w0.y, v1); fma4(r, w0.z, v2); fma4(r, w0.w, v3);
+                    fma4(r, w1.x, v4); fma4(r, w1.y, v5); fma4(r, w1.z, v6); fma4(r, w1.w, v7);
+                    acc[s] = r;
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(fullA(as));
-                if (lane == 0 && (warp == 8 || warp == 23)) DF_TRACE(warp == 8 ? 3 : 4, ks, 1);
-            }
-        } else {
-            // ---- shared-memory path: the chunk's brick + halo region is staged by ONE TMA tile copy; 8 fat gather warps ----
-            // thread = (row, 8 channels): 4 lanes per row, lane j owns channels [8j, 8j+8) = one 16-byte K chunk of the A
-            // operand, fetched as two float4 halves.  Odd rows take the upper half first, so a quarter-warp (2 rows x 4
-            // lanes) covers all 32 banks exactly once per LDS.128.  Each thread serves rows r0 and r0 + 64 per K step; the
-            // four (row, half) items are software-pipelined: the 8 corner loads of the next item are in flight while the
-            // current one is blended, across K steps too, so the LSU and the FMA pipe overlap inside every warp.
-            const int j4 = lane & 3, r0 = gt >> 2, swp = r0 & 1;
-            // every corner is fetched by a PREDICATED pair (ld.shared from the staged region | ld.global when the sample left
-            // the region): no branch, so the loads stay in flight across the blend of the previous item, and the common case
-            // runs at the shared-memory rate (a generic-address load measured at the L1 rate instead)
-            const uint32_t rs0 = smem_u32(sReg) + (2 * j4 + swp) * 16, rs1 = smem_u32(sReg) + (2 * j4 + (swp ^ 1)) * 16;
-            const float4 *xg = reinterpret_cast<const float4 *>(a.X + (i64)b * a.vol_c);
-            auto ldp = [&](int ps, int row, int4 &o0, int4 &o1, float4 &w0, float4 &w1) {
-                const int4 *prm = sPrm + (ps * 128 + row) * DF_PSTRIDE;
-                o0 = prm[0]; o1 = prm[1];
-                w0 = *reinterpret_cast<const float4 *>(prm + 2); w1 = *reinterpret_cast<const float4 *>(prm + 3);
-            };
-            auto issue = [&](float4(&v)[8], const int4 &o0, const int4 &o1, int half, int chunk) {
-                const int in = o0.x >= 0;
-                const uint32_t sb = half ? rs1 : rs0;
-                const float4 *gb = xg + chunk * (DF_KC / 4) + (2 * j4 + (half ^ swp));
-                const int ox = o0.x & 0x7fffffff;
-                v[0] = ld_region_or_global(sb, gb, ox, in); v[1] = ld_region_or_global(sb, gb, o0.y, in);
-                v[2] = ld_region_or_global(sb, gb, o0.z, in); v[3] = ld_region_or_global(sb, gb, o0.w, in);
-                v[4] = ld_region_or_global(sb, gb, o1.x, in); v[5] = ld_region_or_global(sb, gb, o1.y, in);
-                v[6] = ld_region_or_global(sb, gb, o1.z, in); v[7] = ld_region_or_global(sb, gb, o1.w, in);
-            };
-            auto blend = [&](const float4(&v)[8], const float4 &w0, const float4 &w1) {
-                float4 r = f4zero();
-                fma4(r, w0.x, v[0]); fma4(r, w0.y, v[1]); fma4(r, w0.z, v[2]); fma4(r, w0.w, v[3]);
-                fma4(r, w1.x, v[4]); fma4(r, w1.y, v[5]); fma4(r, w1.z, v[6]); fma4(r, w1.w, v[7]);
-                return r;
-            };
-            auto store_row = [&](uint8_t *slot, int row, const float4 &h0, const float4 &h1) {   // results of half 0 / half 1
-                uint2 hl, ll, hu, lu;
-                split_bf16x4(swp ? h1 : h0, hl, ll);   // channels 8j .. 8j+3
-                split_bf16x4(swp ? h0 : h1, hu, lu);   // channels 8j+4 .. 8j+7
-                const int boff = j4 * DF_LBO + row * 16;
-                *reinterpret_cast<uint4 *>(slot + boff) = make_uint4(hl.x, hl.y, hu.x, hu.y);
-                *reinterpret_cast<uint4 *>(slot + DF_APLANE + boff) = make_uint4(ll.x, ll.y, lu.x, lu.y);
-            };
-            int4 oA0, oA1, oB0, oB1;
-            float4 wA0, wA1, wB0, wB1, va[8], vb[8];
-            int chunk = 0, tap = 0;
-            mbar_wait(regFull, 0);
-            mbar_wait(fullP(0), 0);
-            ldp(0, r0, oA0, oA1, wA0, wA1);
-            issue(va, oA0, oA1, 0, chunk);
-            for (int ks = 0; ks < KS; ++ks) {
-                const int as = ks % DF_SA, ps = ks % DF_SP;
-                const uint32_t phA = ((ks / DF_SA) & 1) ^ 1;
-                uint8_t *slot = sA + as * DF_ASLOT;
-                if (lane == 0 && warp == 8) DF_TRACE(3, ks, 0);
-                issue(vb, oA0, oA1, 1, chunk);
-                const float4 ra0 = blend(va, wA0, wA1);
-                ldp(ps, r0 + 64, oB0, oB1, wB0, wB1);
-                issue(va, oB0, oB1, 0, chunk);
-                const float4 ra1 = blend(vb, wA0, wA1);
-                mbar_wait(emptyA(as), phA);
-                store_row(slot, r0, ra0, ra1);
-                issue(vb, oB0, oB1, 1, chunk);
-                const float4 rb0 = blend(va, wB0, wB1);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(emptyP(ps));    // both rows' parameters are in registers
-                const int nks = ks + 1;
-                const bool more = nks < KS, same = more && tap + 1 < K;
-                if (same) {   // first item of the next K step: in flight while this step's last item is blended and stored
-                    mbar_wait(fullP(nks % DF_SP), (nks / DF_SP) & 1);
-                    ldp(nks % DF_SP, r0, oA0, oA1, wA0, wA1);
-                    issue(va, oA0, oA1, 0, chunk);
+                if (u0 + 2 == DF_UNITS) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(emptyP(ps));    // parameters consumed
                 }
-                const float4 rb1 = blend(vb, wB0, wB1);
-                store_row(slot, r0 + 64, rb0, rb1);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(fullA(as));
-                if (lane == 0 && warp == 8) DF_TRACE(3, ks, 1);
-                if (++tap == K) tap = 0;
-                if (more && !same) {   // chunk boundary: every load of the old region has been consumed by this warp
-                    if (lane == 0) mbar_arrive(regEmpty);
-                    ++chunk;
-                    mbar_wait(regFull, chunk & 1);
-                    mbar_wait(fullP(nks % DF_SP), (nks / DF_SP) & 1);
-                    ldp(nks % DF_SP, r0, oA0, oA1, wA0, wA1);
-                    issue(va, oA0, oA1, 0, chunk);
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int row = (ggt >> 3) + (u0 + s) * (DF_GT / 8);
+                    uint2 hi, lo;
+                    split_bf16x4(acc[s], hi, lo);
+                    const int boff = (cg >> 1) * DF_LBO + row * 16 + (cg & 1) * 8;
+                    *reinterpret_cast<uint2 *>(slot + boff) = hi;
+                    *reinterpret_cast<uint2 *>(slot + DF_APLANE + boff) = lo;
                 }
             }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(fullA(as));
         }
         epilogue();
     }
     tc_fence_before();
     __syncthreads();
-    if (tid == 128) DF_TRACE(1, 10, 1);
     if (warp == 0) {
         __syncwarp();
         tc_fence_after();
@@ -661,14 +467,10 @@ __global__ void pack_weight_df_kernel(const float *__restrict__ w, __nv_bfloat16
 size_t df_smem_bytes(int NT)
 {
     return (size_t)DF_SA * DF_ASLOT + (size_t)DF_SB * 2 * (DF_KC / 8) * NT * 16 + (size_t)DF_SP * 128 * DF_PSTRIDE * 16 +
-           128 * sizeof(DfRow) + (2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6 + 2) * 8 + 16 + 3 * 128 * sizeof(float) + 256 + DF_REGION_BYTES;
+           128 * sizeof(DfRow) + (2 * DF_SA + 2 * DF_SB + 2 * DF_SP + 1 + 6) * 8 + 16 + 3 * 128 * sizeof(float) + 256;
 }
 
 }  // namespace
-
-static long long *g_df_trace = nullptr;
-static int g_df_trace_cta = 0;
-void deform3d_set_trace(long long *buf, int cta) { g_df_trace = buf; g_df_trace_cta = cta; }
 
 bool deform3d_tc_supported(const IgemmArgs &a)
 {
@@ -698,7 +500,6 @@ int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, const DeformChain
     const int n_tiles = (int)cdiv(g.Co, a.NT);
     a.tiles_d = (int)cdiv(g.Do, DF_BD); a.tiles_h = (int)cdiv(g.Ho, DF_BH); a.tiles_w = (int)cdiv(g.Wo, DF_BW);
     a.vol_c = (i64)g.D * g.H * g.W * g.C;
-    a.trace = g_df_trace; a.trace_cta = g_df_trace_cta;
     a.chunk_split = 0; a.ysplit = 0;
     a.chain = 0; a.W1p = a.W2p = nullptr; a.b1 = a.b2 = a.U = a.R = nullptr; a.ldU = a.ldR = 0;
     if (chain && chain->stages) {
@@ -719,15 +520,12 @@ int deform3d_tc(const IgemmArgs &ga, const float *w, void *bp, const DeformChain
     static SmemOptIn optin;   // per launch site (= per kernel instantiation), per device
     DLKA_TRY(optin.ensure(deform3d_tc_kernel, smem));
     dim3 grid((unsigned)((i64)g.B * a.tiles_d * a.tiles_h * a.tiles_w), (unsigned)n_tiles);
-    if (ga.ksplit_steps > 0 && !a.chain && !DF_REGION) {   // K split over channel chunks (small volumes: a few tiles, a long K loop)
+    if (ga.ksplit_steps > 0 && !a.chain) {   // K split over channel chunks (small volumes: a few tiles, a long K loop)
         a.chunk_split = ga.ksplit_steps;
         a.ysplit = ga.ysplit_stride;
         grid.z = (unsigned)((g.C / DF_KC) / a.chunk_split);
     }
-    CUtensorMap tmapX;
-    memset(&tmapX, 0, sizeof(tmapX));
-    if (DF_REGION && !make_tmap_cl5(&tmapX, a.X, g.B, g.C, g.D, g.H, g.W, DF_KC, DF_RW, DF_RH, DF_RD, 1)) return DLKA_ERR_CUDA;
-    DLKA_LAUNCH(a.chain ? "tc_deform3d_chain" : "tc_deform3d", st, (deform3d_tc_kernel<<<grid, DF_THREADS, smem, st>>>(a, tmapX)));
+    DLKA_LAUNCH(a.chain ? "tc_deform3d_chain" : "tc_deform3d", st, (deform3d_tc_kernel<<<grid, DF_THREADS, smem, st>>>(a)));
     return DLKA_OK;
 }
 

@@ -62,7 +62,6 @@ struct DeformChain {
     const void *W1p; const float *b1; const float *U; int ldU;
     const void *W2p; const float *b2; const float *R; int ldR;
 };
-void deform3d_set_trace(long long *buf, int cta);   // debug timeline of one CTA (tools/df_trace.py)
 bool deform3d_tc_supported(const IgemmArgs &a);
 bool deform3d_chain_supported(const IgemmArgs &a);
 int deform3d_tc(const IgemmArgs &a, const float *w, void *bp, const DeformChain *chain, cudaStream_t st);

@@ -389,8 +389,10 @@ class LKA_Attention3d_deform_ACDC(LKA_Attention3d_deform):
         self.proj_2 = nn.Conv3d(d_model, d_model, 1)
 
 
-def deform_conv3d_autograd(x, offset, weight, bias, stride=(1, 1, 1), padding=(1, 1, 1), dilation=(1, 1, 1)):
-    """Differentiable pure-torch restatement of the 3D deformable conv forward (groups = deformable groups = 1), used as the
+def deform_conv3d_autograd(x, offset, weight, bias, stride=(1, 1, 1), padding=(1, 1, 1), dilation=(1, 1, 1), group=1,
+                           deformable_group=1):
+    """Differentiable pure-torch restatement of the 3D deformable conv forward (weight groups: deform_conv_cuda.cu:84-110,
+    deformable groups: the offset channel ((dg * K + tap) * 3 + axis) of deform_im2col_cuda.cuh:222-235), used as the
     backward oracle: autograd through it yields exactly the gradients dmcn_get_gradient_weight / dmcn_get_coordinate_weight
     define (deform_im2col_cuda.cuh:74-190) -- the corner weights are differentiated, floor() has zero derivative, and the
     sample / corner validity rules are those of dmcn_im2col_bilinear (cuh:30-65, 248).  Small shapes only."""
@@ -406,13 +408,17 @@ def deform_conv3d_autograd(x, offset, weight, bias, stride=(1, 1, 1), padding=(1
     od = (torch.arange(Do, dtype=x.dtype) * sd - pd).view(1, Do, 1, 1)
     oh = (torch.arange(Ho, dtype=x.dtype) * sh - ph).view(1, 1, Ho, 1)
     ow = (torch.arange(Wo, dtype=x.dtype) * sw - pw).view(1, 1, 1, Wo)
-    xf = x.reshape(B, C, D * H * W)
-    cols = []
-    for tap in range(K):
+    cpd = C // deformable_group
+    gcols = []
+    for dgi in range(deformable_group):
+      xf = x[:, dgi * cpd:(dgi + 1) * cpd].reshape(B, cpd, D * H * W)
+      cols = []
+      for tap in range(K):
         i, j, k = tap // (kh * kw), (tap // kw) % kh, tap % kw
-        p_d = od + i * dd + offset[:, 3 * tap]          # [B, Do, Ho, Wo]
-        p_h = oh + j * dh + offset[:, 3 * tap + 1]
-        p_w = ow + k * dw + offset[:, 3 * tap + 2]
+        oc = 3 * (dgi * K + tap)
+        p_d = od + i * dd + offset[:, oc]               # [B, Do, Ho, Wo]
+        p_h = oh + j * dh + offset[:, oc + 1]
+        p_w = ow + k * dw + offset[:, oc + 2]
         valid = (p_d > -1) & (p_h > -1) & (p_w > -1) & (p_d < D) & (p_h < H) & (p_w < W)
         d0, h0, w0 = torch.floor(p_d).detach(), torch.floor(p_h).detach(), torch.floor(p_w).detach()
         ld, lh, lw = p_d - d0, p_h - h0, p_w - w0
@@ -424,12 +430,15 @@ def deform_conv3d_autograd(x, offset, weight, bias, stride=(1, 1, 1), padding=(1
                     ok = valid & (di >= 0) & (di <= D - 1) & (hi >= 0) & (hi <= H - 1) & (wi >= 0) & (wi <= W - 1)
                     wgt = (ld if cd else 1 - ld) * (lh if ch else 1 - lh) * (lw if cw else 1 - lw)
                     idx = (di.clamp(0, D - 1) * H + hi.clamp(0, H - 1)) * W + wi.clamp(0, W - 1)
-                    g = torch.gather(xf, 2, idx.long().view(B, 1, -1).expand(B, C, -1)).view(B, C, Do, Ho, Wo)
+                    g = torch.gather(xf, 2, idx.long().view(B, 1, -1).expand(B, cpd, -1)).view(B, cpd, Do, Ho, Wo)
                     val = val + g * (wgt * ok.to(x.dtype)).unsqueeze(1)
         cols.append(val)
-    col = torch.stack(cols, dim=2)                       # [B, C, K, Do, Ho, Wo]
-    out = torch.einsum("bckdhw,ock->bodhw", col, weight.reshape(Co, C, K))
-    return out + bias.view(1, Co, 1, 1, 1)
+      gcols.append(torch.stack(cols, dim=2))             # [B, cpd, K, Do, Ho, Wo]
+    col = torch.cat(gcols, dim=1)                        # [B, C, K, Do, Ho, Wo]
+    cpg, copg = C // group, Co // group
+    outs = [torch.einsum("bckdhw,ock->bodhw", col[:, gi * cpg:(gi + 1) * cpg],
+                         weight[gi * copg:(gi + 1) * copg].reshape(copg, cpg, K)) for gi in range(group)]
+    return torch.cat(outs, dim=1) + bias.view(1, Co, 1, 1, 1)
 
 
 class PatchExpand(nn.Module):

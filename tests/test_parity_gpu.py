@@ -597,12 +597,41 @@ def test_deform_conv_pack3d_autograd_end_to_end(dl, oracle, math):
         assert rel_err(p.grad, po.grad) < TOL, n
 
 
-def test_deform_conv3d_backward_refuses_groups(dl):
+@pytest.mark.parametrize("C,Co,group,dgrp,dims,scale", [
+    (16, 8, 2, 1, (4, 5, 6), 0.7),      # weight groups only
+    (16, 16, 1, 2, (5, 4, 6), 1.5),     # deformable groups only (each half of the channels has its own sampling grid)
+    (32, 24, 2, 4, (4, 4, 5), 0.7),     # both, different counts
+    (16, 16, 4, 4, (3, 4, 4), 0.5),     # 4 channels per deformable group: one float4 per group
+])
+def test_deform_conv3d_backward_groups_vs_autograd_oracle(dl, oracle, C, Co, group, dgrp, dims, scale, math):
+    """group / deformable_group != 1 (deform_conv_cuda.cu:160-166, 204-270) against autograd through the oracle, whose FORWARD with
+    groups is first checked against the forward oracle (pinned to the compiled reference in tests/test_ref_d3d_gpu.py)."""
+    torch.manual_seed(32)
+    D, H, W = dims
+    x = torch.randn(2, C, D, H, W, requires_grad=True)
+    w = (torch.randn(Co, C // group, 3, 3, 3) * 0.2).requires_grad_()
+    b = torch.randn(Co, requires_grad=True)
+    off = (torch.randn(2, dgrp * 81, D, H, W) * scale).requires_grad_()
+    gout = torch.randn(2, Co, D, H, W)
+    ref = oracle.deform_conv3d_autograd(x, off, w, b, (1, 1, 1), (1, 1, 1), (1, 1, 1), group, dgrp)
+    with torch.no_grad():
+        fwd = oracle.deform_conv3d(x, off, w, b, 1, 1, 1, group, dgrp)
+    assert rel_err(ref.detach(), fwd) < 1e-5
+    ref.backward(gout)
+    gi, go, gw, gb = dl.ops.deform_conv3d_backward(x.detach().to(DEV), w.detach().to(DEV), b.detach().to(DEV), off.detach().to(DEV),
+                                                   gout.to(DEV), 3, 1, 1, 1, group, dgrp)
+    for name, got, want in (("grad_input", gi, x.grad), ("grad_offset", go, off.grad), ("grad_weight", gw, w.grad),
+                            ("grad_bias", gb, b.grad)):
+        assert got.shape == want.shape, name
+        assert rel_err(got, want) < TOL, name
+
+
+def test_deform_conv3d_backward_refuses_indivisible_groups(dl):
     x = torch.randn(1, 8, 3, 3, 3, device=DEV)
-    w = torch.randn(8, 4, 3, 3, 3, device=DEV)
+    w = torch.randn(9, 4, 3, 3, 3, device=DEV)   # 9 output channels in 2 groups
     with pytest.raises(RuntimeError):
-        dl.ops.deform_conv3d_backward(x, w, torch.zeros(8, device=DEV), torch.zeros(1, 81, 3, 3, 3, device=DEV),
-                                      torch.zeros(1, 8, 3, 3, 3, device=DEV), 3, 1, 1, 1, 2, 1)
+        dl.ops.deform_conv3d_backward(x, w, torch.zeros(9, device=DEV), torch.zeros(1, 81, 3, 3, 3, device=DEV),
+                                      torch.zeros(1, 9, 3, 3, 3, device=DEV), 3, 1, 1, 1, 2, 1)
 
 
 # ----------------------------------------------------------------------------- 1x1 projections at large M (generic kernel by

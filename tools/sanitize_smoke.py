@@ -10,7 +10,7 @@ import deformablelka_b200 as dl
 
 dev = "cuda:0"
 torch.manual_seed(0)
-for math in ("bf16x3", "fp32"):
+for math in os.environ.get("DLKA_SMOKE_MATH", "bf16x3,fp32").split(","):
     os.environ["DLKA_MATH"] = math
     with torch.no_grad():
         m3 = dl.LKA_Attention3d_deform(32)
@@ -41,5 +41,19 @@ for math in ("bf16x3", "fp32"):
         g = dl.ops.deform_conv3d_backward(x, torch.randn(32, 32, 3, 3, 3, device=dev), torch.randn(32, device=dev),   # N2
                                           torch.randn(1, 81, 5, 6, 7, device=dev) * 4, torch.randn(1, 32, 5, 6, 7, device=dev),
                                           3, 1, 1, 1, 1, 1)
+        # round-2 kernels: K-split offset conv + thread-per-voxel stencil (small grid, C = 64), persistent 1x1 streaming kernel
+        # (>= 2 tiles per SM), grouped 3D backward, 2D operator backward
+        m64 = dl.LKA_Attention3d_deform(64)
+        m64.spatial_gating_unit.deform_conv.conv_offset.bias.uniform_(-2, 2)
+        m64 = m64.to(dev)
+        y = m64(torch.randn(1, 8 * 8 * 8, 64, device=dev), 1, 64, 8, 8, 8)
+        y = dl.ops.linear_tokens_forward(torch.randn(40000, 32, device=dev), torch.randn(32, 32, device=dev), torch.randn(32, device=dev))
+        xg = torch.randn(1, 16, 4, 5, 6, device=dev)
+        g = dl.ops.deform_conv3d_backward(xg, torch.randn(16, 8, 3, 3, 3, device=dev), torch.randn(16, device=dev),
+                                          torch.randn(1, 2 * 81, 4, 5, 6, device=dev), torch.randn(1, 16, 4, 5, 6, device=dev),
+                                          3, 1, 1, 1, 2, 2)
+        x2 = torch.randn(1, 16, 9, 11, device=dev)
+        g = dl.ops.deform_conv2d_backward(x2, torch.randn(1, 50, 9, 11, device=dev), torch.randn(16, 1, 5, 5, device=dev), None,
+                                          torch.randn(1, 16, 9, 11, device=dev), padding=2)
     torch.cuda.synchronize()
     print("ok", math, flush=True)
