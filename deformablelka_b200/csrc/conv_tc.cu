@@ -30,12 +30,14 @@ using namespace ptx;
 
 constexpr int CT_CTRL_WARPS = 4;
 constexpr int CT_NPW = 8;          // producer / epilogue warps
-#ifndef DLKA_CT_SB
-#define DLKA_CT_SB 2
+#ifndef DLKA_CT_MTMAX
 #define DLKA_CT_MTMAX 2
 #define DLKA_CT_MINB 2
 #endif
-constexpr int CT_SB = DLKA_CT_SB;  // weight ring depth
+// weight ring depth (ConvTileArgs::sb): 2 when two CTAs share an SM (the other CTA hides the L2 latency of a weight tile), up to
+// CT_SB_MAX when the region buffers leave room for one CTA only (2D 7x7 dil 3: a 7 KB tile per tap from L2 for ~340 cycles of
+// MMAs -- with 2 slots in flight the loop ran at the copy latency, 3x under the tensor rate)
+constexpr int CT_SB_MAX = 6;
 constexpr int CT_KCH = 16;         // channels per K chunk (= one UMMA K step)
 constexpr int CT_LPAD = 64;        // bytes added to the plane stride (bank spread between the 2 planes)
 
@@ -57,6 +59,7 @@ struct ConvTileArgs {
     int RD, RH, RW;      // region extent (voxels)
     int tiles_d, tiles_h, tiles_w;  // CTA grid decomposition
     int lbo;             // plane stride in bytes = RV*16 + pad
+    int sb;              // weight ring depth, 2 .. CT_SB_MAX
     int csplit;          // > 0: grid.z slices of `csplit` K chunks; slice z writes to Y + z * ysplit (bias in slice 0 only)
     i64 ysplit;
 };
@@ -74,14 +77,15 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
     const int B_HALF = 2 * NT * 16, B_SLOT = 2 * B_HALF;
     uint8_t *sR = smem;
     uint8_t *sB = sR + 2 * R_BUF;
+    const int CT_SB = a.sb;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + CT_SB * B_SLOT);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 + 2 * CT_SB + 1);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 + 2 * CT_SB_MAX + 1);
     const uint32_t bar0 = smem_u32(bars);
     auto fullR = [&](int s) { return bar0 + 8u * s; };
     auto emptyR = [&](int s) { return bar0 + 8u * (2 + s); };
     auto fullB = [&](int s) { return bar0 + 8u * (4 + s); };
-    auto emptyB = [&](int s) { return bar0 + 8u * (4 + CT_SB + s); };
-    const uint32_t accFull = bar0 + 8u * (4 + 2 * CT_SB);
+    auto emptyB = [&](int s) { return bar0 + 8u * (4 + CT_SB_MAX + s); };
+    const uint32_t accFull = bar0 + 8u * (4 + 2 * CT_SB_MAX);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tile = blockIdx.y;
@@ -301,7 +305,7 @@ __global__ void pack_weight_ct_kernel(const float *__restrict__ w, const float *
 size_t ct_smem_bytes(const ConvTileArgs &a)
 {
     const size_t rbuf = (size_t)4 * a.lbo;  // hi+lo, 2 planes each
-    return 2 * rbuf + (size_t)CT_SB * 4 * a.NT * 16 + (4 + 2 * CT_SB + 1) * 8 + 16 + 128;
+    return 2 * rbuf + (size_t)a.sb * 4 * a.NT * 16 + (4 + 2 * CT_SB_MAX + 1) * 8 + 16 + 128;
 }
 
 bool ct_plan(const IgemmArgs &g, ConvTileArgs &a)
@@ -314,7 +318,7 @@ bool ct_plan(const IgemmArgs &g, ConvTileArgs &a)
     if (g.ybrick && geo.ndim != 3) return false;
     a.ybrick = g.ybrick; a.bt_d = (int)cdiv(geo.Do, 4); a.bt_h = (int)cdiv(geo.Ho, 4); a.bt_w = (int)cdiv(geo.Wo, 8);
     a.g = geo; a.X = g.X; a.xch = g.xch; a.bias = g.bias; a.Y = g.Y; a.ldY = g.ldY;
-    a.act = 0; a.slope = 0.f; a.E = nullptr; a.ldE = 0; a.csplit = 0; a.ysplit = 0;
+    a.act = 0; a.slope = 0.f; a.E = nullptr; a.ldE = 0; a.csplit = 0; a.ysplit = 0; a.sb = 2;
     a.NT = tc_nt(geo.Co);
     const bool is3d = geo.ndim == 3;
     for (int mt = DLKA_CT_MTMAX; mt >= 1; mt >>= 1) {
@@ -327,12 +331,20 @@ bool ct_plan(const IgemmArgs &g, ConvTileArgs &a)
         if (a.lbo / 16 >= (1 << 14) || a.RW * 16 / 16 >= (1 << 14)) continue;
         if (mt * a.NT > 512) continue;
         if (ct_smem_bytes(a) > 220 * 1024) continue;
-        // small problems: prefer fewer tiles per CTA so that the grid still fills the SMs
+        // small problems: prefer fewer tiles per CTA so that the grid still fills the SMs.  2D nets with large kernels (7x7 dil 3,
+        // C up to 384) are bound by streaming the weights from L2 -- every CTA walks the whole packed tensor, 7 KB per tap for 3
+        // MMAs -- so there two tiles per CTA (half the weight bytes per output) win as long as half the SMs get a CTA
         const i64 blocks = (i64)geo.B * (is3d ? cdiv(geo.Do, mt) * cdiv(geo.Ho, 16) : cdiv(geo.Ho, 16 * mt)) * cdiv(geo.Wo, 8);
-        if (mt > 1 && blocks < 148) continue;
+        if (mt > 1 && blocks < (is3d ? 148 : 74)) continue;
         a.tiles_d = is3d ? (int)cdiv(geo.Do, mt) : 1;
         a.tiles_h = is3d ? (int)cdiv(geo.Ho, 16) : (int)cdiv(geo.Ho, 16 * mt);
         a.tiles_w = (int)cdiv(geo.Wo, 8);
+        // one CTA per SM anyway (> half the shared memory): deepen the weight ring as far as it fits
+        if (ct_smem_bytes(a) > 113 * 1024)
+            while (a.sb < CT_SB_MAX) {
+                ++a.sb;
+                if (ct_smem_bytes(a) > 220 * 1024) { --a.sb; break; }
+            }
         return true;
     }
     return false;

@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) deform3d_ps_kernel(const Deform
             if (a.chain) tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(a.chain ? barE1 : accEmpty(buf));   // no chain: buffer and row table are free again
+            if (lane == 0) mbar_arrive(a.chain ? barE1 : accEmpty(buf));   // no chain: the accumulator buffer is free again
             if (!a.chain) continue;
             // ---- stage 1: conv1 + bias, gate with U ----
             mbar_wait_sleep(barC1, (uint32_t)i & 1u);

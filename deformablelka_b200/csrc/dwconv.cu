@@ -163,6 +163,77 @@ __global__ void __launch_bounds__(256) deform_dwconv_cl_kernel(const float *__re
     }
 }
 
+// 2D depthwise deformable conv with SHARED sampling parameters: in the kernel above every thread of a pixel (C/4 of them) re-derives
+// the same sampling position, validity and bilinear weights for every tap -- more instructions than the gather and the blend
+// themselves.  Here a block owns PB consecutive pixels: phase 1 computes one 32-byte record per (pixel, offset group, tap)
+// {4 clamped corner offsets, 4 corner weights with validity and the DCNv2 mask folded in} into shared memory (rules of
+// torchvision's bilinear_interpolate through make_sample2), phase 2 runs thread = (pixel, 4 channels) over the taps with two
+// broadcast LDS.128, four LDG.128 and the blend.
+__global__ void __launch_bounds__(256) deform_dwconv2d_shared_kernel(const float *__restrict__ x, const float *__restrict__ off,
+                                                                     const float *__restrict__ mask, const float *__restrict__ wp,
+                                                                     const float *__restrict__ bias, float *__restrict__ y,
+                                                                     const ConvGeo g, i64 M, int PB)
+{
+    extern __shared__ __align__(16) uint8_t dsm[];
+    const int K = g.K, dg = g.dg, C = g.C, C4 = C / 4, cpg = C / dg;
+    const int nrec = PB * dg * K;
+    int4 *sO = reinterpret_cast<int4 *>(dsm);
+    float4 *sW = reinterpret_cast<float4 *>(dsm) + nrec;
+    const i64 ngroups = (M + PB - 1) / PB;
+    for (i64 grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const i64 m0 = grp * PB;
+        for (int e = threadIdx.x; e < nrec; e += blockDim.x) {
+            const int tap = e % K, dgi = (e / K) % dg, p = e / (K * dg);
+            const i64 m = m0 + p;
+            int4 o = make_int4(0, 0, 0, 0);
+            float4 w = f4zero();
+            if (m < M) {
+                const int wo = (int)(m % g.Wo), ho = (int)((m / g.Wo) % g.Ho);
+                const int kk = tap % g.kw, jj = tap / g.kw;
+                const float *op = off + m * (i64)(dg * 2 * K) + ((i64)dgi * K + tap) * 2;
+                const float ph = sample_pos(ho, g.sh, g.ph, jj, g.dh, __ldg(op));
+                const float pw = sample_pos(wo, g.sw, g.pw, kk, g.dw, __ldg(op + 1));
+                const Sample2 sm = make_sample2(ph, pw, g.H, g.W);
+                if (sm.mask & 1) {
+                    const float lh = sm.l[0], lw = sm.l[1], hh = 1.f - lh, hw = 1.f - lw;
+                    const float mk = mask ? __ldg(mask + m * (i64)(dg * K) + dgi * K + tap) : 1.f;
+                    w.x = (sm.mask & (1 << 1)) ? hh * hw * mk : 0.f;
+                    w.y = (sm.mask & (1 << 2)) ? hh * lw * mk : 0.f;
+                    w.z = (sm.mask & (1 << 3)) ? lh * hw * mk : 0.f;
+                    w.w = (sm.mask & (1 << 4)) ? lh * lw * mk : 0.f;
+                    const int h0 = max(sm.lo[0], 0), h1 = min(sm.lo[0] + 1, g.H - 1), w0 = max(sm.lo[1], 0), w1 = min(sm.lo[1] + 1, g.W - 1);
+                    o.x = (h0 * g.W + w0) * C; o.y = (h0 * g.W + w1) * C; o.z = (h1 * g.W + w0) * C; o.w = (h1 * g.W + w1) * C;
+                }
+            }
+            sO[e] = o;
+            sW[e] = w;
+        }
+        __syncthreads();
+        for (int item = threadIdx.x; item < PB * C4; item += blockDim.x) {
+            const int p = item / C4, c = (item % C4) * 4;
+            const i64 m = m0 + p;
+            if (m >= M) continue;
+            const int b = (int)(m / ((i64)g.Ho * g.Wo));
+            const float *img = x + (i64)b * g.H * g.W * C + c;
+            const int r0 = (p * dg + c / cpg) * K;
+            float4 acc = bias ? ldg4(bias + c) : f4zero();
+#pragma unroll 2
+            for (int tap = 0; tap < K; ++tap) {
+                const int4 o = sO[r0 + tap];
+                const float4 w = sW[r0 + tap];
+                const float4 v0 = ldg4(img + o.x), v1 = ldg4(img + o.y), v2 = ldg4(img + o.z), v3 = ldg4(img + o.w);
+                float4 v = f4zero();
+                fma4(v, w.x, v0); fma4(v, w.y, v1); fma4(v, w.z, v2); fma4(v, w.w, v3);
+                const float4 wv = ldg4(wp + (i64)tap * C + c);
+                acc.x = fmaf(wv.x, v.x, acc.x); acc.y = fmaf(wv.y, v.y, acc.y);
+                acc.z = fmaf(wv.z, v.z, acc.z); acc.w = fmaf(wv.w, v.w, acc.w);
+            }
+            *reinterpret_cast<float4 *>(y + m * (i64)C + c) = acc;
+        }
+        __syncthreads();   // the records are rewritten by the next pixel group
+    }
+}
+
 int pack_dw(const float *w, float *wp, int C, int taps, cudaStream_t st)
 {
     if (pack_skipped()) return DLKA_OK;   // prepacked weights: see PackSkipScope
@@ -224,10 +295,27 @@ int deform_dwconv_cl(const float *x, const float *off, const float *mask, const 
     const i64 total = M * (g.C / 4);
     if (total <= 0) return DLKA_OK;
     const int blocks = (int)(cdiv(total, 256) < 148 * 32 ? cdiv(total, 256) : 148 * 32);
-    if (g.ndim == 3)
+    if (g.ndim == 3) {
         DLKA_LAUNCH("deform_dwconv3d", st, deform_dwconv_cl_kernel<3><<<blocks, 256, 0, st>>>(x, off, mask, w_packed, bias, y, g, M));
-    else
-        DLKA_LAUNCH("deform_dwconv2d", st, deform_dwconv_cl_kernel<2><<<blocks, 256, 0, st>>>(x, off, mask, w_packed, bias, y, g, M));
+        return DLKA_OK;
+    }
+    // shared-parameter kernel: pixels per block chosen so that (PB * C/4) fills whole rounds of 256 threads where possible and the
+    // grid still has ~4 blocks per SM; records must fit the (opt-in) shared memory and image offsets 32 bits
+    const int C4 = g.C / 4;
+    int PB = 16;
+    if ((16 * C4) % 256 != 0 && (32 * C4) % 256 == 0 && M / 32 >= 4 * 148) PB = 32;
+    while (PB > 4 && M / PB < 4 * 148) PB >>= 1;
+    const size_t smem = (size_t)PB * g.dg * g.K * 32;
+    if (smem <= 96 * 1024 && (i64)g.H * g.W * g.C < ((i64)1 << 31)) {
+        static SmemOptIn optin;
+        DLKA_TRY(optin.ensure(deform_dwconv2d_shared_kernel, smem));
+        const i64 ngroups = cdiv(M, (i64)PB);
+        const int nb = (int)(ngroups < 148 * 16 ? ngroups : 148 * 16);
+        DLKA_LAUNCH("deform_dwconv2d", st,
+                    deform_dwconv2d_shared_kernel<<<nb, 256, smem, st>>>(x, off, mask, w_packed, bias, y, g, M, PB));
+        return DLKA_OK;
+    }
+    DLKA_LAUNCH("deform_dwconv2d", st, deform_dwconv_cl_kernel<2><<<blocks, 256, 0, st>>>(x, off, mask, w_packed, bias, y, g, M));
     return DLKA_OK;
 }
 
