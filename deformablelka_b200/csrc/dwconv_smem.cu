@@ -221,10 +221,17 @@ bool dwconv_smem_supported(int C, int kd, int kh, int kw, int dd, int dh, int dw
 int dwconv_smem(const float *x, const float *wp, const float *bias, float *y, int B, int C, int D, int H, int W, int kd, int k,
                 int dd, int dil, cudaStream_t st, bool cm)
 {
-    if (kd == 5 && k == 5 && dd == 1 && dil == 1)
+    if (kd == 5 && k == 5 && dd == 1 && dil == 1) {
+        // mid-size volumes (32^3 stage of the 3D nets): with 4 output planes per CTA the grid is under half a wave
+        const i64 ctas = cdiv(D, DLKA_DS5_TD) * cdiv(H, DLKA_DS5_TH) * cdiv(W, DLKA_DS5_TW) * (C / DS_CCH) * B;
+        if (ctas < 148) return launch_ds<5, 5, 1, 1, 2, DLKA_DS5_TH, DLKA_DS5_TW, DLKA_DS5_R, DLKA_DS5_VW>(x, wp, bias, y, B, C, D, H, W, st, cm);
         return launch_ds<5, 5, 1, 1, DLKA_DS5_TD, DLKA_DS5_TH, DLKA_DS5_TW, DLKA_DS5_R, DLKA_DS5_VW>(x, wp, bias, y, B, C, D, H, W, st, cm);
-    if (kd == 7 && k == 7 && dd == 3 && dil == 3)
+    }
+    if (kd == 7 && k == 7 && dd == 3 && dil == 3) {
+        // sub-lattices of at most 12 x 12 (volumes up to 36 wide): an 11 x 12 tile instead of 15 x 22 (2.5x fewer lanes per CTA)
+        if (cdiv(H, 3) <= 11 && cdiv(W, 3) <= 12) return launch_ds<7, 7, 3, 3, 2, 11, 12, 6, 2>(x, wp, bias, y, B, C, D, H, W, st, cm);
         return launch_ds<7, 7, 3, 3, DLKA_DS7_TD, DLKA_DS7_TH, DLKA_DS7_TW, DLKA_DS7_R, DLKA_DS7_VW>(x, wp, bias, y, B, C, D, H, W, st, cm);
+    }
     if (kd == 5 && k == 7 && dd == 3 && dil == 3) return launch_ds<5, 7, 3, 3, 2, 15, 22, 11, 2>(x, wp, bias, y, B, C, D, H, W, st, cm);
     if (kd == 3 && k == 5 && dd == 1 && dil == 3) return launch_ds<3, 5, 1, 3, 4, 16, 16, 8, 2>(x, wp, bias, y, B, C, D, H, W, st, cm);
     if (kd == 3 && k == 3 && dd == 1 && dil == 1) return launch_ds<3, 3, 1, 1, 4, 16, 16, 8, 2>(x, wp, bias, y, B, C, D, H, W, st, cm);
