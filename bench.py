@@ -103,6 +103,24 @@ C4_BLOCKS = ((32, 32, 6), (64, 16, 6), (128, 8, 6), (256, 4, 3))   # (C, cube ed
 C2_BLOCKS = ((384, 14), (192, 28), (96, 56))                          # (C, H = W) of the 2D net's decoder blocks at batch 24
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner on rank 0) are sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
 def _time_call(fn, iters=20, warm=5):
     for _ in range(warm):
         fn()
@@ -197,7 +215,7 @@ def run_c4net(args, dl, dev, world, rank):
         ms = max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
         launches = dl.launch_count() - n0
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": "3D D-LKA Net, D-LKA block path fwd (21 blocks), patches/s @ batch 2 per GPU", "value": 2 * world / (ms * 1e-3),
             "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -277,7 +295,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "GVoxel/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "GVoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 def main():
@@ -295,6 +313,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -495,7 +514,7 @@ def main():
         v, t, sample = cpu_reference_sample(C, threads)
         out["cpu_baseline"] = {"value": v, "unit": "GVoxel/s", "cores": threads, "kind": "port", "sample": sample,
                                "seconds": t}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 

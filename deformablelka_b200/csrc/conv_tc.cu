@@ -20,6 +20,8 @@
 #include <atomic>
 #include <mutex>
 
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
 
@@ -34,7 +36,8 @@ constexpr int CT_NPW = 8;          // producer / epilogue warps
 #define DLKA_CT_MTMAX 2
 #define DLKA_CT_MINB 2
 #endif
-// weight ring depth (ConvTileArgs::sb): 2 when two CTAs share an SM (the other CTA hides the L2 latency of a weight tile), up to
+// weight ring depth (ConvTileArgs::sb): 3 when two CTAs share an SM and it still fits half the shared memory (headline conv_offset:
+// 2 -> 3 slots took it from 2.39 to 2.19 ms -- a 6 KB tile per tap from L2 against ~290 cycles of MMAs), else 2; up to
 // CT_SB_MAX when the region buffers leave room for one CTA only (2D 7x7 dil 3: a 7 KB tile per tap from L2 for ~340 cycles of
 // MMAs -- with 2 slots in flight the loop ran at the copy latency, 3x under the tensor rate)
 constexpr int CT_SB_MAX = 6;
@@ -121,18 +124,18 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(128, NT);
             const uint32_t sbo = (uint32_t)a.RW * 16u;
-            int bi = 0;  // running weight-tile index
+            int bs = 0;           // weight ring slot and its phase bit (running counters: the ring depth is a runtime value)
+            uint32_t bph = 0;
             for (int c = 0; c < nchunks; ++c) {
                 const int rb = c & 1;
                 mbar_wait(fullR(rb), (c >> 1) & 1);
                 tc_fence_after();
                 const uint32_t rhi = smem_u32(sR + rb * R_BUF), rlo = rhi + R_HALF;
-                for (int tap = 0; tap < K; ++tap, ++bi) {
-                    const int bs = bi % CT_SB;
-                    mbar_wait(fullB(bs), (bi / CT_SB) & 1);
+                int kk = 0, jj = 0, ii = 0;   // tap = (ii * kh + jj) * kw + kk, kept as counters (no divisions on the issue path)
+                for (int tap = 0; tap < K; ++tap) {
+                    mbar_wait(fullB(bs), bph);
                     tc_fence_after();
                     const uint32_t bhi = smem_u32(sB + bs * B_SLOT), blo = bhi + B_HALF;
-                    const int kk = tap % g.kw, jj = (tap / g.kw) % g.kh, ii = tap / (g.kw * g.kh);
                     const uint64_t bd_hi = make_smem_desc(bhi, NT * 16, 128), bd_lo = make_smem_desc(blo, NT * 16, 128);
 #pragma unroll
                     for (int t = 0; t < MT; ++t) {
@@ -147,6 +150,8 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
                         umma_bf16(d_tmem, ad_hi, bd_lo, idesc, 1u);
                     }
                     umma_commit(emptyB(bs));
+                    if (++bs == CT_SB) { bs = 0; bph ^= 1u; }
+                    if (++kk == g.kw) { kk = 0; if (++jj == g.kh) { jj = 0; ++ii; } }
                 }
                 umma_commit(emptyR(rb));
             }
@@ -157,11 +162,13 @@ __global__ void __launch_bounds__((CT_CTRL_WARPS + CT_NPW) * 32, DLKA_CT_MINB) c
         if (elect_one()) {
             const int total = nchunks * K;
             const uint8_t *src = a.Bp + ((i64)n_tile * nchunks_all + chunk0) * K * B_SLOT;
+            int bs = 0;
+            uint32_t bph = 1;   // emptyB starts "free"
             for (int bi = 0; bi < total; ++bi) {
-                const int bs = bi % CT_SB;
-                mbar_wait(emptyB(bs), ((bi / CT_SB) & 1) ^ 1);
+                mbar_wait(emptyB(bs), bph);
                 mbar_arrive_expect_tx(fullB(bs), (uint32_t)B_SLOT);
                 bulk_g2s(smem_u32(sB + bs * B_SLOT), src + (i64)bi * B_SLOT, (uint32_t)B_SLOT, fullB(bs));
+                if (++bs == CT_SB) { bs = 0; bph ^= 1u; }
             }
         }
     } else if (warp >= CT_CTRL_WARPS) {
@@ -321,7 +328,10 @@ bool ct_plan(const IgemmArgs &g, ConvTileArgs &a)
     a.act = 0; a.slope = 0.f; a.E = nullptr; a.ldE = 0; a.csplit = 0; a.ysplit = 0; a.sb = 2;
     a.NT = tc_nt(geo.Co);
     const bool is3d = geo.ndim == 3;
-    for (int mt = DLKA_CT_MTMAX; mt >= 1; mt >>= 1) {
+    // tuning knobs (environment, read once): DLKA_CT_MT = largest MT tried, DLKA_CT_SB = ring depth when two CTAs share an SM
+    static const int env_mt = [] { const char *e = getenv("DLKA_CT_MT"); return e ? atoi(e) : DLKA_CT_MTMAX; }();
+    static const int env_sb = [] { const char *e = getenv("DLKA_CT_SB"); return e ? atoi(e) : 3; }();
+    for (int mt = env_mt; mt >= 1; mt >>= 1) {
         a.MT = mt;
         a.RD = is3d ? mt + (geo.kd - 1) * geo.dd : 1;
         a.RH = (is3d ? 16 : 16 * mt) + (geo.kh - 1) * geo.dh;
@@ -340,11 +350,17 @@ bool ct_plan(const IgemmArgs &g, ConvTileArgs &a)
         a.tiles_h = is3d ? (int)cdiv(geo.Ho, 16) : (int)cdiv(geo.Ho, 16 * mt);
         a.tiles_w = (int)cdiv(geo.Wo, 8);
         // one CTA per SM anyway (> half the shared memory): deepen the weight ring as far as it fits
-        if (ct_smem_bytes(a) > 113 * 1024)
+        if (ct_smem_bytes(a) > 112 * 1024) {
             while (a.sb < CT_SB_MAX) {
                 ++a.sb;
                 if (ct_smem_bytes(a) > 220 * 1024) { --a.sb; break; }
             }
+        } else {
+            while (a.sb < env_sb) {
+                ++a.sb;
+                if (ct_smem_bytes(a) > 112 * 1024) { --a.sb; break; }
+            }
+        }
         return true;
     }
     return false;
