@@ -144,6 +144,9 @@ def other_configs(dl, dev):
             m = dl.deformable_LKA_Attention(C).to(dev).eval()
             x = torch.randn(24, C, hw, hw, device=dev)
             out[f"c2_block2d_24x{C}x{hw}x{hw}_ms"] = _time_call(lambda: m(x))
+            g = dl.GraphedCall(m, x)            # same call replayed as one CUDA graph (host launch path out of the way)
+            out[f"c2_block2d_24x{C}x{hw}x{hw}_graph_ms"] = _time_call(lambda: g(x))
+            del g
         torch.manual_seed(1234)
         B, C, D, H, W = 2, 64, 32, 64, 64
         x = torch.randn(B, C, D, H, W, device=dev); w = torch.randn(C, C, 3, 3, 3, device=dev) * 0.05
@@ -154,6 +157,9 @@ def other_configs(dl, dev):
             m = make_block(C, dev)
             x = torch.randn(2, s * s * s, C, device=dev)
             out[f"c4_block3d_2x{C}x{s}x{s}x{s}_ms"] = _time_call(lambda: m(x, 2, C, s, s, s))
+            g = dl.GraphedCall(m, x, 2, C, s, s, s)
+            out[f"c4_block3d_2x{C}x{s}x{s}x{s}_graph_ms"] = _time_call(lambda: g(x, 2, C, s, s, s))
+            del g
     return out
 
 
@@ -198,29 +204,45 @@ def run_c4net(args, dl, dev, world, rank):
                 for _ in range(n):
                     m(x, 2, C, s, s, s)
 
+        n_a = dl.launch_count()
         for _ in range(args.warmup):
             step()
+        launches_per_step = (dl.launch_count() - n_a) // max(args.warmup, 1)
         torch.cuda.synchronize()
+        run = step
+        if not args.no_graph:   # the 21 calls of a step recorded ONCE as a CUDA graph; every timed step replays the same kernels
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            run = graph.replay
+            run()
+            torch.cuda.synchronize()
         if world > 1:
             import torch.distributed as dist
             dist.barrier()
             torch.cuda.synchronize()
-        n0 = dl.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            step()
+            run()
         e1.record()
         torch.cuda.synchronize()
         ms = max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
-        launches = dl.launch_count() - n0
+        launches = launches_per_step * args.steps   # kernels executed in the timed region (replayed from the graph when graphed)
     if rank == 0:
         emit(({
             "metric": "3D D-LKA Net, D-LKA block path fwd (21 blocks), patches/s @ batch 2 per GPU", "value": 2 * world / (ms * 1e-3),
             "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[3]/[4]: LKA_Attention3d_deform at the 21 block shapes of the 3D net, 64x128x128 patches",
-                       "blocks": [list(b) for b in C4_BLOCKS], "math": args.math, "parallelism": f"dp{world}"},
+                       "blocks": [list(b) for b in C4_BLOCKS], "math": args.math, "parallelism": f"dp{world}",
+                       "launch": "eager" if args.no_graph else "cuda_graph (one graph per step)"},
             "gpu_launches": int(launches)}))
 
 
@@ -309,6 +331,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--config", default="headline", choices=["headline", "c4net"], help="c4net: BASELINE configs[3] / [4] (block path)")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="c4net: launch the 21 block calls eagerly instead of replaying one CUDA graph")
     ap.add_argument("--no-profile-pass", action="store_true", help="skip the per-kernel event pass (tools/measure_traffic.py)")
     args = ap.parse_args()
     if args.warmup < 3:

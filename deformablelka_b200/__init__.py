@@ -9,6 +9,7 @@ from ._lib import LIB_PATH, launch_count  # noqa: F401
 from .deform_conv3d import DeformConv as DeformConv3d, DeformConvFunction, DeformConvPack  # noqa: F401
 from .deformable_LKA import DeformConv, DeformConv2d, deformable_LKA, deformable_LKA_Attention  # noqa: F401
 from .lka3d import LKA3d_deform, LKA_Attention3d_deform  # noqa: F401
+from .graphs import GraphedCall  # noqa: F401  (CUDA-graph replay of an inference call)
 from . import acdc, sliding_window  # noqa: F401  (ACDC variant of the 3D block: acdc.LKA3d_deform, acdc.LKA_Attention3d_deform)
 from .blocks import (DWConvLKA, FinalPatchExpand_X4, Mlp, MyDecoderLayer, PatchExpand,  # noqa: F401
                      TransformerBlock_3D_single_deform_LKA, deformableLKABlock)
@@ -16,5 +17,5 @@ from .blocks import (DWConvLKA, FinalPatchExpand_X4, Mlp, MyDecoderLayer, PatchE
 __all__ = [
     "ops", "DeformConv", "DeformConv2d", "deformable_LKA", "deformable_LKA_Attention",
     "DeformConv3d", "DeformConvFunction", "DeformConvPack", "LKA3d_deform", "LKA_Attention3d_deform",
-    "deformableLKABlock", "Mlp", "DWConvLKA", "TransformerBlock_3D_single_deform_LKA", "launch_count", "LIB_PATH",
+    "deformableLKABlock", "Mlp", "DWConvLKA", "TransformerBlock_3D_single_deform_LKA", "launch_count", "LIB_PATH", "GraphedCall",
 ]
