@@ -36,7 +36,11 @@ namespace {
 #ifndef DLKA_DS7_VW
 #define DLKA_DS7_VW 2
 #endif
-constexpr int DS_CCH = 32;                                     // channels per CTA
+#ifndef DLKA_DS_CCH
+#define DLKA_DS_CCH 32
+#endif
+constexpr int DS_CCH = DLKA_DS_CCH;                            // channels per CTA (32, or 16: half the shared memory, two CTAs per SM)
+static_assert(DS_CCH == 32 || DS_CCH == 16, "channels per CTA");
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid)
 {
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
     }
     // weights of the chunk -> smem ([tap][C] packed layout in global: 128 contiguous bytes per tap)
     for (int i = tid; i < KD * K * K * (DS_CCH / 4); i += DS_THREADS) {
-        const int tap = i >> 3, qq = i & 7;
+        const int tap = i / (DS_CCH / 4), qq = i % (DS_CCH / 4);
         cp_async16(sW + i, wp + (i64)tap * C + c0 + qq * 4, true);
     }
     cp_async_commit();
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
             for (int r = 0; r < DS_R; ++r) {
                 const int wrr = pw_ + L * (zw0 + wr * DS_R + r);
                 if (wrr < W)
-                    *reinterpret_cast<vec *>(y + (i64)chunk * ych + ((((i64)b * D + dr) * H + hr) * W + wrr) * yldv + q * VW) = acc[t][r];
+                    *reinterpret_cast<vec *>(y + (i64)(c0 >> 5) * ych + ((((i64)b * D + dr) * H + hr) * W + wrr) * yldv + (c0 & 31) + q * VW) = acc[t][r];
             }
         }
     }
@@ -184,12 +188,12 @@ int launch_ds(const float *x, const float *wp, const float *bias, float *y, int 
 {
     // output addressing: y + chunk * ych + voxel * yldv + channel-in-chunk.  channels-last: ych = 32, yldv = C;
     // chunk-major [C/32][B][D][H][W][32] (the gather layout of deform_ps.cu): ych = B*D*H*W*32, yldv = 32
-    const i64 ych = cm ? (i64)B * D * H * W * DS_CCH : DS_CCH;
-    const int yldv = cm ? DS_CCH : C;
+    const i64 ych = cm ? (i64)B * D * H * W * 32 : 32;   // the chunk-major layout is defined on 32-channel chunks whatever DS_CCH is
+    const int yldv = cm ? 32 : C;
     constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;
     constexpr int DS_THREADS = (DS_CCH / VW) * (DS_TW / DS_R) * DS_TH;
     static_assert(PW * L <= 256 && PH * L <= 256, "TMA box extent");
-    const size_t smem = ((size_t)KD * K * K * 8 + 2 * (size_t)PH * PW * 8) * sizeof(float4) + 64;
+    const size_t smem = ((size_t)KD * K * K * (DS_CCH / 4) + 2 * (size_t)PH * PW * (DS_CCH / 4)) * sizeof(float4) + 64;
     auto kern = dwconv_smem_kernel<KD, K, LD, L, DS_TD, DS_TH, DS_TW, DS_R, VW>;
     static SmemOptIn optin;   // per template instance, per device
     DLKA_TRY(optin.ensure(kern, smem));
