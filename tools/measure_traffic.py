@@ -45,7 +45,7 @@ def main():
     os.makedirs(os.path.dirname(out_csv), exist_ok=True)
     cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
            "--csv", "--log-file", out_csv, sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3",
-           "--no-e2e", "--no-cpu-baseline", "--no-profile-pass"]
+           "--no-e2e", "--no-cpu-baseline", "--no-profile-pass", "--no-other-configs"]
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
     rows = [r for r in csv.reader(open(out_csv)) if len(r) > 10]
     hdr = rows[0]
