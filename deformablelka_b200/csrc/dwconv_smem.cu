@@ -16,8 +16,8 @@ namespace dlka {
 namespace {
 
 // tile shapes per stencil (lattice voxels): TD x TH x TW outputs per CTA, R outputs along w per thread.
-// 5^3:    D,H,W = 64,128,128 divide evenly.  7^3 dil 3: the sub-lattices of the headline volume are 22 x 43 x 43, so
-// 15 x 22 tiles (3 x 2 per plane) waste 7 % of the lanes where 16 x 16 wasted 20 %.
+// 5^3:    D,H,W = 64,128,128 divide evenly (TH = 8 variants with 6 / 8 output planes measured 1.52-1.55 ms against 1.22).
+// 7^3 dil 3: the sub-lattices of the headline volume are 22 x 43 x 43: 11 x 22 tiles waste 5 % of the lanes (16 x 16: 20 %).
 #ifndef DLKA_DS5_TD
 #define DLKA_DS5_TD 4
 #define DLKA_DS5_TH 16
@@ -28,13 +28,16 @@ namespace {
 #define DLKA_DS5_VW 2   // channels per thread (4: float4, 8 lanes per voxel; 2: float2, 16 lanes per voxel)
 #endif
 #ifndef DLKA_DS7_TD
-#define DLKA_DS7_TD 2
-#define DLKA_DS7_TH 15
-#define DLKA_DS7_TW 22
-#define DLKA_DS7_R 11
+#define DLKA_DS7_TD 4    // 4 output planes per CTA (10 input planes / 4 outputs instead of 8 / 2: fewer plane hand-offs per output);
+#define DLKA_DS7_TH 11   // 11 x 22 tiles = 4 x 2 per 43 x 43 sub-lattice plane, 352 threads.  Measured at the headline shape:
+#define DLKA_DS7_TW 22   // (2,15,22) 3.23 ms, (3,15,22) 3.19, (4,11,22) 3.17, (5,9,22) 3.83; the ragged last d-tile costs nothing
+#define DLKA_DS7_R 11    // (td_here in the kernel)
 #endif
 #ifndef DLKA_DS7_VW
 #define DLKA_DS7_VW 2
+#endif
+#ifndef DLKA_DS_SPLITBAR
+#define DLKA_DS_SPLITBAR 1
 #endif
 #ifndef DLKA_DS_CCH
 #define DLKA_DS_CCH 32
@@ -65,6 +68,16 @@ template <> struct DsVec<2> {
     static __device__ __forceinline__ void fma(T &a, const T &w, const T &x) { fma2v(a, w, x); }
 };
 
+// plane buffers per CTA: two; -DDLKA_DS_NBUF3 takes three when they fit beside the weights (measured no better: 3.14 vs 3.09 ms)
+__host__ __device__ constexpr int ds_nbuf(int KD, int K, int TH, int TW)
+{
+#if DLKA_DS_SPLITBAR && DLKA_DS_NBUF3
+    return ((size_t)3 * (TH + K - 1) * (TW + K - 1) * (DS_CCH / 4) + (size_t)KD * K * K * (DS_CCH / 4)) * 16 + 64 <= (size_t)227 * 1024 - 1024 ? 3 : 2;
+#else
+    return 2;
+#endif
+}
+
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -82,9 +95,10 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
     constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;   // plane extent (lattice voxels)
     constexpr int PLANE_F4 = PH * PW * (DS_CCH / 4);         // float4 elements per plane (128 B per voxel)
     constexpr int NPLANES = DS_TD + KD - 1;
+    constexpr int NBUF = ds_nbuf(KD, K, DS_TH, DS_TW);       // plane buffers
     extern __shared__ __align__(128) float4 smem4[];
     float4 *sP = smem4;                                      // [2][PH][PW][8] float4 (TMA destination, 128-byte aligned)
-    float4 *sW = sP + 2 * PLANE_F4;                          // [KD*K*K][8] float4 : weights of this channel chunk
+    float4 *sW = sP + NBUF * PLANE_F4;                       // [KD*K*K][8] float4 : weights of this channel chunk
     uint64_t *bars = reinterpret_cast<uint64_t *>(sW + KD * K * K * (DS_CCH / 4));   // one per plane buffer
 
     const int tid = threadIdx.x;
@@ -101,11 +115,17 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
     const int b = blockIdx.z;
     const int c0 = chunk * DS_CCH;
     const int zd0 = td * DS_TD, zh0 = th * DS_TH, zw0 = tw * DS_TW;   // lattice tile origin
+    // ragged last d-tile: only td_here of the DS_TD output planes exist on this phase's sub-lattice, so the plane loop stops
+    // early and the FMA blocks of the missing outputs are skipped (CTA-uniform branches): no wasted work when DS_TD does not
+    // divide the lattice depth
+    const int ld_phase = (D - pd_ + LD - 1) / LD;
+    const int td_here = ld_phase - zd0 < DS_TD ? ld_phase - zd0 : DS_TD;
+    const int nplanes = td_here + KD - 1;
+    if (td_here <= 0) return;   // nothing issued yet: the whole CTA leaves
 
     const uint32_t bar0 = ptx::smem_u32(bars);
     if (tid == 0) {
-        ptx::mbar_init(bar0, 1);
-        ptx::mbar_init(bar0 + 8u, 1);
+        for (int i = 0; i < NBUF; ++i) ptx::mbar_init(bar0 + 8u * i, 1);
         ptx::fence_barrier_init();
     }
     // weights of the chunk -> smem ([tap][C] packed layout in global: 128 contiguous bytes per tap)
@@ -133,14 +153,28 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
             for (int r = 0; r < DS_R; ++r) acc[t][r] = bv;
     }
 
+#if DLKA_DS_SPLITBAR
+    if (tid == 0)
+        for (int i = 0; i < NBUF && i < nplanes; ++i) load_plane(i, i);
+#else
     if (tid == 0) load_plane(0, 0);
+#endif
     cp_async_wait<0>();
     __syncthreads();   // weights landed
 #pragma unroll 1
-    for (int s = 0; s < NPLANES; ++s) {
-        if (tid == 0 && s + 1 < NPLANES) load_plane(s + 1, (s + 1) & 1);   // that buffer was released by the barrier below
-        ptx::mbar_wait(bar0 + 8u * (s & 1), (s >> 1) & 1);
-        const vec *pl = reinterpret_cast<const vec *>(sP + (s & 1) * PLANE_F4);
+    for (int s = 0; s < nplanes; ++s) {
+#if !DLKA_DS_SPLITBAR
+        if (tid == 0 && s + 1 < nplanes) load_plane(s + 1, (s + 1) & 1);   // that buffer was released by the barrier below
+#endif
+#if DLKA_DS_SPLITBAR
+        const int buf = s % NBUF;
+        const uint32_t bph = (uint32_t)(s / NBUF) & 1u;
+#else
+        const int buf = s & 1;
+        const uint32_t bph = (uint32_t)(s >> 1) & 1u;
+#endif
+        ptx::mbar_wait(bar0 + 8u * buf, bph);
+        const vec *pl = reinterpret_cast<const vec *>(sP + buf * PLANE_F4);
         // plane s contributes to output t with depth tap i = s - t
 #pragma unroll
         for (int j = 0; j < K; ++j) {
@@ -151,7 +185,7 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
 #pragma unroll
             for (int t = 0; t < DS_TD; ++t) {
                 const int i = s - t;
-                if (i < 0 || i >= KD) continue;  // uniform across the CTA
+                if (i < 0 || i >= KD || t >= td_here) continue;  // uniform across the CTA
                 const vec *wrow = reinterpret_cast<const vec *>(sW) + ((i * K + j) * K) * LPV + q;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
@@ -161,9 +195,25 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
                 }
             }
         }
+#if DLKA_DS_SPLITBAR
+        // split hand-off: only the warp that refills buffer `buf` with plane s + NBUF waits until every warp has finished reading
+        // plane s (named barrier 1 + buf: bar.sync by warp 0, bar.arrive by the others, who run on into the planes already
+        // resident).  A warp can arrive for plane s + NBUF on the same barrier only after that plane's TMA, which follows this
+        // bar.sync.  (3.16 -> 3.09 ms and 1.22 -> 1.16 ms with two buffers against the CTA-wide barrier.)
+        if (s + NBUF < nplanes) {
+            const int id = 1 + buf;
+            if (tid < 32) {
+                asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(DS_THREADS) : "memory");
+                if (tid == 0) load_plane(s + NBUF, buf);
+            } else {
+                asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(DS_THREADS) : "memory");
+            }
+        }
+#else
         // everyone is done reading plane buffer (s & 1): it is refilled at the top of the next iteration.  (Per-warp
         // "empty" mbarriers instead of this CTA barrier measured slower: 3.77 vs 3.66 ms and 1.52 vs 1.28 ms.)
         __syncthreads();
+#endif
     }
 
     // store: real coordinates of this thread's outputs
@@ -193,7 +243,7 @@ int launch_ds(const float *x, const float *wp, const float *bias, float *y, int 
     constexpr int PH = DS_TH + K - 1, PW = DS_TW + K - 1;
     constexpr int DS_THREADS = (DS_CCH / VW) * (DS_TW / DS_R) * DS_TH;
     static_assert(PW * L <= 256 && PH * L <= 256, "TMA box extent");
-    const size_t smem = ((size_t)KD * K * K * (DS_CCH / 4) + 2 * (size_t)PH * PW * (DS_CCH / 4)) * sizeof(float4) + 64;
+    const size_t smem = ((size_t)KD * K * K * (DS_CCH / 4) + ds_nbuf(KD, K, DS_TH, DS_TW) * (size_t)PH * PW * (DS_CCH / 4)) * sizeof(float4) + 64;
     auto kern = dwconv_smem_kernel<KD, K, LD, L, DS_TD, DS_TH, DS_TW, DS_R, VW>;
     static SmemOptIn optin;   // per template instance, per device
     DLKA_TRY(optin.ensure(kern, smem));
