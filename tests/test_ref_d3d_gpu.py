@@ -87,3 +87,28 @@ def test_backward_matches_compiled_reference(d3d, oracle, C, Co, dims, scale):
         got = dl.ops.deform_conv3d_backward(x.to(DEV), w.to(DEV), b.to(DEV), off.to(DEV), gout.to(DEV), 3, 1, 1, 1, 1, 1, 64, math=math)
         for n, g_, r in zip(names, got, ref):
             assert rel_err(g_, r) < 1e-3, f"{math} {n}"
+
+
+@pytest.mark.parametrize("C,Co,g,dg,dims,scale", [(16, 8, 2, 1, (5, 6, 7), 0.7), (16, 16, 1, 2, (6, 5, 7), 1.5), (32, 24, 2, 4, (4, 6, 5), 0.7)])
+def test_backward_groups_match_compiled_reference(d3d, oracle, C, Co, g, dg, dims, scale):
+    """group / deformable_group != 1 in the backward (deform_conv_cuda.cu:160-166, 204-270), against the reference's own compiled
+    D3D.deform_conv_backward; same equal-pad argument as above.  The grouped autograd oracle is pinned on the way."""
+    import deformablelka_b200 as dl
+    torch.manual_seed(3)
+    B = 2
+    D, H, W = dims
+    x = torch.randn(B, C, D, H, W); w = torch.randn(Co, C // g, 3, 3, 3) * 0.2; b = torch.randn(Co)
+    off = torch.randn(B, dg * 81, D, H, W) * scale
+    gout = torch.randn(B, Co, D, H, W)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = d3d.deform_conv_backward(x.to(DEV), w.to(DEV), b.to(DEV), off.to(DEV), gout.to(DEV), 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, g, dg, 64)
+    names = ("grad_input", "grad_offset", "grad_weight", "grad_bias")
+    xo, wo, bo, oo = (t.clone().requires_grad_() for t in (x, w, b, off))
+    oracle.deform_conv3d_autograd(xo, oo, wo, bo, (1, 1, 1), (1, 1, 1), (1, 1, 1), g, dg).backward(gout)
+    for n, o_, r in zip(names, (xo.grad, oo.grad, wo.grad, bo.grad), ref):
+        assert rel_err(o_, r) < 2e-5, "oracle " + n
+    for math in ("fp32", "bf16x3"):
+        got = dl.ops.deform_conv3d_backward(x.to(DEV), w.to(DEV), b.to(DEV), off.to(DEV), gout.to(DEV), 3, 1, 1, 1, g, dg, 64, math=math)
+        for n, g_, r in zip(names, got, ref):
+            assert got[0].shape == ref[0].shape
+            assert rel_err(g_, r) < 1e-3, f"{math} {n}"
