@@ -289,3 +289,12 @@ def test_block2d_backward_on_gpu_vs_oracle(oracle):
     for (n, p), (_, po) in zip(m.named_parameters(), om.named_parameters()):
         assert p.grad is not None, n
         assert rel_err(p.grad, po.grad) < 2e-3, n
+
+
+def test_graphed_call_refuses_cpu_tensors():
+    """deformablelka_b200.graphs.GraphedCall captures a CUDA graph: CPU arguments fail loudly, like every other entry."""
+    import deformablelka_b200 as dl
+    with pytest.raises(RuntimeError, match="CPU"):
+        dl.GraphedCall(lambda t: t, torch.zeros(2))
+    with pytest.raises(RuntimeError, match="CPU"):
+        dl.GraphedCall(lambda: None)
