@@ -36,14 +36,8 @@ namespace {
 #ifndef DLKA_DS7_VW
 #define DLKA_DS7_VW 2
 #endif
-#ifndef DLKA_DS_SPLITBAR
-#define DLKA_DS_SPLITBAR 1
-#endif
-#ifndef DLKA_DS_CCH
-#define DLKA_DS_CCH 32
-#endif
-constexpr int DS_CCH = DLKA_DS_CCH;                            // channels per CTA (32, or 16: half the shared memory, two CTAs per SM)
-static_assert(DS_CCH == 32 || DS_CCH == 16, "channels per CTA");
+constexpr int DS_CCH = 32;   // channels per CTA = one 128-byte line per voxel (16 per CTA, two CTAs per SM, measured slower: 8 lanes per
+                             // voxel break the conflict-free LDS.64 pattern, 4.05 / 1.76 ms)
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid)
 {
@@ -68,15 +62,8 @@ template <> struct DsVec<2> {
     static __device__ __forceinline__ void fma(T &a, const T &w, const T &x) { fma2v(a, w, x); }
 };
 
-// plane buffers per CTA: two; -DDLKA_DS_NBUF3 takes three when they fit beside the weights (measured no better: 3.14 vs 3.09 ms)
-__host__ __device__ constexpr int ds_nbuf(int KD, int K, int TH, int TW)
-{
-#if DLKA_DS_SPLITBAR && DLKA_DS_NBUF3
-    return ((size_t)3 * (TH + K - 1) * (TW + K - 1) * (DS_CCH / 4) + (size_t)KD * K * K * (DS_CCH / 4)) * 16 + 64 <= (size_t)227 * 1024 - 1024 ? 3 : 2;
-#else
-    return 2;
-#endif
-}
+// plane buffers per CTA (a third buffer fits for the 11 x 22 tile and was measured: no better, 3.14 vs 3.09 ms)
+__host__ __device__ constexpr int ds_nbuf(int, int, int, int) { return 2; }
 
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -153,26 +140,14 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
             for (int r = 0; r < DS_R; ++r) acc[t][r] = bv;
     }
 
-#if DLKA_DS_SPLITBAR
     if (tid == 0)
         for (int i = 0; i < NBUF && i < nplanes; ++i) load_plane(i, i);
-#else
-    if (tid == 0) load_plane(0, 0);
-#endif
     cp_async_wait<0>();
     __syncthreads();   // weights landed
 #pragma unroll 1
     for (int s = 0; s < nplanes; ++s) {
-#if !DLKA_DS_SPLITBAR
-        if (tid == 0 && s + 1 < nplanes) load_plane(s + 1, (s + 1) & 1);   // that buffer was released by the barrier below
-#endif
-#if DLKA_DS_SPLITBAR
         const int buf = s % NBUF;
         const uint32_t bph = (uint32_t)(s / NBUF) & 1u;
-#else
-        const int buf = s & 1;
-        const uint32_t bph = (uint32_t)(s >> 1) & 1u;
-#endif
         ptx::mbar_wait(bar0 + 8u * buf, bph);
         const vec *pl = reinterpret_cast<const vec *>(sP + buf * PLANE_F4);
         // plane s contributes to output t with depth tap i = s - t
@@ -195,7 +170,6 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
                 }
             }
         }
-#if DLKA_DS_SPLITBAR
         // split hand-off: only the warp that refills buffer `buf` with plane s + NBUF waits until every warp has finished reading
         // plane s (named barrier 1 + buf: bar.sync by warp 0, bar.arrive by the others, who run on into the planes already
         // resident).  A warp can arrive for plane s + NBUF on the same barrier only after that plane's TMA, which follows this
@@ -209,26 +183,21 @@ __global__ void __launch_bounds__((DS_CCH / VW) * (DS_TW / DS_R) * DS_TH, 1)
                 asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(DS_THREADS) : "memory");
             }
         }
-#else
-        // everyone is done reading plane buffer (s & 1): it is refilled at the top of the next iteration.  (Per-warp
-        // "empty" mbarriers instead of this CTA barrier measured slower: 3.77 vs 3.66 ms and 1.52 vs 1.28 ms.)
-        __syncthreads();
-#endif
     }
 
-    // store: real coordinates of this thread's outputs
+    // store: real coordinates of this thread's outputs.  One 64-bit address per (thread, t); the R outputs along w are L voxels apart
     const int hr = ph_ + L * (zh0 + hl);
     if (hr < H) {
+        const int w0r = pw_ + L * (zw0 + wr * DS_R);           // real w of output r = 0
+        const i64 wstep = (i64)L * yldv;
 #pragma unroll
         for (int t = 0; t < DS_TD; ++t) {
             const int dr = pd_ + LD * (zd0 + t);
             if (dr >= D) continue;
+            float *yp = y + (i64)(c0 >> 5) * ych + ((((i64)b * D + dr) * H + hr) * W + w0r) * yldv + (c0 & 31) + q * VW;
 #pragma unroll
-            for (int r = 0; r < DS_R; ++r) {
-                const int wrr = pw_ + L * (zw0 + wr * DS_R + r);
-                if (wrr < W)
-                    *reinterpret_cast<vec *>(y + (i64)(c0 >> 5) * ych + ((((i64)b * D + dr) * H + hr) * W + wrr) * yldv + (c0 & 31) + q * VW) = acc[t][r];
-            }
+            for (int r = 0; r < DS_R; ++r)
+                if (w0r + L * r < W) *reinterpret_cast<vec *>(yp + r * wstep) = acc[t][r];
         }
     }
 }

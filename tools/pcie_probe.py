@@ -14,8 +14,8 @@ dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 node = dl.ops.bind_host_thread(dev)
 n = 2 * 64 * 128 * 128 * 96
-hx = dl.ops.pinned_empty((n,), torch.float32, dev)
-hy = dl.ops.pinned_empty((n,), torch.float32, dev)
+hx = dl.ops.pinned_empty((n,), dev)
+hy = dl.ops.pinned_empty((n,), dev)
 hx.zero_(); hy.zero_()
 dx = torch.empty(n, device=dev); dy = torch.zeros(n, device=dev)
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
