@@ -16,6 +16,8 @@ from __future__ import annotations
 
 import torch
 
+from ._lib import Workspace
+
 
 class GraphedCall:
     def __init__(self, fn, *example_args, warmup: int = 3, **kwargs):
@@ -38,9 +40,15 @@ class GraphedCall:
                 self.fn(*self.static_args, **self.kwargs)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # the library's scratch buffer is cached per (device, stream): the warm-up stream's copy is not needed again ...
+        Workspace._bufs.pop((dev.index if dev.index is not None else torch.cuda.current_device(), side.cuda_stream), None)
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.static_out = self.fn(*self.static_args, **self.kwargs)
+            key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
+        # ... and the one allocated during capture (from the graph's private pool) is what every replay writes to: this object keeps
+        # it alive, and the cache forgets it so that an unrelated call on a recycled stream cannot regrow / replace it
+        self._workspace = Workspace._bufs.pop(key, None)
         return self
 
     def __call__(self, *args):
