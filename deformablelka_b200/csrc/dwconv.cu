@@ -163,6 +163,10 @@ __global__ void __launch_bounds__(256) deform_dwconv_cl_kernel(const float *__re
     }
 }
 
+#ifndef DLKA_DW2D_UNROLL
+#define DLKA_DW2D_UNROLL 7
+#endif
+constexpr int DW2D_UNROLL = DLKA_DW2D_UNROLL;   // taps in flight per thread, 4 corner loads each (2 -> 7: 560 -> 512 us at 24x96x56x56)
 // 2D depthwise deformable conv with SHARED sampling parameters: in the kernel above every thread of a pixel (C/4 of them) re-derives
 // the same sampling position, validity and bilinear weights for every tap -- more instructions than the gather and the blend
 // themselves.  Here a block owns PB consecutive pixels: phase 1 computes one 32-byte record per (pixel, offset group, tap)
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(256) deform_dwconv2d_shared_kernel(const float
             const float *img = x + (i64)b * g.H * g.W * C + c;
             const int r0 = (p * dg + c / cpg) * K;
             float4 acc = bias ? ldg4(bias + c) : f4zero();
-#pragma unroll 2
+#pragma unroll DW2D_UNROLL
             for (int tap = 0; tap < K; ++tap) {
                 const int4 o = sO[r0 + tap];
                 const float4 w = sW[r0 + tap];
